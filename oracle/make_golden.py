@@ -1,0 +1,113 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden
+
+Every array below is an output of the reference's own modules imported from
+/root/reference (see oracle/refshim.py); the weights are the reference's own
+random init (``torch.manual_seed``), stored so the fixtures travel to the GPU box.
+Configs are reduced (nf=16, 3 levels, F=64) so that the fixtures stay small; the
+full-size comparison against the live reference is tests/test_oracle_vs_reference.py.
+TEST INFRASTRUCTURE – see oracle/__init__.py.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import refshim, sde as sde_mod
+from .arch import NetConfig, state_dict_manifest
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+SMALL = dict(nf=16, ch_mult=(1, 2, 2), image_size=64, num_res_blocks=2)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def golden_network(name, backbone, cfg: NetConfig, seed):
+    model = refshim.make_score_model(backbone=backbone, seed=seed, nf=cfg.nf, ch_mult=cfg.ch_mult,
+                                     image_size=cfg.image_size, attn_resolutions=cfg.attn_resolutions,
+                                     n_fft=126, hop_length=32)
+    sd = model.dnn.state_dict()
+    assert [k for k, _ in state_dict_manifest(cfg)] == list(sd.keys())
+    g = torch.Generator().manual_seed(seed + 100)
+    B, F, T = 2, 64, 64
+    x = torch.complex(torch.randn(B, 1, F, T, generator=g), torch.randn(B, 1, F, T, generator=g)) * 0.3
+    y = torch.complex(torch.randn(B, 1, F, T, generator=g), torch.randn(B, 1, F, T, generator=g)) * 0.3
+    t = torch.tensor([0.83, 0.11])
+    with torch.no_grad():
+        dnn_out = model.dnn(torch.cat([x, y], dim=1), t)
+        score = model(x, y, t)
+
+    # PC sampler with injected noise.  'euler_maruyama' is not reachable through pc_sampler in the
+    # reference: predictors.py:49 forwards `stepsize` into OUVESDE.sde() -> TypeError.
+    samples = {}
+    N = 3
+    for pred, corr in [("reverse_diffusion", "ald"), ("reverse_diffusion", "langevin"), ("none", "ald"),
+                       ("reverse_diffusion", "none")]:
+        nd = sde_mod.n_noise_draws(N, pred, corr, 1)
+        draws = sde_mod.make_noise((B, 1, F, T), nd, seed=7)
+        with refshim.injected_noise(draws):
+            smp, nfe = model.get_pc_sampler(pred, corr, y, N=N, corrector_steps=1, snr=0.5)()
+        samples[f"pc_{pred}_{corr}"] = _np(smp)
+        samples[f"nfe_{pred}_{corr}"] = np.int64(nfe)
+
+    # full enhancement chain (enhancement.py:75-96 sequence on CPU)
+    from sgmse.util.other import pad_spec
+    L = 2000
+    wav = 0.1 * torch.randn(B, L, generator=g)
+    outs, Ys = [], []
+    for b in range(B):
+        yb = wav[b:b + 1]
+        norm = yb.abs().max()
+        Y = torch.unsqueeze(model._forward_transform(model._stft(yb / norm)), 0)
+        Y = pad_spec(Y)
+        draws = [d[b:b + 1] for d in sde_mod.make_noise((B, 1, F, Y.shape[-1]), sde_mod.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=11)]
+        with refshim.injected_noise(draws):
+            smp, _ = model.get_pc_sampler("reverse_diffusion", "ald", Y, N=N, corrector_steps=1, snr=0.5)()
+        xh = model.to_audio(smp.squeeze(), L) * norm
+        outs.append(_np(xh)); Ys.append(_np(Y[0]))
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"),
+        **{"w/" + k: _np(v) for k, v in sd.items()},
+        x=_np(x), y=_np(y), t=_np(t), dnn_out=_np(dnn_out), score=_np(score),
+        wav=_np(wav), enh=np.stack(outs), Y=np.stack(Ys), **samples)
+    print(name, "params", sum(v.numel() for v in sd.values()))
+
+
+def golden_ops():
+    """Op-level outputs of the reference layer library (FIR resamplers, STFT chain)."""
+    refshim.import_reference()
+    from sgmse.backbones.ncsnpp_utils import up_or_down_sampling as uds
+    from sgmse.data_module import SpecsDataModule
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 8, 12, generator=g)
+    dm = SpecsDataModule(base_dir="/nonexistent", n_fft=126, hop_length=32)
+    dm48 = SpecsDataModule(base_dir="/nonexistent", n_fft=1534, hop_length=384, spec_factor=0.065,
+                           spec_abs_exponent=0.667)
+    wav = 0.1 * torch.randn(2, 2000, generator=g)
+    wav48 = 0.1 * torch.randn(1, 6000, generator=g)
+    S = dm.stft(wav)
+    S48 = dm48.stft(wav48)
+    np.savez_compressed(
+        os.path.join(OUT, "ops.npz"),
+        fir_x=_np(x), fir_down=_np(uds.downsample_2d(x, (1, 3, 3, 1), factor=2)),
+        fir_up=_np(uds.upsample_2d(x, (1, 3, 3, 1), factor=2)),
+        wav=_np(wav), stft=_np(S), spec_fwd=_np(dm.spec_fwd(S)), spec_back=_np(dm.spec_back(dm.spec_fwd(S))),
+        istft=_np(dm.istft(S, 2000)),
+        wav48=_np(wav48), stft48=_np(S48), spec_fwd48=_np(dm48.spec_fwd(S48)), istft48=_np(dm48.istft(S48, 6000)))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    golden_ops()
+    golden_network("ncsnpp_small", "ncsnpp", NetConfig.ncsnpp(attn_resolutions=(16,), **SMALL), seed=1)
+    golden_network("ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
+
+
+if __name__ == "__main__":
+    main()
