@@ -1,0 +1,149 @@
+/* sgmse_b200 — C-ABI of the B200-native reverse-SDE enhancement engine.
+ *
+ * Drop-in boundary for the hot path of sp-uhh/sgmse.  Plain C: opaque handle, raw
+ * device/host pointers and sizes, int return codes (0 = ok, non-zero = error; the message is available
+ * from sgmse_b200_last_error()).  Nothing here throws and no torch type crosses the boundary; the Python
+ * shim (sgmse_b200/_lib.py) binds these with ctypes and forwards `tensor.data_ptr()` and the current
+ * CUDA stream.
+ *
+ * The only native/FFI boundary the reference itself has is the pybind11 module `upfirdn2d`
+ * (/root/reference/sgmse/backbones/ncsnpp_utils/op/upfirdn2d.cpp:12-23, upfirdn2d_kernel.cu:209-369); the
+ * engine replaces that op together with the Python call stack above it:
+ *
+ *   entry point                      replaces (reference file:line)
+ *   ------------------------------   ---------------------------------------------------------------
+ *   sgmse_b200_dnn_forward           NCSNpp.forward / NCSNpp_48k.forward   sgmse/backbones/ncsnpp.py:256-419,
+ *                                    ncsnpp_48k.py:259-424 (incl. upfirdn2d, op/upfirdn2d.py:148-159)
+ *   sgmse_b200_score                 ScoreModel.forward (legacy branch)    sgmse/model.py:307-310
+ *   sgmse_b200_pc_sample             sampling.get_pc_sampler()/pc_sampler  sgmse/sampling/__init__.py:26-70,
+ *                                    predictors.py:41-76, correctors.py:37-94, sdes.py:72-137,188-229,
+ *                                    ScoreModel.get_pc_sampler (minibatch loop) sgmse/model.py:348-368
+ *   sgmse_b200_analysis              _stft + _forward_transform + pad_spec sgmse/data_module.py:162-175,212-214,
+ *                                    sgmse/util/other.py:76-90, model.py:435-438
+ *   sgmse_b200_synthesis             to_audio (spec_back + istft) + renorm sgmse/data_module.py:177-188,216-218,
+ *                                    model.py:411-412,457-458
+ *   sgmse_b200_enhance               ScoreModel.enhance                    sgmse/model.py:426-465
+ *                                    (= enhancement.py:75-96 per file)
+ *   sgmse_b200_load_weights          model.dnn.state_dict() after eval()   sgmse/model.py:111-125 (EMA swap)
+ *
+ * Threading: one engine per (device, caller); an engine is not thread-safe.  All work is enqueued on the
+ * `stream` argument (a cudaStream_t passed as void*; NULL = legacy default stream).
+ * Ownership: the caller owns every buffer it passes; the engine owns weights, workspace, cuFFT plans and
+ * CUDA graph executables.
+ */
+#ifndef SGMSE_B200_H
+#define SGMSE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgmse_b200_engine sgmse_b200_engine;
+
+enum { SGMSE_B200_BACKBONE_NCSNPP = 0, SGMSE_B200_BACKBONE_NCSNPP_48K = 1 };
+/* arithmetic mode: 0 = fp32 activations, CUDA-core convolutions (validation);
+ *                  1 = fp16 activations, CUDA-core convolutions (debug);
+ *                  2 = fp16 activations, tcgen05 tensor-core convolutions (product path) */
+enum { SGMSE_B200_MODE_FP32 = 0, SGMSE_B200_MODE_FP16_DIRECT = 1, SGMSE_B200_MODE_FP16_TC = 2 };
+enum { SGMSE_B200_PRED_REVERSE_DIFFUSION = 0, SGMSE_B200_PRED_EULER_MARUYAMA = 1, SGMSE_B200_PRED_NONE = 2 };
+enum { SGMSE_B200_CORR_ALD = 0, SGMSE_B200_CORR_LANGEVIN = 1, SGMSE_B200_CORR_NONE = 2 };
+enum { SGMSE_B200_PAD_ZERO = 0, SGMSE_B200_PAD_REFLECTION = 1 };
+
+typedef struct sgmse_b200_config {
+  /* backbone (kwargs of NCSNpp.__init__, ncsnpp.py:50-74) */
+  int backbone;
+  int nf;
+  int num_levels;            /* len(ch_mult) */
+  int ch_mult[8];
+  int num_res_blocks;
+  int num_attn_resolutions;
+  int attn_resolutions[8];
+  int image_size;            /* 256 */
+  int progressive_output_skip;   /* progressive == 'output_skip' (else 'none') */
+  int progressive_input_skip;    /* progressive_input == 'input_skip' (else 'none') */
+  int scale_by_sigma;
+  /* OUVESDE (sdes.py:148-166) + ScoreModel.t_eps (model.py:29) */
+  float theta, sigma_min, sigma_max, t_eps;
+  /* SpecsDataModule (data_module.py:121-147) */
+  int n_fft, hop_length, sqrt_window;
+  float spec_factor, spec_abs_exponent;
+  int sample_rate;
+  /* engine */
+  int mode;                  /* SGMSE_B200_MODE_* */
+  int max_batch;             /* utterances processed together (micro-batch); larger batches are looped */
+  int use_graphs;            /* capture the N-step sampler loop as one CUDA graph */
+} sgmse_b200_config;
+
+typedef struct sgmse_b200_sampler {
+  int N;                     /* reverse steps (30) */
+  int predictor;             /* SGMSE_B200_PRED_* */
+  int corrector;             /* SGMSE_B200_CORR_* */
+  int corrector_steps;       /* 1 */
+  float snr;                 /* 0.5 */
+  int denoise;               /* 1: return x_mean of the last predictor step */
+  int probability_flow;      /* 0 */
+  unsigned long long seed;   /* Philox seed (ignored with injected noise) */
+  int utt_offset;            /* global index of utterance 0 (noise is keyed by global utterance id) */
+  int pad_mode;              /* SGMSE_B200_PAD_* (enhance/analysis only) */
+} sgmse_b200_sampler;
+
+const char* sgmse_b200_last_error(void);
+const char* sgmse_b200_version(void);
+
+int sgmse_b200_create(const sgmse_b200_config* cfg, sgmse_b200_engine** out);
+void sgmse_b200_destroy(sgmse_b200_engine* e);
+
+/* Weight manifest = the backbone's state_dict() in order: (key, numel).  Host-only; works without a GPU. */
+int sgmse_b200_manifest_count(const sgmse_b200_engine* e);
+int sgmse_b200_manifest_entry(const sgmse_b200_engine* e, int i, char* name, int name_cap, long long* numel);
+long long sgmse_b200_weights_numel(const sgmse_b200_engine* e);
+/* blob: fp32, all state_dict() tensors flattened and concatenated in manifest order (host memory). */
+int sgmse_b200_load_weights(sgmse_b200_engine* e, const float* blob_host, long long numel);
+/* same blob, already resident on this device (e.g. after an NCCL broadcast from rank 0) */
+int sgmse_b200_load_weights_device(sgmse_b200_engine* e, const float* blob_dev, long long numel, void* stream);
+
+/* Backbone contract: x c64 [B,2,F,T], t f32 [B] -> out c64 [B,1,F,T]  (device pointers). */
+int sgmse_b200_dnn_forward(sgmse_b200_engine* e, const void* x, const float* t, void* out, int B, int F, int T,
+                           void* stream);
+/* score = -dnn(cat[x_t, y], t); x_t, y, out: c64 [B,1,F,T] */
+int sgmse_b200_score(sgmse_b200_engine* e, const void* x_t, const void* y, const float* t, void* out, int B, int F,
+                     int T, void* stream);
+/* PC sampler.  y, out: c64 [B,1,F,T] (device).  noise: NULL (in-kernel Philox keyed by seed / global utterance
+ * id / draw index) or device c64 [n_draws,B,1,F,T] consumed in the order prior, then per step the corrector
+ * draws and the predictor draw (the order torch.randn_like is called in the reference).  *nfe receives
+ * N * (corrector_steps + 1). */
+int sgmse_b200_pc_sample(sgmse_b200_engine* e, const void* y, int B, int F, int T, const sgmse_b200_sampler* s,
+                         const void* noise, void* out, int* nfe, void* stream);
+int sgmse_b200_noise_draws(const sgmse_b200_sampler* s);
+
+/* padded frame count for a waveform of L samples */
+int sgmse_b200_padded_frames(const sgmse_b200_engine* e, int L);
+/* wav f32 [B,L] (device) -> Y c64 [B,1,F,Tpad], norm f32 [B] (device) */
+int sgmse_b200_analysis(sgmse_b200_engine* e, const float* wav, int B, int L, int pad_mode, void* Y, float* norm,
+                        void* stream);
+/* X c64 [B,1,F,Tpad], norm f32 [B] -> wav f32 [B,L] (device) */
+int sgmse_b200_synthesis(sgmse_b200_engine* e, const void* X, const float* norm, int B, int Tpad, int L, float* wav,
+                         void* stream);
+/* One call: wav [B,L] -> enhanced wav [B,L].  host_buffers != 0: wav/out are host pointers (pinned memory
+ * recommended); the H2D / D2H copies are part of the call and it returns after the result is in `out`. */
+int sgmse_b200_enhance(sgmse_b200_engine* e, const float* wav, int B, int L, const sgmse_b200_sampler* s,
+                       const void* noise, float* out, int host_buffers, void* stream);
+
+/* Introspection / debugging */
+/* bytes of activation workspace one forward pass of (B, F, T) needs; host-only (no CUDA call); -1 on error */
+long long sgmse_b200_workspace_bytes(sgmse_b200_engine* e, int B, int F, int T);
+/* copy a recorded intermediate activation (see sgmse_b200_set_option "record_taps") as fp32 NCHW to host */
+int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, long long cap, int shape[4]);
+/* options: "record_taps" (0/1), "use_graphs" (0/1), "tc_mask" (bit i set = conv class i may use tcgen05),
+ * "time_convs" (0/1: bracket every convolution launch with CUDA events; disables graph replay) */
+int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value);
+/* counters: "kernel_launches" (since creation), "graph_launches", "workspace_bytes", "weights_bytes",
+ * "tc_convs_last_forward", "direct_convs_last_forward", "launches_last_forward",
+ * "timed_conv_tc_us" / "timed_conv_tc_mflop" / "timed_conv_tc_kbytes" / "timed_conv_tc_count" /
+ * "timed_conv_direct_us" (sums over the launches timed since "time_convs" was switched on) */
+long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGMSE_B200_H */

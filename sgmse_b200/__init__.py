@@ -1,0 +1,6 @@
+"""sgmse_b200 — B200-native (sm_100a) reverse-SDE enhancement engine behind sp-uhh/sgmse's
+``ScoreModel.enhance()`` / ``get_pc_sampler()``.  See DESIGN.md and include/sgmse_b200.h."""
+from .engine import Engine, EngineConfig  # noqa: F401
+from .api import install, uninstall, engine_from_score_model, config_from_score_model  # noqa: F401
+
+__all__ = ["Engine", "EngineConfig", "install", "uninstall", "engine_from_score_model", "config_from_score_model"]

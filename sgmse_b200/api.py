@@ -1,0 +1,168 @@
+"""Drop-in installation behind the reference's public API.
+
+``install(model)`` snapshots the configuration and (EMA-swapped) weights of a live
+``sgmse.model.ScoreModel`` and rebinds
+
+* ``model.get_pc_sampler(predictor_name, corrector_name, y, N=None, minibatch=None, **kw)``
+  (/root/reference/sgmse/model.py:348-368) -> callable returning ``(sample c64 [B,1,F,T], nfe)``
+  (with ``minibatch`` the second element is a list, model.py:359-367),
+* ``model.enhance(y, sampler_type, predictor, corrector, N, corrector_steps, snr, timeit, **kw)``
+  (model.py:426-465) -> ``np.ndarray [T]`` or ``(x_hat, nfe, rtf)``,
+* ``model.forward(x_t, y, t)`` (legacy branch, model.py:307-310),
+
+to the B200 engine.  ``sgmse/model.py`` itself is untouched; ``uninstall(model)`` restores the
+original bound methods.  The predictor / corrector names are the reference registry names
+(sampling/predictors.py:41,55,68; correctors.py:37,59,84) and unknown names raise the same
+``ValueError`` as ``Registry.get_by_name`` (util/registry.py:25-30).
+"""
+from __future__ import annotations
+
+import time
+import types
+from math import ceil
+from typing import Optional
+
+import torch
+
+from .engine import Engine, EngineConfig, PREDICTORS, CORRECTORS, _lookup
+
+
+def config_from_score_model(model, mode="fp16_tc", max_batch=8, use_graphs=True) -> EngineConfig:
+    """Read every hyper-parameter of the hot path from a live ScoreModel."""
+    dnn = model.dnn
+    backbone = getattr(model, "backbone", None) or type(dnn).__name__.lower()
+    if backbone not in ("ncsnpp", "ncsnpp_48k"):
+        raise NotImplementedError(f"sgmse_b200 accelerates the 'ncsnpp' and 'ncsnpp_48k' backbones, not '{backbone}'")
+    for attr, want in (("resblock_type", "biggan"), ("embedding_type", "fourier"), ("skip_rescale", True),
+                       ("conditional", True), ("centered", True)):
+        if getattr(dnn, attr, want) != want:
+            raise NotImplementedError(f"NCSN++ option {attr}={getattr(dnn, attr)!r} is outside the accelerated path")
+    nf = dnn.nf
+    # ch_mult is not kept as an attribute (ncsnpp.py:79): recover it from the block list
+    mods = list(dnn.all_modules)
+    i, ch_mult = 4, []
+    L = dnn.num_resolutions
+    for lvl in range(L):
+        seen = 0
+        while seen < dnn.num_res_blocks:
+            m = mods[i]
+            i += 1
+            if type(m).__name__ == "ResnetBlockBigGANpp":
+                if seen == 0:
+                    ch_mult.append(m.out_ch // nf)
+                seen += 1
+        while type(mods[i]).__name__ == "AttnBlockpp":
+            i += 1
+        if lvl != L - 1:
+            i += 1                                         # down-sampling resblock
+            if dnn.progressive_input == "input_skip":
+                i += 1                                     # Combine
+    dm = model.data_module
+    if getattr(dm, "transform_type", "exponent") != "exponent":
+        raise NotImplementedError("only transform_type='exponent' is accelerated")
+    hann = torch.hann_window(dm.n_fft, periodic=True)
+    window = "hann" if torch.allclose(dm.window.cpu().float(), hann, atol=1e-6) else "sqrthann"
+    sde = model.sde
+    if type(sde).__name__ != "OUVESDE":
+        raise NotImplementedError("only the OUVE SDE is accelerated")
+    return EngineConfig(
+        backbone=backbone, nf=nf, ch_mult=tuple(ch_mult), num_res_blocks=dnn.num_res_blocks,
+        attn_resolutions=tuple(dnn.attn_resolutions), image_size=dnn.all_resolutions[0],
+        progressive=dnn.progressive, progressive_input=dnn.progressive_input, scale_by_sigma=bool(dnn.scale_by_sigma),
+        theta=float(sde.theta), sigma_min=float(sde.sigma_min), sigma_max=float(sde.sigma_max), t_eps=float(model.t_eps),
+        n_fft=dm.n_fft, hop_length=dm.hop_length, window=window, spec_factor=float(dm.spec_factor),
+        spec_abs_exponent=float(dm.spec_abs_exponent), sr=int(getattr(model, "sr", 16000)),
+        mode=mode, max_batch=max_batch, use_graphs=use_graphs)
+
+
+def engine_from_score_model(model, load_weights=True, **kw) -> Engine:
+    """``model`` should be in ``eval()`` mode so that the EMA weights are the ones in ``model.dnn``
+    (model.py:111-122)."""
+    eng = Engine(config_from_score_model(model, **kw))
+    if load_weights:
+        eng.load_state_dict(model.dnn.state_dict())
+    return eng
+
+
+def make_pc_sampler(engine: Engine, default_N: int):
+    def get_pc_sampler(self, predictor_name, corrector_name, y, N=None, minibatch=None, **kwargs):
+        N = default_N if N is None else N
+        _lookup(PREDICTORS, predictor_name, "Predictor")
+        _lookup(CORRECTORS, corrector_name, "Corrector")
+        kw = dict(N=N, predictor=predictor_name, corrector=corrector_name,
+                  corrector_steps=kwargs.get("corrector_steps", 1), snr=kwargs.get("snr", 0.1),
+                  denoise=kwargs.get("denoise", True), probability_flow=kwargs.get("probability_flow", False),
+                  seed=kwargs.get("seed", int(torch.randint(0, 2 ** 62, (1,)).item())))
+        if "eps" in kwargs and abs(kwargs["eps"] - engine.cfg.t_eps) > 1e-12:
+            raise NotImplementedError("eps other than ScoreModel.t_eps is baked into the engine configuration")
+        noise = kwargs.get("noise", None)
+
+        if minibatch is None:
+            def pc_sampler():
+                with torch.no_grad():
+                    return engine.pc_sample(y, noise=noise, **kw)
+            return pc_sampler
+
+        M = y.shape[0]
+
+        def batched_sampling_fn():
+            samples, ns = [], []
+            for i in range(int(ceil(M / minibatch))):
+                sl = slice(i * minibatch, (i + 1) * minibatch)
+                nz = noise[:, sl] if noise is not None else None
+                smp, n = engine.pc_sample(y[sl], noise=nz, **{**kw, "utt_offset": i * minibatch})
+                samples.append(smp)
+                ns.append(n)
+            return torch.cat(samples, dim=0), ns
+        return batched_sampling_fn
+    return get_pc_sampler
+
+
+def make_enhance(engine: Engine):
+    def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="ald", N=30,
+                corrector_steps=1, snr=0.5, timeit=False, **kwargs):
+        """One-call speech enhancement of noisy speech `y` [1, T] (or [B, T])."""
+        if getattr(self.sde, "sampler_type", "pc") != "pc":
+            raise NotImplementedError("only the PC sampler is accelerated (sde.sampler_type must be 'pc')")
+        start = time.time()
+        yy = y if y.dim() == 2 else y[None]
+        x_hat = engine.enhance(yy.detach().cpu().float(), N=N, predictor=predictor, corrector=corrector,
+                               corrector_steps=corrector_steps, snr=snr,
+                               seed=kwargs.get("seed", int(torch.randint(0, 2 ** 62, (1,)).item())),
+                               pad_mode=kwargs.get("pad_mode", "zero_pad"))
+        x_hat = x_hat.squeeze().numpy()
+        end = time.time()
+        nfe = N * ((corrector_steps if corrector != "none" else 0) + 1)
+        if timeit:
+            rtf = (end - start) / (x_hat.shape[-1] / self.sr)
+            return x_hat, nfe, rtf
+        return x_hat
+    return enhance
+
+
+def install(model, engine: Optional[Engine] = None, **kw) -> Engine:
+    """Route ``model.get_pc_sampler`` / ``model.enhance`` / ``model.forward`` through the engine."""
+    if engine is None:
+        engine = engine_from_score_model(model, **kw)
+    model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "enhance", "forward")}
+    model._sgmse_b200_engine = engine
+    model.get_pc_sampler = types.MethodType(make_pc_sampler(engine, default_N=model.sde.N), model)
+    model.enhance = types.MethodType(make_enhance(engine), model)
+
+    def forward(self, x_t, y, t):
+        return engine.score(x_t, y, t)
+    model.forward = types.MethodType(forward, model)
+    return engine
+
+
+def uninstall(model):
+    saved = getattr(model, "_sgmse_b200_saved", None)
+    if saved is None:
+        return
+    for k, v in saved.items():
+        if v is None:
+            model.__dict__.pop(k, None)
+        else:
+            model.__dict__[k] = v
+    del model._sgmse_b200_saved
+    del model._sgmse_b200_engine

@@ -1,0 +1,1095 @@
+// Host side of the engine: architecture walk, weight packing, the network forward pass as a static
+// launch sequence over a bump-allocated workspace, the predictor-corrector loop (captured as one CUDA
+// graph), the cuFFT STFT/iSTFT front/back end, and the C-ABI of include/sgmse_b200.h.
+//
+// Reference call stack replaced: ScoreModel.enhance (model.py:426-465) -> get_pc_sampler
+// (sampling/__init__.py:26-70) -> NCSNpp.forward (backbones/ncsnpp.py:256-419).
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <tuple>
+
+using namespace sgmse;
+typedef sgmse_b200_engine Engine;
+
+namespace sgmse {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+const char* get_last_error() { return g_last_error.c_str(); }
+}  // namespace sgmse
+
+namespace {
+
+constexpr float INV_SQRT2 = 0.70710678118654752440f;
+
+int gn_groups(int c) { return std::min(c / 4, 32); }   // layerspp.py:219
+
+// ------------------------------------------------------------------------------------------------
+// architecture walk: mirrors NCSNpp.__init__ (ncsnpp.py:104-253) / NCSNpp_48k.__init__
+// ------------------------------------------------------------------------------------------------
+struct Walker {
+  Engine& e;
+  long long off = 0;
+  int midx = 0;
+  long long add(const std::string& name, long long numel) {
+    e.manifest.push_back(ParamRef{name, numel, off});
+    const long long o = off;
+    off += numel;
+    return o;
+  }
+  std::string mod(const char* leaf) const { return "all_modules." + std::to_string(midx) + "." + leaf; }
+
+  void resblock(int cin, int cout, bool up, bool down) {
+    Layer l{};
+    l.kind = LK_RES; l.idx = midx; l.cin = cin; l.cout = cout; l.up = up; l.down = down;
+    l.shortcut = (cin != cout) || up || down;                // layerspp.py:233
+    const int temb_dim = 4 * e.cfg.nf;
+    l.gn0_w = add(mod("GroupNorm_0.weight"), cin); l.gn0_b = add(mod("GroupNorm_0.bias"), cin);
+    l.conv0_w = add(mod("Conv_0.weight"), (long long)cout * cin * 9); l.conv0_b = add(mod("Conv_0.bias"), cout);
+    l.dense_w = add(mod("Dense_0.weight"), (long long)cout * temb_dim); l.dense_b = add(mod("Dense_0.bias"), cout);
+    l.gn1_w = add(mod("GroupNorm_1.weight"), cout); l.gn1_b = add(mod("GroupNorm_1.bias"), cout);
+    l.conv1_w = add(mod("Conv_1.weight"), (long long)cout * cout * 9); l.conv1_b = add(mod("Conv_1.bias"), cout);
+    if (l.shortcut) { l.conv2_w = add(mod("Conv_2.weight"), (long long)cout * cin); l.conv2_b = add(mod("Conv_2.bias"), cout); }
+    l.temb_off = e.total_temb_c;
+    e.total_temb_c += cout;
+    e.layers.push_back(l);
+    ++midx;
+  }
+  void attn(int c) {
+    Layer l{};
+    l.kind = LK_ATTN; l.idx = midx; l.cin = l.cout = c;
+    l.gn0_w = add(mod("GroupNorm_0.weight"), c); l.gn0_b = add(mod("GroupNorm_0.bias"), c);
+    for (int k = 0; k < 4; ++k) {
+      const std::string n = "NIN_" + std::to_string(k);
+      l.nin_w[k] = add(mod((n + ".W").c_str()), (long long)c * c);
+      l.nin_b[k] = add(mod((n + ".b").c_str()), c);
+    }
+    e.layers.push_back(l);
+    ++midx;
+  }
+  void combine(int c) {
+    Layer l{};
+    l.kind = LK_COMBINE; l.idx = midx; l.cin = 4; l.cout = c;
+    l.conv0_w = add(mod("Conv_0.weight"), (long long)c * 4); l.conv0_b = add(mod("Conv_0.bias"), c);
+    e.layers.push_back(l);
+    ++midx;
+  }
+  void outconv(int c) {
+    Layer l{};
+    l.kind = LK_OUTCONV; l.idx = midx; l.cin = c; l.cout = 4;
+    l.gn0_w = add(mod("weight"), c); l.gn0_b = add(mod("bias"), c);
+    ++midx;
+    l.conv0_w = add(mod("weight"), (long long)4 * c * 9); l.conv0_b = add(mod("bias"), 4);
+    ++midx;
+    e.layers.push_back(l);
+  }
+};
+
+void build_network(Engine& e) {
+  const sgmse_b200_config& c = e.cfg;
+  SG_CHECK(c.nf > 0 && c.nf % 8 == 0, "nf=%d must be a positive multiple of 8", c.nf);
+  SG_CHECK(c.num_levels >= 1 && c.num_levels <= 8, "num_levels=%d out of range", c.num_levels);
+  SG_CHECK(c.num_res_blocks >= 1, "num_res_blocks must be >= 1");
+  SG_CHECK(c.backbone == SGMSE_B200_BACKBONE_NCSNPP || c.backbone == SGMSE_B200_BACKBONE_NCSNPP_48K, "unknown backbone %d", c.backbone);
+  Walker w{e};
+  const int nf = c.nf, L = c.num_levels, temb_dim = 4 * nf;
+  e.outl_w = w.add("output_layer.weight", 8);          // assigned before all_modules (ncsnpp.py:104)
+  e.outl_b = w.add("output_layer.bias", 2);
+  e.gfp_w = w.add(w.mod("W"), nf); ++w.midx;
+  e.lin1_w = w.add(w.mod("weight"), (long long)temb_dim * 2 * nf); e.lin1_b = w.add(w.mod("bias"), temb_dim); ++w.midx;
+  e.lin2_w = w.add(w.mod("weight"), (long long)temb_dim * temb_dim); e.lin2_b = w.add(w.mod("bias"), temb_dim); ++w.midx;
+  e.inconv_w = w.add(w.mod("weight"), (long long)nf * 4 * 9); e.inconv_b = w.add(w.mod("bias"), nf); ++w.midx;
+
+  auto has_attn = [&](int res) {
+    for (int i = 0; i < c.num_attn_resolutions; ++i) if (c.attn_resolutions[i] == res) return true;
+    return false;
+  };
+  std::vector<int> hs_c{nf};
+  int in_ch = nf;
+  for (int lvl = 0; lvl < L; ++lvl) {
+    const int res = c.image_size >> lvl;
+    for (int b = 0; b < c.num_res_blocks; ++b) {
+      const int out_ch = nf * c.ch_mult[lvl];
+      w.resblock(in_ch, out_ch, false, false);
+      in_ch = out_ch;
+      if (has_attn(res)) w.attn(in_ch);
+      hs_c.push_back(in_ch);
+    }
+    if (lvl != L - 1) {
+      w.resblock(in_ch, in_ch, false, true);
+      if (c.progressive_input_skip) w.combine(in_ch);
+      hs_c.push_back(in_ch);
+    }
+  }
+  in_ch = hs_c.back();
+  w.resblock(in_ch, in_ch, false, false);
+  w.attn(in_ch);
+  w.resblock(in_ch, in_ch, false, false);
+  for (int lvl = L - 1; lvl >= 0; --lvl) {
+    const int res = c.image_size >> lvl;
+    for (int b = 0; b < c.num_res_blocks + 1; ++b) {
+      const int out_ch = nf * c.ch_mult[lvl];
+      w.resblock(in_ch + hs_c.back(), out_ch, false, false);
+      hs_c.pop_back();
+      in_ch = out_ch;
+    }
+    if (has_attn(res)) w.attn(in_ch);
+    if (c.progressive_output_skip) w.outconv(in_ch);
+    if (lvl != 0) w.resblock(in_ch, in_ch, true, false);
+  }
+  SG_CHECK(hs_c.empty(), "internal: skip stack not empty");
+  if (!c.progressive_output_skip) w.outconv(in_ch);
+  e.weights_numel = w.off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing (host) + upload
+// ------------------------------------------------------------------------------------------------
+template <typename T> T from_float(float v);
+template <> float from_float<float>(float v) { return v; }
+template <> __half from_float<__half>(float v) { return __float2half_rn(v); }
+
+void* upload(Engine& e, const void* host, size_t bytes) {
+  void* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, bytes));
+  CUDA_OK(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+  e.dev_allocs.push_back(d);
+  e.weights_bytes += bytes;
+  return d;
+}
+
+// rows: list of (pointer to [Cout][Cin][kh*kw] fp32, Cin, taps)
+struct PackSrc { const float* w; int cin; int taps; };
+void pack_conv(Engine& e, const std::vector<PackSrc>& srcs, int cout, bool out_major_src, ConvW& cw) {
+  // out_major_src: true for Conv2d weights [Cout][Cin][taps]; false for NIN weights [Cin][Cout]
+  int ktot = 0;
+  for (auto& s : srcs) ktot += s.taps * s.cin;
+  cw.ktot = ktot; cw.cout = cout;
+  std::vector<float> kd((size_t)ktot * cout);   // [k][cout]
+  int kbase = 0;
+  for (auto& s : srcs) {
+    for (int tap = 0; tap < s.taps; ++tap)
+      for (int ci = 0; ci < s.cin; ++ci) {
+        float* dst = kd.data() + (size_t)(kbase + tap * s.cin + ci) * cout;
+        if (out_major_src)
+          for (int co = 0; co < cout; ++co) dst[co] = s.w[((size_t)co * s.cin + ci) * s.taps + tap];
+        else
+          for (int co = 0; co < cout; ++co) dst[co] = s.w[(size_t)ci * cout + co];
+      }
+    kbase += s.taps * s.cin;
+  }
+  const bool f16 = e.cfg.mode != SGMSE_B200_MODE_FP32;
+  if (!f16) {
+    cw.w_direct = upload(e, kd.data(), kd.size() * 4);
+  } else {
+    std::vector<__half> hd(kd.size());
+    for (size_t i = 0; i < kd.size(); ++i) hd[i] = __float2half_rn(kd[i]);
+    cw.w_direct = upload(e, hd.data(), hd.size() * 2);
+    if (e.cfg.mode == SGMSE_B200_MODE_FP16_TC && cout % 64 == 0 && ktot % 64 == 0) {
+      std::vector<__half> ht((size_t)cout * ktot);
+      for (int k = 0; k < ktot; ++k)
+        for (int co = 0; co < cout; ++co) ht[(size_t)co * ktot + k] = hd[(size_t)k * cout + co];
+      cw.w_tc = (__half*)upload(e, ht.data(), ht.size() * 2);
+    }
+  }
+}
+
+void free_weights(Engine& e) {
+  for (void* p : e.dev_allocs) cudaFree(p);
+  e.dev_allocs.clear();
+  if (e.blob_dev) { cudaFree(e.blob_dev); e.blob_dev = nullptr; }
+  e.weights_bytes = 0;
+  e.loaded = false;
+}
+
+void load_weights(Engine& e, const float* blob) {
+  free_weights(e);
+  const sgmse_b200_config& c = e.cfg;
+  CUDA_OK(cudaMalloc(&e.blob_dev, (size_t)e.weights_numel * 4));
+  CUDA_OK(cudaMemcpy(e.blob_dev, blob, (size_t)e.weights_numel * 4, cudaMemcpyHostToDevice));
+  e.weights_bytes += (size_t)e.weights_numel * 4;
+  const int nf = c.nf, D = 4 * nf;
+  {  // input conv [nf][4][3][3] -> [36][nf]
+    std::vector<float> p((size_t)36 * nf);
+    for (int co = 0; co < nf; ++co)
+      for (int ci = 0; ci < 4; ++ci)
+        for (int tap = 0; tap < 9; ++tap) p[(size_t)(tap * 4 + ci) * nf + co] = blob[e.inconv_w + ((size_t)co * 4 + ci) * 9 + tap];
+    e.inconv_w_packed = (float*)upload(e, p.data(), p.size() * 4);
+  }
+  std::vector<float> dw((size_t)e.total_temb_c * D), db(e.total_temb_c);
+  for (Layer& l : e.layers) {
+    if (l.kind == LK_RES) {
+      pack_conv(e, {{blob + l.conv0_w, l.cin, 9}}, l.cout, true, l.c0);
+      std::vector<PackSrc> s1{{blob + l.conv1_w, l.cout, 9}};
+      if (l.shortcut) s1.push_back({blob + l.conv2_w, l.cin, 1});
+      pack_conv(e, s1, l.cout, true, l.c1);
+      std::vector<float> b1(blob + l.conv1_b, blob + l.conv1_b + l.cout);
+      if (l.shortcut) for (int i = 0; i < l.cout; ++i) b1[i] += blob[l.conv2_b + i];
+      l.c1.bias = (float*)upload(e, b1.data(), b1.size() * 4);
+      memcpy(dw.data() + (size_t)l.temb_off * D, blob + l.dense_w, (size_t)l.cout * D * 4);
+      for (int i = 0; i < l.cout; ++i) db[l.temb_off + i] = blob[l.dense_b + i] + blob[l.conv0_b + i];
+    } else if (l.kind == LK_ATTN) {
+      const int C = l.cin;
+      // q|k|v as one 1x1 conv with 3C outputs: NIN weights are [in][out] (layers.py:549)
+      std::vector<float> wq((size_t)C * 3 * C), bq(3 * C);
+      for (int j = 0; j < 3; ++j) {
+        for (int ci = 0; ci < C; ++ci)
+          for (int co = 0; co < C; ++co) wq[(size_t)ci * 3 * C + j * C + co] = blob[l.nin_w[j] + (size_t)ci * C + co];
+        for (int co = 0; co < C; ++co) bq[j * C + co] = blob[l.nin_b[j] + co];
+      }
+      pack_conv(e, {{wq.data(), C, 1}}, 3 * C, false, l.c0);
+      l.c0.bias = (float*)upload(e, bq.data(), bq.size() * 4);
+      pack_conv(e, {{blob + l.nin_w[3], C, 1}}, C, false, l.c1);
+      l.c1.bias = e.blob_dev + l.nin_b[3];
+    } else if (l.kind == LK_COMBINE) {
+      const int C = l.cout;
+      std::vector<float> p((size_t)4 * C);
+      for (int co = 0; co < C; ++co)
+        for (int ci = 0; ci < 4; ++ci) p[(size_t)ci * C + co] = blob[l.conv0_w + (size_t)co * 4 + ci];
+      l.small_w = (float*)upload(e, p.data(), p.size() * 4);
+      l.small_b = e.blob_dev + l.conv0_b;
+    } else {  // LK_OUTCONV: [4][C][3][3] -> [9*C][4]
+      const int C = l.cin;
+      std::vector<float> p((size_t)9 * C * 4);
+      for (int o = 0; o < 4; ++o)
+        for (int ci = 0; ci < C; ++ci)
+          for (int tap = 0; tap < 9; ++tap) p[((size_t)tap * C + ci) * 4 + o] = blob[l.conv0_w + ((size_t)o * C + ci) * 9 + tap];
+      l.small_w = (float*)upload(e, p.data(), p.size() * 4);
+      for (int o = 0; o < 4; ++o) l.out_bias_host[o] = blob[l.conv0_b + o];
+    }
+  }
+  e.dense_w_stacked = (float*)upload(e, dw.data(), dw.size() * 4);
+  e.dense_b_stacked = (float*)upload(e, db.data(), db.size() * 4);
+  for (int o = 0; o < 2; ++o) {
+    for (int i = 0; i < 4; ++i) e.out_layer.w[o][i] = blob[e.outl_w + o * 4 + i];
+    e.out_layer.b[o] = blob[e.outl_b + o];
+  }
+  e.out_layer.scale_after = c.backbone == SGMSE_B200_BACKBONE_NCSNPP_48K ? 1 : 0;
+  e.out_layer.scale_by_sigma = c.scale_by_sigma;
+  for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec);
+  e.graphs.clear();
+  e.loaded = true;
+}
+
+TembWeights temb_weights(const Engine& e) {
+  TembWeights w{};
+  w.gfp_w = e.blob_dev + e.gfp_w;
+  w.l1_w = e.blob_dev + e.lin1_w; w.l1_b = e.blob_dev + e.lin1_b;
+  w.l2_w = e.blob_dev + e.lin2_w; w.l2_b = e.blob_dev + e.lin2_b;
+  w.dense_w = e.dense_w_stacked; w.dense_b = e.dense_b_stacked;
+  w.nf = e.cfg.nf; w.totalC = e.total_temb_c;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward pass
+// ------------------------------------------------------------------------------------------------
+struct Fwd {
+  Engine& e;
+  cudaStream_t st;
+  const float* temb;     // table row(s) for this evaluation
+  int temb_stride;       // 0: one row for all samples; totalC: one row per sample
+  bool dry;
+  DType dt;
+
+  TensorDesc act(int N, int H, int W, int C, bool stats) {
+    TensorDesc t;
+    t.N = N; t.H = H; t.W = W; t.C = C; t.dt = dt;
+    t.p = e.arena.alloc(t.bytes());
+    if (stats) t.stats = (float*)e.arena.alloc(t.stats_capacity_floats() * 4);
+    return t;
+  }
+  float4* act4(int N, int H, int W) { return (float4*)e.arena.alloc((size_t)N * H * W * 16); }
+  void count(int n = 1) { e.kernel_launches += n; e.launches_this_forward += n; }
+  void tap(const std::string& name, const TensorDesc& t) { if (e.record_taps && !dry) e.taps[name] = t; }
+  void tap4(const std::string& name, const float4* p, int N, int H, int W) {
+    if (e.record_taps && !dry) e.taps4[name] = {p, {N, 4, H, W}};
+  }
+
+  void conv(const ConvArgs& a, TensorDesc& out, int cls) {
+    if (dry) return;
+    const bool want_tc = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && ((e.tc_mask >> cls) & 1);
+    const bool tc = want_tc && conv_tc_supported(a, out);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e.time_convs) {
+      CUDA_OK(cudaEventCreate(&ev0)); CUDA_OK(cudaEventCreate(&ev1));
+      CUDA_OK(cudaEventRecord(ev0, st));
+    }
+    if (tc) { launch_conv_tc(st, a, out, e.dbg_flag); ++e.tc_convs; }
+    else { launch_conv_direct(st, a, out); ++e.direct_convs; }
+    if (e.time_convs) {
+      CUDA_OK(cudaEventRecord(ev1, st));
+      const double flops = 2.0 * (double)out.N * out.H * out.W * out.C * a.ktot();
+      const double bytes = (double)out.bytes() + (a.residual ? (double)out.bytes() : 0.0) +
+                           [&] { double b = 0; for (int i = 0; i < a.nseg; ++i) b += (double)a.seg[i].src.bytes(); return b; }();
+      e.conv_events.push_back(ConvTiming{ev0, ev1, flops, bytes, tc});
+    }
+    count();
+  }
+
+  float2* gn(const TensorDesc& x0, const TensorDesc* x1, long long g_off, long long b_off) {
+    const int Ct = x0.C + (x1 ? x1->C : 0);
+    float2* ab = (float2*)e.arena.alloc((size_t)x0.N * Ct * 8);
+    if (!dry) { launch_gn_finalize(st, x0, x1, e.blob_dev + g_off, e.blob_dev + b_off, gn_groups(Ct), ab); count(); }
+    return ab;
+  }
+
+  TensorDesc resblock(const Layer& l, const TensorDesc& x0, const TensorDesc* x1) {
+    const int N = x0.N, Ct = x0.C + (x1 ? x1->C : 0);
+    SG_CHECK(Ct == l.cin, "resblock %d: expected %d input channels, got %d", l.idx, l.cin, Ct);
+    const Resample rs = l.up ? RS_UP : (l.down ? RS_DOWN : RS_NONE);
+    const int Ho = l.up ? x0.H * 2 : (l.down ? x0.H / 2 : x0.H);
+    const int Wo = l.up ? x0.W * 2 : (l.down ? x0.W / 2 : x0.W);
+    float2* ab0 = gn(x0, x1, l.gn0_w, l.gn0_b);
+    TensorDesc h0 = act(N, Ho, Wo, Ct, false);
+    TensorDesc xr;                                 // FIR-resampled raw input (up/down blocks)
+    if (rs != RS_NONE) {
+      SG_CHECK(!x1, "resampling resblock with concatenated input");
+      xr = act(N, Ho, Wo, Ct, false);
+      if (!dry) { launch_gn_apply(st, x0, nullptr, ab0, true, rs, h0, &xr); count(); }
+    } else if (!dry) {
+      launch_gn_apply(st, x0, x1, ab0, true, RS_NONE, h0, nullptr); count();
+    }
+    TensorDesc h1 = act(N, Ho, Wo, l.cout, true);
+    {
+      ConvArgs a;
+      a.nseg = 1; a.seg[0].src = h0; a.seg[0].taps = 9;
+      a.w_direct = l.c0.w_direct; a.w_tc = l.c0.w_tc;
+      a.temb = temb + l.temb_off; a.temb_stride = temb_stride;   // Conv_0.bias is folded into the table
+      conv(a, h1, 0);
+    }
+    float2* ab1 = gn(h1, nullptr, l.gn1_w, l.gn1_b);
+    TensorDesc h2 = act(N, Ho, Wo, l.cout, false);
+    if (!dry) { launch_gn_apply(st, h1, nullptr, ab1, true, RS_NONE, h2, nullptr); count(); }
+    TensorDesc out = act(N, Ho, Wo, l.cout, true);
+    {
+      ConvArgs a;
+      a.nseg = 1; a.seg[0].src = h2; a.seg[0].taps = 9;
+      if (l.shortcut) {
+        if (rs != RS_NONE) { a.seg[a.nseg].src = xr; a.seg[a.nseg++].taps = 1; }
+        else {
+          a.seg[a.nseg].src = x0; a.seg[a.nseg++].taps = 1;
+          if (x1) { a.seg[a.nseg].src = *x1; a.seg[a.nseg++].taps = 1; }
+        }
+      } else {
+        a.residual = &x0;
+      }
+      a.w_direct = l.c1.w_direct; a.w_tc = l.c1.w_tc; a.bias = l.c1.bias; a.scale = INV_SQRT2;
+      conv(a, out, 1);
+    }
+    tap("m" + std::to_string(l.idx), out);
+    return out;
+  }
+
+  TensorDesc attn(const Layer& l, const TensorDesc& x) {
+    const int C = l.cin;
+    SG_CHECK(x.C == C, "attention %d: channel mismatch", l.idx);
+    float2* ab = gn(x, nullptr, l.gn0_w, l.gn0_b);
+    TensorDesc hn = act(x.N, x.H, x.W, C, false);
+    if (!dry) { launch_gn_apply(st, x, nullptr, ab, false, RS_NONE, hn, nullptr); count(); }
+    TensorDesc qkv = act(x.N, x.H, x.W, 3 * C, false);
+    {
+      ConvArgs a;
+      a.nseg = 1; a.seg[0].src = hn; a.seg[0].taps = 1;
+      a.w_direct = l.c0.w_direct; a.w_tc = l.c0.w_tc; a.bias = l.c0.bias;
+      conv(a, qkv, 2);
+    }
+    TensorDesc av = act(x.N, x.H, x.W, C, false);
+    if (!dry) { launch_attention(st, qkv, av); count(); }
+    TensorDesc out = act(x.N, x.H, x.W, C, true);
+    {
+      ConvArgs a;
+      a.nseg = 1; a.seg[0].src = av; a.seg[0].taps = 1;
+      a.w_direct = l.c1.w_direct; a.w_tc = l.c1.w_tc; a.bias = l.c1.bias;
+      a.residual = &x; a.scale = INV_SQRT2;
+      conv(a, out, 3);
+    }
+    tap("m" + std::to_string(l.idx), out);
+    return out;
+  }
+
+  const float4* outconv(const Layer& l, const TensorDesc& h, const float4* addend) {
+    float2* ab = gn(h, nullptr, l.gn0_w, l.gn0_b);
+    TensorDesc a = act(h.N, h.H, h.W, h.C, false);
+    if (!dry) { launch_gn_apply(st, h, nullptr, ab, true, RS_NONE, a, nullptr); count(); }
+    float4* out = act4(h.N, h.H, h.W);
+    if (!dry) { launch_out_conv(st, a, l.small_w, l.out_bias_host, addend, out); count(); }
+    return out;
+  }
+
+  // returns the 4-channel tensor that feeds `/t` + output_layer
+  const float4* run(const float4* state, int B, int H, int W) {
+    const sgmse_b200_config& c = e.cfg;
+    const int L = c.num_levels;
+    SG_CHECK(H % (1 << (L - 1)) == 0 && W % (1 << (L - 1)) == 0, "F=%d, T=%d must be multiples of %d", H, W, 1 << (L - 1));
+    if (c.num_attn_resolutions > 0 && c.backbone == SGMSE_B200_BACKBONE_NCSNPP)
+      SG_CHECK(H == c.image_size, "ncsnpp places attention for F == image_size == %d (got F=%d), see ncsnpp.py:84,308", c.image_size, H);
+    e.arena.reset();
+    e.launches_this_forward = 0;
+    e.tc_convs = e.direct_convs = 0;
+    if (e.record_taps && !dry) { e.taps.clear(); e.taps4.clear(); }
+    size_t it = 0;
+    auto next = [&](LayerKind k) -> const Layer& {
+      SG_CHECK(it < e.layers.size() && e.layers[it].kind == k, "internal: layer sequence mismatch at %zu", it);
+      return e.layers[it++];
+    };
+    auto next_is = [&](LayerKind k) { return it < e.layers.size() && e.layers[it].kind == k; };
+
+    std::vector<TensorDesc> hs;
+    {
+      TensorDesc h0 = act(B, H, W, c.nf, true);
+      if (!dry) { launch_input_conv(st, state, B, H, W, e.inconv_w_packed, e.blob_dev + e.inconv_b, h0); count(); }
+      tap("in_conv", h0);
+      hs.push_back(h0);
+    }
+    const float4* pyr_in = state;
+    int ph = H, pw = W;
+    for (int lvl = 0; lvl < L; ++lvl) {
+      for (int b = 0; b < c.num_res_blocks; ++b) {
+        TensorDesc h = resblock(next(LK_RES), hs.back(), nullptr);
+        if (next_is(LK_ATTN)) h = attn(next(LK_ATTN), h);
+        hs.push_back(h);
+      }
+      if (lvl != L - 1) {
+        TensorDesc h = resblock(next(LK_RES), hs.back(), nullptr);
+        if (c.progressive_input_skip) {
+          const Layer& l = next(LK_COMBINE);
+          float4* pd = act4(B, ph / 2, pw / 2);
+          if (!dry) { launch_fir4(st, pyr_in, B, ph, pw, RS_DOWN, pd); count(); }
+          pyr_in = pd; ph /= 2; pw /= 2;
+          TensorDesc o = act(B, h.H, h.W, h.C, true);
+          if (!dry) { launch_combine(st, pyr_in, l.small_w, l.small_b, h, o); count(); }
+          tap("m" + std::to_string(l.idx), o);
+          h = o;
+        }
+        hs.push_back(h);
+      }
+    }
+    TensorDesc h = hs.back();
+    h = resblock(next(LK_RES), h, nullptr);
+    h = attn(next(LK_ATTN), h);
+    h = resblock(next(LK_RES), h, nullptr);
+
+    const float4* pyramid = nullptr;
+    int qh = 0, qw = 0;
+    for (int lvl = L - 1; lvl >= 0; --lvl) {
+      for (int b = 0; b < c.num_res_blocks + 1; ++b) {
+        TensorDesc skip = hs.back();
+        hs.pop_back();
+        h = resblock(next(LK_RES), h, &skip);
+      }
+      if (next_is(LK_ATTN)) h = attn(next(LK_ATTN), h);
+      if (c.progressive_output_skip) {
+        const Layer& l = next(LK_OUTCONV);
+        const float4* add = nullptr;
+        if (pyramid) {
+          float4* up = act4(B, qh * 2, qw * 2);
+          if (!dry) { launch_fir4(st, pyramid, B, qh, qw, RS_UP, up); count(); }
+          add = up;
+        }
+        pyramid = outconv(l, h, add);
+        qh = h.H; qw = h.W;
+        tap4("pyr" + std::to_string(lvl), pyramid, B, qh, qw);
+      }
+      if (lvl != 0) h = resblock(next(LK_RES), h, nullptr);
+    }
+    SG_CHECK(hs.empty(), "internal: skip stack not empty after the up path");
+    if (!c.progressive_output_skip) {
+      pyramid = outconv(next(LK_OUTCONV), h, nullptr);
+      tap4("pyr0", pyramid, B, h.H, h.W);
+    }
+    SG_CHECK(it == e.layers.size(), "internal: %zu of %zu layers consumed", it, e.layers.size());
+    return pyramid;
+  }
+};
+
+void clear_graphs(Engine& e) {
+  for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec);
+  e.graphs.clear();
+}
+
+// Workspace for one forward pass of (B, F, T).  The bump allocation is replayed identically by every
+// forward of the same shape, so buffer addresses (and with them captured graphs) stay valid as long as
+// the arena itself is not re-allocated.
+void ensure_arena(Engine& e, int B, int F, int T) {
+  const auto key = std::make_tuple(B, F, T);
+  auto it = e.arena_need.find(key);
+  if (it == e.arena_need.end()) {
+    Arena saved = e.arena;
+    e.arena = Arena{};
+    e.arena.dry = true;
+    Fwd f{e, nullptr, nullptr, 0, true, e.cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
+    f.run(nullptr, B, F, T);
+    const size_t need = e.arena.high + 4096;
+    e.arena = saved;
+    it = e.arena_need.emplace(key, need).first;
+  }
+  if (it->second > e.arena.cap) {
+    clear_graphs(e);
+    if (e.arena.base) { CUDA_OK(cudaDeviceSynchronize()); cudaFree(e.arena.base); e.arena.base = nullptr; e.arena.cap = 0; }
+    CUDA_OK(cudaMalloc((void**)&e.arena.base, it->second));
+    e.arena.cap = it->second;
+  }
+  e.arena.dry = false;
+}
+
+template <typename T>
+void ensure_buf(T*& p, size_t& cap_elems, size_t need_elems) {
+  if (need_elems <= cap_elems) return;
+  if (p) { CUDA_OK(cudaDeviceSynchronize()); cudaFree(p); p = nullptr; }
+  CUDA_OK(cudaMalloc((void**)&p, need_elems * sizeof(T)));
+  cap_elems = need_elems;
+}
+
+void ensure_persistent(Engine& e, size_t px, int rows) {
+  if (px > e.persist_px) {
+    if (e.state) { CUDA_OK(cudaDeviceSynchronize()); cudaFree(e.state); cudaFree(e.xmean); }
+    CUDA_OK(cudaMalloc((void**)&e.state, px * sizeof(float4)));
+    CUDA_OK(cudaMalloc((void**)&e.xmean, px * sizeof(float2)));
+    e.persist_px = px;
+    clear_graphs(e);
+  }
+  if (rows > e.persist_rows) {
+    if (e.temb_table) { CUDA_OK(cudaDeviceSynchronize()); cudaFree(e.temb_table); cudaFree(e.temb_scratch); cudaFree(e.t_dev); cudaFree(e.coef_dev); }
+    CUDA_OK(cudaMalloc((void**)&e.temb_table, (size_t)rows * e.total_temb_c * 4));
+    CUDA_OK(cudaMalloc((void**)&e.temb_scratch, (size_t)rows * 4 * e.cfg.nf * 4));
+    CUDA_OK(cudaMalloc((void**)&e.t_dev, (size_t)rows * 4));
+    CUDA_OK(cudaMalloc((void**)&e.coef_dev, (size_t)rows * 4 * sizeof(UpdateCoef)));
+    e.persist_rows = rows;
+    clear_graphs(e);
+  }
+  if (!e.rng_dev) {
+    CUDA_OK(cudaMalloc((void**)&e.rng_dev, sizeof(RngParams)));
+    CUDA_OK(cudaMalloc((void**)&e.lv_scratch, (size_t)std::max(e.cfg.max_batch, 1) * 64 * 2 * 4));
+    CUDA_OK(cudaMalloc((void**)&e.dbg_flag, 4));
+    CUDA_OK(cudaMemset(e.dbg_flag, 0, 4));
+  }
+}
+
+__global__ void extract_x_kernel(const float4* __restrict__ state, size_t total, float2* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) { const float4 s = state[i]; out[i] = make_float2(s.x, s.y); }
+}
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ src, int is_half, int C, int HW, size_t total, float* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into NCHW output
+  if (i >= total) return;
+  const int p = (int)(i % HW);
+  const int c = (int)((i / HW) % C);
+  const size_t n = i / ((size_t)HW * C);
+  const size_t s = (n * HW + p) * C + c;
+  dst[i] = is_half ? __half2float(((const __half*)src)[s]) : ((const float*)src)[s];
+}
+
+// ------------------------------------------------------------------------------------------------
+// network evaluation with per-sample times (backbone contract / score)
+// ------------------------------------------------------------------------------------------------
+void dnn_forward(Engine& e, const float2* x, const float2* y, const float* t, float2* out, int B, int F, int T,
+                 bool negate, cudaStream_t st) {
+  SG_CHECK(e.loaded, "weights not loaded");
+  const int mb = std::max(1, e.cfg.max_batch);
+  ensure_arena(e, std::min(B, mb), F, T);
+  ensure_persistent(e, (size_t)std::min(B, mb) * F * T, std::max(mb, 64));
+  const size_t px1 = (size_t)F * T;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int Bc = std::min(mb, B - b0);
+    launch_pack_state(st, x + b0 * px1, y + b0 * px1, Bc, F, T, e.state); ++e.kernel_launches;
+    launch_temb(st, temb_weights(e), t + b0, Bc, e.temb_scratch, e.temb_table); e.kernel_launches += 2;
+    Fwd f{e, st, e.temb_table, e.total_temb_c, false, e.cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
+    const float4* p = f.run(e.state, Bc, F, T);
+    launch_out_layer(st, p, Bc, F, T, e.out_layer, t + b0, out + b0 * px1, negate); ++e.kernel_launches;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// predictor-corrector sampler
+// ------------------------------------------------------------------------------------------------
+std::vector<float> linspace_f32(float start, float end, int steps) {
+  // torch.linspace (CPU, fp32): step = (end-start)/(steps-1); first half from start, second half from end
+  std::vector<float> v(steps);
+  if (steps == 1) { v[0] = start; return v; }
+  const float step = (end - start) / (float)(steps - 1);
+  const int half = steps / 2;
+  for (int i = 0; i < steps; ++i) v[i] = i < half ? start + step * (float)i : end - step * (float)(steps - 1 - i);
+  return v;
+}
+
+int noise_draws(const sgmse_b200_sampler& s) {
+  const int c = s.corrector != SGMSE_B200_CORR_NONE ? s.corrector_steps : 0;
+  const int p = s.predictor != SGMSE_B200_PRED_NONE ? 1 : 0;
+  return 1 + s.N * (c + p);
+}
+
+struct SamplerTables {
+  std::vector<float> ts;
+  std::vector<UpdateCoef> coef;    // one per update, in execution order (langevin entries filled on device)
+};
+
+SamplerTables make_tables(const Engine& e, const sgmse_b200_sampler& s) {
+  // sdes.py:188-219, predictors.py:41-65, correctors.py:69-81, sampling/__init__.py:56-62
+  SamplerTables tb;
+  const sgmse_b200_config& c = e.cfg;
+  tb.ts = linspace_f32(1.0f, c.t_eps, s.N);
+  const double th = c.theta, smin = c.sigma_min, smax = c.sigma_max, ls = log(smax / smin);
+  const double pf = s.probability_flow ? 0.5 : 1.0;
+  for (int i = 0; i < s.N; ++i) {
+    const double t = tb.ts[i];
+    const double std = sqrt(smin * smin * exp(-2 * th * t) * (exp(2 * (th + ls) * t) - 1) * ls / (th + ls));
+    const double g = smin * pow(smax / smin, t) * sqrt(2 * ls);
+    if (s.corrector != SGMSE_B200_CORR_NONE)
+      for (int k = 0; k < s.corrector_steps; ++k) {
+        const double eps = 2.0 * (s.snr * std) * (s.snr * std);
+        tb.coef.push_back(UpdateCoef{0.f, (float)eps, (float)sqrt(2 * eps)});
+      }
+    if (s.predictor == SGMSE_B200_PRED_REVERSE_DIFFUSION) {
+      const float dtf = i != s.N - 1 ? tb.ts[i] - tb.ts[i + 1] : tb.ts[s.N - 1];
+      const double dt = dtf, G = g * sqrt(dt);
+      tb.coef.push_back(UpdateCoef{(float)(-th * dt), (float)(G * G * pf), s.probability_flow ? 0.f : (float)G});
+    } else if (s.predictor == SGMSE_B200_PRED_EULER_MARUYAMA) {
+      // x + (theta (y-x) - g^2 score) * dt + g sqrt(-dt) z,  dt = -1/N   (predictors.py:46-52, as intended;
+      // the reference's call site forwards `stepsize` into OUVESDE.sde() and raises TypeError)
+      const double dt = -1.0 / s.N;
+      tb.coef.push_back(UpdateCoef{(float)(th * dt), (float)(-g * g * pf * dt), s.probability_flow ? 0.f : (float)(g * sqrt(-dt))});
+    }
+  }
+  return tb;
+}
+
+// One micro-batch.  y/out: [Bc][F*T] float2; noise: nullptr or base of [draws][Btot][F*T] with chunk offset applied.
+void sample_chunk(Engine& e, const float2* y, int Bc, int F, int T, const sgmse_b200_sampler& s, const float2* noise,
+                  size_t noise_draw_stride, float2* out, cudaStream_t st, bool inside_capture) {
+  const SamplerTables tb = make_tables(e, s);
+  const size_t px = (size_t)Bc * F * T;
+  const RngParams* rng = e.rng_dev;
+  auto nz = [&](int draw) { return noise ? noise + (size_t)draw * noise_draw_stride : nullptr; };
+  const sgmse_b200_config& c = e.cfg;
+  const double th = c.theta, smin = c.sigma_min, smax = c.sigma_max, ls = log(smax / smin);
+  const float std1 = (float)sqrt(smin * smin * exp(-2 * th) * (exp(2 * (th + ls)) - 1) * ls / (th + ls));
+
+  launch_pack_state(st, y, y, Bc, F, T, e.state); ++e.kernel_launches;
+  int draw = 0;
+  launch_prior(st, e.state, Bc, F, T, std1, nz(draw), rng, draw); ++e.kernel_launches;
+  ++draw;
+  int ci = 0;
+  bool have_mean = false;
+  Fwd f{e, st, nullptr, 0, false, e.cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
+  for (int i = 0; i < s.N; ++i) {
+    const float inv_t = 1.0f / tb.ts[i];
+    f.temb = e.temb_table + (size_t)i * e.total_temb_c;
+    if (s.corrector != SGMSE_B200_CORR_NONE)
+      for (int k = 0; k < s.corrector_steps; ++k) {
+        const float4* p = f.run(e.state, Bc, F, T);
+        if (s.corrector == SGMSE_B200_CORR_LANGEVIN) {
+          launch_langevin_coef(st, p, Bc, F, T, e.out_layer, inv_t, nz(draw), rng, draw, s.snr, e.lv_scratch, e.coef_dev + ci);
+          e.kernel_launches += 2;
+        }
+        launch_pc_update(st, e.state, p, Bc, F, T, e.out_layer, nullptr, inv_t, e.coef_dev + ci, nz(draw), rng, draw, nullptr);
+        ++e.kernel_launches; ++draw; ++ci;
+        have_mean = false;
+      }
+    if (s.predictor != SGMSE_B200_PRED_NONE) {
+      const float4* p = f.run(e.state, Bc, F, T);
+      const bool last = i == s.N - 1;
+      launch_pc_update(st, e.state, p, Bc, F, T, e.out_layer, nullptr, inv_t, e.coef_dev + ci, nz(draw), rng, draw,
+                       (last && s.denoise) ? e.xmean : nullptr);
+      ++e.kernel_launches; ++draw; ++ci;
+      have_mean = last && s.denoise;
+    }
+  }
+  if (have_mean) {
+    CUDA_OK(cudaMemcpyAsync(out, e.xmean, px * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+  } else {
+    // NonePredictor returns (x, x): x_mean == x  (predictors.py:75-76)
+    extract_x_kernel<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(e.state, px, out);
+    CUDA_OK(cudaGetLastError()); ++e.kernel_launches;
+  }
+  (void)inside_capture;
+}
+
+void prepare_tables(Engine& e, const sgmse_b200_sampler& s, cudaStream_t st) {
+  const SamplerTables tb = make_tables(e, s);
+  CUDA_OK(cudaMemcpyAsync(e.t_dev, tb.ts.data(), tb.ts.size() * 4, cudaMemcpyHostToDevice, st));
+  if (!tb.coef.empty())
+    CUDA_OK(cudaMemcpyAsync(e.coef_dev, tb.coef.data(), tb.coef.size() * sizeof(UpdateCoef), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));   // tb is a temporary; keep the host buffers alive until copied
+  launch_temb(st, temb_weights(e), e.t_dev, s.N, e.temb_scratch, e.temb_table); e.kernel_launches += 2;
+}
+
+void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200_sampler& s, const float2* noise,
+               float2* out, int* nfe, cudaStream_t st_in) {
+  SG_CHECK(e.loaded, "weights not loaded");
+  // stream capture is illegal on the legacy default stream: run on an engine-owned (blocking) stream instead
+  cudaStream_t st = st_in;
+  if (!st) {
+    if (!e.own_stream) CUDA_OK(cudaStreamCreate(&e.own_stream));
+    st = e.own_stream;
+  }
+  struct SyncOnExit { cudaStream_t s; bool on; ~SyncOnExit() { if (on) cudaStreamSynchronize(s); } } sync_guard{st, st_in == nullptr};
+  SG_CHECK(s.N >= 1 && s.corrector_steps >= 0, "bad sampler settings");
+  SG_CHECK(s.predictor >= 0 && s.predictor <= 2, "Predictor with id %d unknown.", s.predictor);
+  SG_CHECK(s.corrector >= 0 && s.corrector <= 2, "Corrector with id %d unknown.", s.corrector);
+  const int mb = std::max(1, e.cfg.max_batch);
+  const int csteps = s.corrector != SGMSE_B200_CORR_NONE ? s.corrector_steps : 0;
+  ensure_arena(e, std::min(B, mb), F, T);
+  ensure_persistent(e, (size_t)std::min(B, mb) * F * T, std::max({mb, 64, s.N * (csteps + 1) + 1}));
+  prepare_tables(e, s, st);
+  const size_t px1 = (size_t)F * T;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int Bc = std::min(mb, B - b0);
+    RngParams rp{s.seed, s.utt_offset + b0, 0};
+    CUDA_OK(cudaMemcpyAsync(e.rng_dev, &rp, sizeof(rp), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const float2* nchunk = noise ? noise + b0 * px1 : nullptr;
+    const bool graph_ok = e.cfg.use_graphs && !noise && !e.time_convs;
+    if (!graph_ok) {
+      sample_chunk(e, y + b0 * px1, Bc, F, T, s, nchunk, (size_t)B * px1, out + b0 * px1, st, false);
+      continue;
+    }
+    // graph path: the graph works on engine-owned staging (state <- ystage, xmean/out via ostage)
+    GraphKey key{Bc, F, T, s.N, s.predictor, s.corrector, csteps, s.denoise, s.probability_flow, s.snr};
+    auto it = e.graphs.find(key);
+    if (it == e.graphs.end()) {
+      // one eager network evaluation first: sets function attributes and surfaces launch errors early
+      {
+        launch_pack_state(st, y + b0 * px1, y + b0 * px1, Bc, F, T, e.state);
+        Fwd f{e, st, e.temb_table, 0, false, e.cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
+        f.run(e.state, Bc, F, T);
+        CUDA_OK(cudaStreamSynchronize(st));
+      }
+      cudaGraph_t g = nullptr;
+      const long long launches_before = e.kernel_launches;
+      CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      try {
+        // y is read from / the result written to engine-owned buffers so the graph is pointer-stable
+        sample_chunk(e, (const float2*)e.stft_buf[3], Bc, F, T, s, nullptr, 0, (float2*)e.stft_buf[3], st, true);
+      } catch (...) {
+        cudaStreamEndCapture(st, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      CUDA_OK(cudaStreamEndCapture(st, &g));
+      cudaGraphExec_t ge = nullptr;
+      CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      const long long nodes = e.kernel_launches - launches_before;   // kernels recorded, not executed
+      e.kernel_launches = launches_before;
+      it = e.graphs.emplace(key, GraphEntry{ge, nodes}).first;
+    }
+    CUDA_OK(cudaMemcpyAsync(e.stft_buf[3], y + b0 * px1, Bc * px1 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+    ++e.graph_launches;
+    e.kernel_launches += it->second.kernel_nodes;
+    CUDA_OK(cudaMemcpyAsync(out + b0 * px1, e.stft_buf[3], Bc * px1 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+  }
+  if (nfe) *nfe = s.N * (csteps + 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// STFT front / back end
+// ------------------------------------------------------------------------------------------------
+void ensure_stft_buf(Engine& e, int slot, size_t bytes) {
+  if (bytes <= e.stft_cap[slot]) return;
+  if (e.stft_buf[slot]) { CUDA_OK(cudaDeviceSynchronize()); cudaFree(e.stft_buf[slot]); e.stft_buf[slot] = nullptr; }
+  CUDA_OK(cudaMalloc(&e.stft_buf[slot], bytes));
+  e.stft_cap[slot] = bytes;
+  if (slot == 3) { for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec); e.graphs.clear(); }
+}
+
+cufftHandle fft_plan(Engine& e, bool inverse, int n_fft, int batch) {
+  const std::pair<int, int> key{(inverse ? 1 << 28 : 0) | n_fft, batch};
+  auto it = e.fft_plans.find(key);
+  if (it != e.fft_plans.end()) return it->second;
+  cufftHandle h;
+  int n[1] = {n_fft};
+  const cufftResult r = cufftPlanMany(&h, 1, n, nullptr, 1, n_fft, nullptr, 1, n_fft / 2 + 1, inverse ? CUFFT_C2R : CUFFT_R2C, batch);
+  SG_CHECK(r == CUFFT_SUCCESS, "cufftPlanMany(n=%d, batch=%d) failed: %d", n_fft, batch, (int)r);
+  e.fft_plans[key] = h;
+  return h;
+}
+
+int frames_of(const Engine& e, int L) { return 1 + L / e.cfg.hop_length; }
+int padded_frames(const Engine& e, int L) { const int nT = frames_of(e, L); return (nT + 63) / 64 * 64; }
+
+void analysis(Engine& e, const float* wav, int B, int L, int pad_mode, float2* Y, float* norm, cudaStream_t st) {
+  const sgmse_b200_config& c = e.cfg;
+  const int nT = frames_of(e, L), Tpad = padded_frames(e, L), F = c.n_fft / 2 + 1;
+  SG_CHECK(L > c.n_fft / 2, "waveform too short for reflect padding");
+  ensure_stft_buf(e, 0, (size_t)B * nT * c.n_fft * 4);
+  ensure_stft_buf(e, 1, (size_t)B * nT * F * 8);
+  launch_absmax(st, wav, B, L, norm);
+  launch_frame(st, wav, norm, B, L, c.n_fft, c.hop_length, nT, c.sqrt_window, (float*)e.stft_buf[0]);
+  cufftHandle h = fft_plan(e, false, c.n_fft, B * nT);
+  SG_CHECK(cufftSetStream(h, st) == CUFFT_SUCCESS, "cufftSetStream failed");
+  SG_CHECK(cufftExecR2C(h, (cufftReal*)e.stft_buf[0], (cufftComplex*)e.stft_buf[1]) == CUFFT_SUCCESS, "cufftExecR2C failed");
+  launch_spec_fwd(st, (const float2*)e.stft_buf[1], B, nT, F, F, Tpad, c.spec_factor, c.spec_abs_exponent,
+                  pad_mode == SGMSE_B200_PAD_REFLECTION, Y);
+  e.kernel_launches += 4;
+}
+
+void synthesis(Engine& e, const float2* X, const float* norm, int B, int Tpad, int L, float* wav, cudaStream_t st) {
+  const sgmse_b200_config& c = e.cfg;
+  const int F = c.n_fft / 2 + 1;
+  ensure_stft_buf(e, 0, (size_t)B * Tpad * c.n_fft * 4);
+  ensure_stft_buf(e, 1, (size_t)B * Tpad * F * 8);
+  launch_spec_back(st, X, B, F, Tpad, F, c.spec_factor, c.spec_abs_exponent, (float2*)e.stft_buf[1]);
+  cufftHandle h = fft_plan(e, true, c.n_fft, B * Tpad);
+  SG_CHECK(cufftSetStream(h, st) == CUFFT_SUCCESS, "cufftSetStream failed");
+  SG_CHECK(cufftExecC2R(h, (cufftComplex*)e.stft_buf[1], (cufftReal*)e.stft_buf[0]) == CUFFT_SUCCESS, "cufftExecC2R failed");
+  launch_overlap_add(st, (const float*)e.stft_buf[0], norm, B, Tpad, c.n_fft, c.hop_length, c.sqrt_window, L, wav);
+  e.kernel_launches += 3;
+}
+
+void enhance(Engine& e, const float* wav, int B, int L, const sgmse_b200_sampler& s, const float2* noise, float* out,
+             bool host, cudaStream_t st) {
+  const int Tpad = padded_frames(e, L), F = e.cfg.n_fft / 2 + 1;
+  const size_t px = (size_t)B * F * Tpad;
+  // slot 2: [wav in | wav out | norm | Y | X]
+  const size_t wav_bytes = ((size_t)B * L * 4 + 255) & ~(size_t)255;
+  ensure_stft_buf(e, 2, 2 * wav_bytes + 256 + ((size_t)B * 4 + 255) / 256 * 256 + 2 * px * 8);
+  uint8_t* base = (uint8_t*)e.stft_buf[2];
+  float* wav_d = (float*)base;
+  float* out_d = (float*)(base + wav_bytes);
+  float* norm = (float*)(base + 2 * wav_bytes);
+  float2* Y = (float2*)(base + 2 * wav_bytes + ((size_t)B * 4 + 255) / 256 * 256);
+  float2* X = Y + px;
+  const int mb = std::max(1, e.cfg.max_batch);
+  ensure_stft_buf(e, 3, (size_t)std::min(B, mb) * F * Tpad * 8);
+  const float* wsrc = wav;
+  if (host) { CUDA_OK(cudaMemcpyAsync(wav_d, wav, (size_t)B * L * 4, cudaMemcpyHostToDevice, st)); wsrc = wav_d; }
+  analysis(e, wsrc, B, L, s.pad_mode, Y, norm, st);
+  pc_sample(e, Y, B, F, Tpad, s, noise, X, nullptr, st);
+  float* odst = host ? out_d : out;
+  synthesis(e, X, norm, B, Tpad, L, odst, st);
+  if (host) {
+    CUDA_OK(cudaMemcpyAsync(out, out_d, (size_t)B * L * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+#define API_BEGIN try {
+#define API_END                                                          \
+  return 0;                                                              \
+  }                                                                      \
+  catch (const sgmse::Error& err) { sgmse::set_last_error(err.msg); return 1; } \
+  catch (const std::exception& ex) { sgmse::set_last_error(ex.what()); return 2; } \
+  catch (...) { sgmse::set_last_error("unknown error"); return 3; }
+
+extern "C" {
+
+const char* sgmse_b200_last_error(void) { return sgmse::get_last_error(); }
+const char* sgmse_b200_version(void) { return "sgmse_b200 0.1 (sm_100a)"; }
+
+int sgmse_b200_create(const sgmse_b200_config* cfg, sgmse_b200_engine** out) {
+  API_BEGIN
+  SG_CHECK(cfg && out, "null argument");
+  std::unique_ptr<Engine> e(new Engine());
+  e->cfg = *cfg;
+  if (e->cfg.max_batch <= 0) e->cfg.max_batch = 8;
+  SG_CHECK(cfg->mode >= 0 && cfg->mode <= 2, "unknown mode %d", cfg->mode);
+  build_network(*e);
+  *out = e.release();
+  API_END
+}
+
+void sgmse_b200_destroy(sgmse_b200_engine* e) {
+  if (!e) return;
+  cudaDeviceSynchronize();
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec);
+  for (auto& p : e->fft_plans) cufftDestroy(p.second);
+  free_weights(*e);
+  cudaFree(e->arena.base);
+  cudaFree(e->state); cudaFree(e->xmean); cudaFree(e->temb_table); cudaFree(e->temb_scratch); cudaFree(e->t_dev);
+  cudaFree(e->coef_dev); cudaFree(e->rng_dev); cudaFree(e->lv_scratch); cudaFree(e->dbg_flag);
+  for (int i = 0; i < 4; ++i) cudaFree(e->stft_buf[i]);
+  delete e;
+}
+
+int sgmse_b200_manifest_count(const sgmse_b200_engine* e) { return e ? (int)e->manifest.size() : -1; }
+int sgmse_b200_manifest_entry(const sgmse_b200_engine* e, int i, char* name, int name_cap, long long* numel) {
+  API_BEGIN
+  SG_CHECK(e && i >= 0 && i < (int)e->manifest.size(), "manifest index out of range");
+  if (name && name_cap > 0) { strncpy(name, e->manifest[i].name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (numel) *numel = e->manifest[i].numel;
+  API_END
+}
+long long sgmse_b200_weights_numel(const sgmse_b200_engine* e) { return e ? e->weights_numel : -1; }
+
+int sgmse_b200_load_weights(sgmse_b200_engine* e, const float* blob, long long numel) {
+  API_BEGIN
+  SG_CHECK(e && blob, "null argument");
+  SG_CHECK(numel == e->weights_numel, "weight blob has %lld floats, the network needs %lld", numel, e->weights_numel);
+  load_weights(*e, blob);
+  API_END
+}
+int sgmse_b200_load_weights_device(sgmse_b200_engine* e, const float* blob_dev, long long numel, void* stream) {
+  API_BEGIN
+  SG_CHECK(e && blob_dev, "null argument");
+  SG_CHECK(numel == e->weights_numel, "weight blob has %lld floats, the network needs %lld", numel, e->weights_numel);
+  std::vector<float> host((size_t)numel);
+  CUDA_OK(cudaMemcpyAsync(host.data(), blob_dev, (size_t)numel * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  load_weights(*e, host.data());
+  API_END
+}
+
+int sgmse_b200_dnn_forward(sgmse_b200_engine* e, const void* x, const float* t, void* out, int B, int F, int T, void* stream) {
+  API_BEGIN
+  SG_CHECK(e && x && t && out && B > 0, "bad argument");
+  const float2* xx = (const float2*)x;   // [B][2][F*T]: channel 0 = x_t, channel 1 = y
+  // the two channels of one sample are F*T apart; re-pack through pack_state per sample pair
+  const size_t px1 = (size_t)F * T;
+  ensure_stft_buf(*e, 3, (size_t)2 * B * px1 * 8);
+  float2* xs = (float2*)e->stft_buf[3];
+  float2* ys = xs + (size_t)B * px1;
+  for (int b = 0; b < B; ++b) {
+    CUDA_OK(cudaMemcpyAsync(xs + b * px1, xx + (size_t)(2 * b) * px1, px1 * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CUDA_OK(cudaMemcpyAsync(ys + b * px1, xx + (size_t)(2 * b + 1) * px1, px1 * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  dnn_forward(*e, xs, ys, t, (float2*)out, B, F, T, false, (cudaStream_t)stream);
+  API_END
+}
+int sgmse_b200_score(sgmse_b200_engine* e, const void* x_t, const void* y, const float* t, void* out, int B, int F, int T, void* stream) {
+  API_BEGIN
+  SG_CHECK(e && x_t && y && t && out && B > 0, "bad argument");
+  dnn_forward(*e, (const float2*)x_t, (const float2*)y, t, (float2*)out, B, F, T, true, (cudaStream_t)stream);
+  API_END
+}
+
+int sgmse_b200_noise_draws(const sgmse_b200_sampler* s) { return s ? noise_draws(*s) : -1; }
+
+int sgmse_b200_pc_sample(sgmse_b200_engine* e, const void* y, int B, int F, int T, const sgmse_b200_sampler* s,
+                         const void* noise, void* out, int* nfe, void* stream) {
+  API_BEGIN
+  SG_CHECK(e && y && s && out && B > 0, "bad argument");
+  const int mb = std::max(1, e->cfg.max_batch);
+  ensure_stft_buf(*e, 3, (size_t)std::min(B, mb) * F * T * 8);
+  pc_sample(*e, (const float2*)y, B, F, T, *s, (const float2*)noise, (float2*)out, nfe, (cudaStream_t)stream);
+  API_END
+}
+
+int sgmse_b200_padded_frames(const sgmse_b200_engine* e, int L) { return e ? padded_frames(*e, L) : -1; }
+
+int sgmse_b200_analysis(sgmse_b200_engine* e, const float* wav, int B, int L, int pad_mode, void* Y, float* norm, void* stream) {
+  API_BEGIN
+  SG_CHECK(e && wav && Y && norm, "bad argument");
+  analysis(*e, wav, B, L, pad_mode, (float2*)Y, norm, (cudaStream_t)stream);
+  API_END
+}
+int sgmse_b200_synthesis(sgmse_b200_engine* e, const void* X, const float* norm, int B, int Tpad, int L, float* wav, void* stream) {
+  API_BEGIN
+  SG_CHECK(e && X && norm && wav, "bad argument");
+  synthesis(*e, (const float2*)X, norm, B, Tpad, L, wav, (cudaStream_t)stream);
+  API_END
+}
+int sgmse_b200_enhance(sgmse_b200_engine* e, const float* wav, int B, int L, const sgmse_b200_sampler* s,
+                       const void* noise, float* out, int host_buffers, void* stream) {
+  API_BEGIN
+  SG_CHECK(e && wav && s && out && B > 0 && L > 0, "bad argument");
+  enhance(*e, wav, B, L, *s, (const float2*)noise, out, host_buffers != 0, (cudaStream_t)stream);
+  API_END
+}
+
+int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, long long cap, int shape[4]) {
+  API_BEGIN
+  SG_CHECK(e && name, "bad argument");
+  CUDA_OK(cudaDeviceSynchronize());
+  auto it = e->taps.find(name);
+  if (it != e->taps.end()) {
+    const TensorDesc& t = it->second;
+    if (shape) { shape[0] = t.N; shape[1] = t.C; shape[2] = t.H; shape[3] = t.W; }
+    if (!out_host) return 0;
+    SG_CHECK((long long)t.numel() <= cap, "tap buffer too small");
+    float* tmp = nullptr;
+    CUDA_OK(cudaMalloc((void**)&tmp, t.numel() * 4));
+    nhwc_to_nchw_kernel<<<(unsigned)((t.numel() + 255) / 256), 256>>>(t.p, t.dt == DT_F16, t.C, t.H * t.W, t.numel(), tmp);
+    cudaError_t err = cudaMemcpy(out_host, tmp, t.numel() * 4, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    CUDA_OK(err);
+    return 0;
+  }
+  auto it4 = e->taps4.find(name);
+  SG_CHECK(it4 != e->taps4.end(), "no recorded activation named '%s'", name);
+  const std::vector<int>& s4 = it4->second.second;
+  const size_t numel = (size_t)s4[0] * 4 * s4[2] * s4[3];
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = s4[i];
+  if (!out_host) return 0;
+  SG_CHECK((long long)numel <= cap, "tap buffer too small");
+  float* tmp = nullptr;
+  CUDA_OK(cudaMalloc((void**)&tmp, numel * 4));
+  nhwc_to_nchw_kernel<<<(unsigned)((numel + 255) / 256), 256>>>(it4->second.first, 0, 4, s4[2] * s4[3], numel, tmp);
+  cudaError_t err = cudaMemcpy(out_host, tmp, numel * 4, cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  CUDA_OK(err);
+  API_END
+}
+
+long long sgmse_b200_workspace_bytes(sgmse_b200_engine* e, int B, int F, int T) {
+  // host-only dry run of the launch sequence (no CUDA call): exercises the whole layer walk
+  try {
+    SG_CHECK(e && B > 0, "bad argument");
+    Arena saved = e->arena;
+    e->arena = Arena{};
+    e->arena.dry = true;
+    Fwd f{*e, nullptr, nullptr, 0, true, e->cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
+    try { f.run(nullptr, B, F, T); } catch (...) { e->arena = saved; throw; }
+    const long long need = (long long)e->arena.high + 4096;
+    e->arena = saved;
+    return need;
+  } catch (const sgmse::Error& err) { sgmse::set_last_error(err.msg); return -1; }
+  catch (...) { sgmse::set_last_error("unknown error"); return -1; }
+}
+
+int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value) {
+  API_BEGIN
+  SG_CHECK(e && key, "bad argument");
+  const std::string k = key;
+  if (k == "record_taps") e->record_taps = value != 0;
+  else if (k == "time_convs") {
+    // per-launch CUDA-event timing of the convolution kernels (eager launches only; see bench.py)
+    CUDA_OK(cudaDeviceSynchronize());
+    for (auto& c : e->conv_events) { cudaEventDestroy(c.start); cudaEventDestroy(c.stop); }
+    e->conv_events.clear();
+    e->time_convs = value != 0;
+  }
+  else if (k == "use_graphs") e->cfg.use_graphs = value != 0;
+  else if (k == "tc_mask") { e->tc_mask = value; for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec); e->graphs.clear(); }
+  else SG_CHECK(false, "unknown option '%s'", key);
+  API_END
+}
+
+long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key) {
+  if (!e || !key) return -1;
+  const std::string k = key;
+  if (k == "kernel_launches") return e->kernel_launches;
+  if (k == "graph_launches") return e->graph_launches;
+  if (k == "workspace_bytes") return (long long)e->arena.cap;
+  if (k == "weights_bytes") return (long long)e->weights_bytes;
+  if (k == "tc_convs_last_forward") return e->tc_convs;
+  if (k == "direct_convs_last_forward") return e->direct_convs;
+  if (k == "launches_last_forward") return e->launches_this_forward;
+  if (k == "timed_conv_tc_us" || k == "timed_conv_tc_mflop" || k == "timed_conv_tc_count" || k == "timed_conv_tc_kbytes" ||
+      k == "timed_conv_direct_us") {
+    cudaDeviceSynchronize();
+    double us = 0, mflop = 0, n = 0, kb = 0, dus = 0;
+    for (const auto& c : e->conv_events) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c.start, c.stop) != cudaSuccess) continue;
+      if (c.tc) { us += ms * 1e3; mflop += c.flops * 1e-6; kb += c.bytes * 1e-3; n += 1; } else dus += ms * 1e3;
+    }
+    if (k == "timed_conv_tc_us") return (long long)us;
+    if (k == "timed_conv_tc_mflop") return (long long)mflop;
+    if (k == "timed_conv_tc_kbytes") return (long long)kb;
+    if (k == "timed_conv_direct_us") return (long long)dus;
+    return (long long)n;
+  }
+  return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+// GroupNorm statistics finalisation and the fused GroupNorm-apply + SiLU (+ FIR up/down) pass.
+//
+// Reference semantics: nn.GroupNorm(min(C/4,32), eps=1e-6) + SiLU of
+// ResnetBlockBigGANpp.forward (/root/reference/sgmse/backbones/ncsnpp_utils/layerspp.py:242-258)
+// and the FIR resamplers upsample_2d / downsample_2d (up_or_down_sampling.py:195-257).
+// HBM-bound elementwise work: 128-bit accesses, one read of x, one write per output.
+#include "kernels.h"
+
+namespace sgmse {
+
+// ------------------------------------------------------------------------------------------------
+// gn_finalize: grid (groups, N).  Sums the producer's per-slot partials in double, fixed order.
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int slots0,
+                                   const float* __restrict__ st1, int C1, int slots1,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   int cpg, double inv_count, float2* __restrict__ ab) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int Ct = C0 + C1;
+  const int max_slots = slots0 > slots1 ? slots0 : slots1;
+  double s = 0.0, q = 0.0;
+  for (int j = threadIdx.x; j < cpg * max_slots; j += blockDim.x) {
+    const int cl = j % cpg, slot = j / cpg;
+    const int ch = g * cpg + cl;
+    if (ch < C0) {
+      if (slot < slots0) {
+        const float2 v = *reinterpret_cast<const float2*>(st0 + (((size_t)n * slots0 + slot) * C0 + ch) * 2);
+        s += v.x; q += v.y;
+      }
+    } else {
+      if (slot < slots1) {
+        const float2 v = *reinterpret_cast<const float2*>(st1 + (((size_t)n * slots1 + slot) * C1 + (ch - C0)) * 2);
+        s += v.x; q += v.y;
+      }
+    }
+  }
+  __shared__ double sh_s[32], sh_q[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh_s[warp] = s; sh_q[warp] = q; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    s = lane < nw ? sh_s[lane] : 0.0;
+    q = lane < nw ? sh_q[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) { sh_s[0] = s; sh_q[0] = q; }
+  }
+  __syncthreads();
+  const double mean = sh_s[0] * inv_count;
+  double var = sh_q[0] * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + 1e-6));
+  for (int cl = threadIdx.x; cl < cpg; cl += blockDim.x) {
+    const int ch = g * cpg + cl;
+    const float a = gamma[ch] * rstd;
+    ab[(size_t)n * Ct + ch] = make_float2(a, beta[ch] - (float)mean * a);
+  }
+}
+
+void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc* s1, const float* gamma,
+                        const float* beta, int groups, float2* ab) {
+  const int C1 = s1 ? s1->C : 0;
+  const int Ct = s0.C + C1;
+  SG_CHECK(Ct % groups == 0, "GroupNorm: %d channels not divisible by %d groups", Ct, groups);
+  SG_CHECK(s0.stats && s0.slots > 0 && (!s1 || (s1->stats && s1->slots > 0)), "GroupNorm input has no statistics");
+  if (s1) SG_CHECK(s1->N == s0.N && s1->H == s0.H && s1->W == s0.W, "concat shape mismatch");
+  const int cpg = Ct / groups;
+  const double inv_count = 1.0 / ((double)s0.H * s0.W * cpg);
+  dim3 grid(groups, s0.N);
+  gn_finalize_kernel<<<grid, 256, 0, st>>>(s0.stats, s0.C, s0.slots, s1 ? s1->stats : nullptr, C1,
+                                           s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab);
+  CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel_stats: stand-alone (sum, sum^2) per (sample, channel) for tiny levels whose producers cannot
+// emit per-tile partials (H*W not a multiple of the tile).  grid (ceil(C/32), N), block (32, 8).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void channel_stats_kernel(const T* __restrict__ x, int HW, int C, float* __restrict__ stats) {
+  const int c = blockIdx.x * 32 + threadIdx.x, n = blockIdx.y;
+  float s = 0.f, q = 0.f;
+  if (c < C)
+    for (int p = threadIdx.y; p < HW; p += 8) { const float v = Act<T>::ld(x + ((size_t)n * HW + p) * C + c); s += v; q += v * v; }
+  __shared__ float sh[8][32][2];
+  sh[threadIdx.y][threadIdx.x][0] = s; sh[threadIdx.y][threadIdx.x][1] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int r = 1; r < 8; ++r) { s += sh[r][threadIdx.x][0]; q += sh[r][threadIdx.x][1]; }
+    stats[((size_t)n * C + c) * 2] = s; stats[((size_t)n * C + c) * 2 + 1] = q;
+  }
+}
+void launch_channel_stats(cudaStream_t st, TensorDesc& t) {
+  SG_CHECK(t.stats != nullptr, "channel_stats: tensor has no statistics buffer");
+  t.slots = 1;
+  dim3 grid(cdiv(t.C, 32), t.N), block(32, 8);
+  if (t.dt == DT_F16) channel_stats_kernel<__half><<<grid, block, 0, st>>>((const __half*)t.p, t.H * t.W, t.C, t.stats);
+  else channel_stats_kernel<float><<<grid, block, 0, st>>>((const float*)t.p, t.H * t.W, t.C, t.stats);
+  CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// gn_apply: one thread = one output pixel x 8 channels.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RS, bool SILU, bool RAW>
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1, int C1,
+                const float2* __restrict__ ab, int N, int Hi, int Wi, T* __restrict__ out0,
+                T* __restrict__ out1) {
+  const int Ct = C0 + C1;
+  const int cv_per_px = Ct >> 3;
+  const int Ho = RS == RS_DOWN ? Hi / 2 : (RS == RS_UP ? Hi * 2 : Hi);
+  const int Wo = RS == RS_DOWN ? Wi / 2 : (RS == RS_UP ? Wi * 2 : Wi);
+  const size_t total = (size_t)N * Ho * Wo * cv_per_px;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cv_per_px);
+    size_t pix = idx / cv_per_px;
+    const int X = (int)(pix % Wo); pix /= Wo;
+    const int Y = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    const int c = cv << 3;
+    const T* src; int Cs, cs;
+    if (c < C0) { src = x0; Cs = C0; cs = c; } else { src = x1; Cs = C1; cs = c - C0; }
+    float a[8], b[8];
+    {
+      const float4* p = reinterpret_cast<const float4*>(ab + (size_t)n * Ct + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { float4 v = p[i]; a[2 * i] = v.x; b[2 * i] = v.y; a[2 * i + 1] = v.z; b[2 * i + 1] = v.w; }
+    }
+    float acc[8], raw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] = 0.f; raw[i] = 0.f; }
+    auto tap = [&](int y, int x, float w) {
+      if ((unsigned)y >= (unsigned)Hi || (unsigned)x >= (unsigned)Wi) return;
+      Vec8<T> v; float f[8];
+      v.load(src + (((size_t)n * Hi + y) * Wi + x) * Cs + cs);
+      v.get(f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float h = fmaf(a[i], f[i], b[i]);
+        if (SILU) h = silu_f(h);
+        acc[i] = fmaf(w, h, acc[i]);
+        if (RAW) raw[i] = fmaf(w, f[i], raw[i]);
+      }
+    };
+    if (RS == RS_NONE) {
+      tap(Y, X, 1.f);
+    } else if (RS == RS_DOWN) {
+      // out[Y,X] = sum_{i,j} k[i]k[j] h[2Y+i-1, 2X+j-1], k = [1,3,3,1]/8, zero outside
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tap(2 * Y + i - 1, 2 * X + j - 1, fir_tap(i) * fir_tap(j));
+    } else {
+      // zero-insert x2, pad (2,1), FIR [1,3,3,1]/4 per axis:
+      //   even Y=2y: 3/4 h[y] + 1/4 h[y-1];  odd Y=2y+1: 3/4 h[y] + 1/4 h[y+1]
+      const int y0 = Y >> 1, x0i = X >> 1;
+      const int y1 = (Y & 1) ? y0 + 1 : y0 - 1;
+      const int x1i = (X & 1) ? x0i + 1 : x0i - 1;
+      tap(y0, x0i, 0.5625f);
+      tap(y0, x1i, 0.1875f);
+      tap(y1, x0i, 0.1875f);
+      tap(y1, x1i, 0.0625f);
+    }
+    Vec8<T> o;
+    o.set(acc);
+    o.store(out0 + idx * 8);
+    if (RAW) { o.set(raw); o.store(out1 + idx * 8); }
+  }
+}
+
+template <typename T>
+static void gn_apply_dispatch(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float2* ab, bool silu,
+                              Resample rs, TensorDesc& out0, TensorDesc* out1) {
+  const int C1 = x1 ? x1->C : 0;
+  const size_t total = out0.numel() / 8;
+  const int block = 256;
+  const int grid = (int)((total + block - 1) / block);
+  const T* p0 = (const T*)x0.p; const T* p1 = x1 ? (const T*)x1->p : nullptr;
+  T* o0 = (T*)out0.p; T* o1 = out1 ? (T*)out1->p : nullptr;
+#define GO(RS_, SILU_, RAW_) \
+  gn_apply_kernel<T, RS_, SILU_, RAW_><<<grid, block, 0, st>>>(p0, x0.C, p1, C1, ab, x0.N, x0.H, x0.W, o0, o1)
+  if (rs == RS_NONE) {
+    if (silu) GO(RS_NONE, true, false); else GO(RS_NONE, false, false);
+  } else if (rs == RS_DOWN) {
+    SG_CHECK(silu && out1 && !x1, "down-sampling gn_apply expects silu, raw output, one source");
+    GO(RS_DOWN, true, true);
+  } else {
+    SG_CHECK(silu && out1 && !x1, "up-sampling gn_apply expects silu, raw output, one source");
+    GO(RS_UP, true, true);
+  }
+#undef GO
+  CUDA_OK(cudaGetLastError());
+}
+
+void launch_gn_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float2* ab, bool silu,
+                     Resample rs, TensorDesc& out0, TensorDesc* out1) {
+  const int C1 = x1 ? x1->C : 0;
+  SG_CHECK(x0.C % 8 == 0 && C1 % 8 == 0, "channel counts must be multiples of 8 (got %d, %d)", x0.C, C1);
+  SG_CHECK(out0.C == x0.C + C1 && out0.N == x0.N, "gn_apply output shape mismatch");
+  const int Ho = rs == RS_DOWN ? x0.H / 2 : (rs == RS_UP ? x0.H * 2 : x0.H);
+  const int Wo = rs == RS_DOWN ? x0.W / 2 : (rs == RS_UP ? x0.W * 2 : x0.W);
+  SG_CHECK(out0.H == Ho && out0.W == Wo, "gn_apply output resolution mismatch");
+  if (x0.dt == DT_F16) gn_apply_dispatch<__half>(st, x0, x1, ab, silu, rs, out0, out1);
+  else gn_apply_dispatch<float>(st, x0, x1, ab, silu, rs, out0, out1);
+}
+
+}  // namespace sgmse

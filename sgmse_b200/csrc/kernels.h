@@ -1,0 +1,131 @@
+// Host-side launcher interface of the sgmse_b200 CUDA kernels (internal; the public boundary is
+// include/sgmse_b200.h).  All activations are NHWC; "stats" are per-(sample, slot, channel)
+// partial (sum, sum of squares) written by the producer of a tensor and consumed by gn_finalize.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sgmse {
+
+enum DType { DT_F32 = 0, DT_F16 = 1 };
+static inline size_t dt_size(DType d) { return d == DT_F32 ? 4 : 2; }
+
+struct TensorDesc {
+  void* p = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;
+  DType dt = DT_F32;
+  float* stats = nullptr;  // [N][slots][C][2]; capacity = N * (H*W/32) * C * 2 floats
+  int slots = 0;           // set by the producing launcher
+  size_t numel() const { return (size_t)N * H * W * C; }
+  size_t bytes() const { return numel() * dt_size(dt); }
+  size_t stats_capacity_floats() const { return (size_t)N * std::max<size_t>(1, (size_t)H * W / 32) * C * 2; }
+};
+
+// ---- GroupNorm ----
+// ab[n][c] = (a, b) with y = a*x + b  (a = gamma*rstd, b = beta - mean*rstd*gamma), eps = 1e-6
+void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc* s1, const float* gamma,
+                        const float* beta, int groups, float2* ab);
+// stand-alone per-(sample, channel) statistics (slots = 1) for levels too small for per-tile partials
+void launch_channel_stats(cudaStream_t st, TensorDesc& t);
+enum Resample { RS_NONE = 0, RS_DOWN = 1, RS_UP = 2 };
+// out0 = [silu](a*x+b) (concat of x0,x1), optionally FIR-resampled; out1 (optional) = FIR-resampled raw x0
+void launch_gn_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float2* ab, bool silu,
+                     Resample rs, TensorDesc& out0, TensorDesc* out1);
+
+// ---- convolutions ----
+struct ConvSeg {
+  TensorDesc src;
+  int taps = 9;  // 9 (3x3, pad 1) or 1 (1x1)
+};
+struct ConvArgs {
+  int nseg = 0;
+  ConvSeg seg[3];
+  const void* w_direct = nullptr;  // [Ktot][Cout], element type of the activations
+  const __half* w_tc = nullptr;    // [Cout][Ktot]
+  const float* bias = nullptr;     // [Cout] (nullable)
+  const float* temb = nullptr;     // per-(row, channel) additive bias table (nullable)
+  int temb_stride = 0;             // floats between consecutive samples' rows (0: all samples share)
+  const TensorDesc* residual = nullptr;
+  float scale = 1.f;               // out = (acc + bias + temb + residual) * scale
+  int ktot() const { int k = 0; for (int i = 0; i < nseg; ++i) k += seg[i].taps * seg[i].src.C; return k; }
+};
+void launch_conv_direct(cudaStream_t st, const ConvArgs& a, TensorDesc& out);
+// tcgen05 implicit GEMM; requires fp16 activations, every segment C % 64 == 0, Cout % 128 == 0
+bool conv_tc_supported(const ConvArgs& a, const TensorDesc& out);
+void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
+
+// input layer: state float4 (x.re,x.im,y.re,y.im) -> conv3x3(4->C); w [36][C] (k = tap*4+cin), bias [C]
+void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
+                       const float* bias, TensorDesc& out);
+// Combine('sum'): out = conv1x1_{4->C}(pyr) + bias + h ; pyr float4 [N,H,W]; w [4][C]
+void launch_combine(cudaStream_t st, const float4* pyr, const float* w, const float* bias, const TensorDesc& h,
+                    TensorDesc& out);
+// 4-channel FIR resample of the input/output pyramids
+void launch_fir4(cudaStream_t st, const float4* in, int N, int H, int W, Resample rs, float4* out);
+// out4 = conv3x3_{C->4}(act) + bias (+ addend);  w [9*C][4] (device), bias: HOST pointer to 4 floats
+void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, const float* bias,
+                     const float4* addend, float4* out);
+
+// ---- attention: qkv [N,H,W,3C] (q|k|v), out [N,H,W,C] = softmax(q k^T / sqrt(C)) v over H*W tokens
+void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out);
+
+// ---- time embedding ----
+struct TembWeights {
+  const float* gfp_w;   // [nf]
+  const float* l1_w;    // [4nf][2nf]
+  const float* l1_b;    // [4nf]
+  const float* l2_w;    // [4nf][4nf]
+  const float* l2_b;
+  const float* dense_w; // [totalC][4nf]  (all Dense_0 stacked)
+  const float* dense_b; // [totalC]       (Dense_0.bias + Conv_0.bias)
+  int nf, totalC;
+};
+// table[r][totalC] for r < R, from t[r]; scratch >= R*4nf floats
+void launch_temb(cudaStream_t st, const TembWeights& w, const float* t, int R, float* scratch, float* table);
+
+// ---- SDE / sampler ----
+struct OutLayer {  // output_layer conv1x1(4->2) (+ the /t ordering of the backbone)
+  float w[2][4];
+  float b[2];
+  int scale_after;  // 0: conv(p/t) (ncsnpp)   1: conv(p)/t (ncsnpp_48k)
+  int scale_by_sigma;
+};
+struct RngParams {  // lives in device memory so that CUDA graphs can be re-launched with a new seed
+  unsigned long long seed;
+  int utt0;
+  int pad;
+};
+struct UpdateCoef {  // x_mean = x + cy*(y-x) + cs*score ; x' = x_mean + cz*z
+  float cy, cs, cz;
+};
+// state <- state with x replaced; score = -out_layer(pyr, 1/t).  coef read from device memory.
+// noise: injected complex normals [N,H,W] (float2) or nullptr -> Philox(rng->seed, rng->utt0+n, draw).
+void launch_pc_update(cudaStream_t st, float4* state, const float4* pyr, int N, int H, int W, const OutLayer& ol,
+                      const float* inv_t /*device [N] or nullptr->use inv_t_scalar*/, float inv_t_scalar,
+                      const UpdateCoef* coef_dev, const float2* noise, const RngParams* rng, int draw,
+                      float2* x_mean_out /*nullable*/);
+// dnn forward output only: out[n,h,w] = out_layer(pyr, 1/t[n])  (complex64)
+void launch_out_layer(cudaStream_t st, const float4* pyr, int N, int H, int W, const OutLayer& ol, const float* t_dev,
+                      float2* out, bool negate);
+void launch_pack_state(cudaStream_t st, const float2* x, const float2* y, int N, int H, int W, float4* state);
+// state.x = y + std1 * z
+void launch_prior(cudaStream_t st, float4* state, int N, int H, int W, float std1, const float2* noise,
+                  const RngParams* rng, int draw);
+// Langevin corrector step size from batch-mean norms: coef = (0, eps, sqrt(2 eps)), eps = 2 (snr*|z|/|g|)^2
+void launch_langevin_coef(cudaStream_t st, const float4* pyr, int N, int H, int W, const OutLayer& ol, float inv_t,
+                          const float2* noise, const RngParams* rng, int draw, float snr, float* scratch,
+                          UpdateCoef* coef_out);
+
+// ---- STFT front/back end (cuFFT plans live in the engine) ----
+void launch_absmax(cudaStream_t st, const float* wav, int B, int L, float* norm);
+void launch_frame(cudaStream_t st, const float* wav, const float* norm, int B, int L, int n_fft, int hop, int nT,
+                  int sqrt_window, float* frames);
+void launch_spec_fwd(cudaStream_t st, const float2* spec /*[B*nT][fstride]*/, int B, int nT, int F, int fstride,
+                     int Tpad, float factor, float expo, int reflect_pad, float2* Y /*[B][F][Tpad]*/);
+void launch_spec_back(cudaStream_t st, const float2* X /*[B][F][Tpad]*/, int B, int F, int Tpad, int fstride,
+                          float factor, float expo, float2* spec /*[B*Tpad][fstride]*/);
+void launch_overlap_add(cudaStream_t st, const float* frames, const float* norm, int B, int Tpad, int n_fft, int hop,
+                        int sqrt_window, int L, float* wav);
+
+}  // namespace sgmse

@@ -1,0 +1,210 @@
+// The 4-channel ends of the network: input conv3x3(4->nf), Combine (conv1x1 4->C of the FIR-down
+// input pyramid, summed into h), the progressive-output conv3x3(C->4), and 4-channel FIR resamplers.
+// All of these are HBM-bound (N=4 or K=4 "GEMMs"): plain coalesced CUDA-core kernels.
+//
+// Reference: ncsnpp.py:293-298 (input conv), layerspp.py:44-59 (Combine), ncsnpp.py:358-379
+// (output_skip pyramid), up_or_down_sampling.py:195-257 (FIR).
+#include "kernels.h"
+
+namespace sgmse {
+
+// ------------------------------------------------------------------------------------------------
+// input conv: state float4 [N,H,W] -> T [N,H,W,C];   w[k][c], k = tap*4 + cin
+// ------------------------------------------------------------------------------------------------
+template <typename T, int TP>
+__global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restrict__ state, int H, int W, int C,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         T* __restrict__ out, float* __restrict__ stats, int slots) {
+  __shared__ float in[TP][36];
+  const int HW = H * W;
+  const int m0 = blockIdx.x * TP;
+  const int n = m0 / HW;
+  const int r0 = m0 - n * HW;
+  for (int i = threadIdx.x; i < TP * 9; i += blockDim.x) {
+    const int p = i / 9, tap = i - p * 9;
+    const int r = r0 + p;
+    const int y = r / W + tap / 3 - 1, x = r % W + tap % 3 - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) v = state[(size_t)n * HW + (size_t)y * W + x];
+    in[p][tap * 4 + 0] = v.x; in[p][tap * 4 + 1] = v.y; in[p][tap * 4 + 2] = v.z; in[p][tap * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float wr[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) wr[k] = w[k * C + c];
+    const float b = bias[c];
+    float s = 0.f, q = 0.f;
+    for (int p = 0; p < TP; ++p) {
+      float acc = b;
+#pragma unroll
+      for (int k = 0; k < 36; ++k) acc = fmaf(wr[k], in[p][k], acc);
+      T* op = out + (size_t)(m0 + p) * C + c;
+      Act<T>::st(op, acc);
+      const float r = Act<T>::ld(op);
+      s += r; q += r * r;
+    }
+    if (stats) {
+      float* d = stats + (((size_t)n * slots + r0 / TP) * C + c) * 2;
+      d[0] = s; d[1] = q;
+    }
+  }
+}
+
+void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
+                       const float* bias, TensorDesc& out) {
+  const int HW = H * W;
+  SG_CHECK(HW % 32 == 0, "input conv: H*W must be a multiple of 32");
+  const int TP = (HW % 128 == 0) ? 128 : 32;
+  out.slots = HW / TP;
+  const int grid = N * HW / TP;
+#define GO(T, TP_) input_conv_kernel<T, TP_><<<grid, 128, 0, st>>>(state, H, W, out.C, w, bias, (T*)out.p, out.stats, out.slots)
+  if (out.dt == DT_F16) { if (TP == 128) GO(__half, 128); else GO(__half, 32); }
+  else { if (TP == 128) GO(float, 128); else GO(float, 32); }
+#undef GO
+  CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Combine: out = W^T pyr + b + h ;  32 pixels per block, thread owns channels
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) combine_kernel(const float4* __restrict__ pyr, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, const T* __restrict__ h, int HW, int M,
+                                                      int C, T* __restrict__ out, float* __restrict__ stats, int slots) {
+  __shared__ float4 pin[32];
+  const int m0 = blockIdx.x * 32;
+  const int n = m0 / HW, r0 = m0 - n * HW;
+  if (threadIdx.x < 32) pin[threadIdx.x] = m0 + threadIdx.x < M ? pyr[m0 + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float w0 = w[c], w1 = w[C + c], w2 = w[2 * C + c], w3 = w[3 * C + c], b = bias[c];
+    float s = 0.f, q = 0.f;
+    for (int p = 0; p < 32 && m0 + p < M; ++p) {
+      const float4 v = pin[p];
+      const size_t o = (size_t)(m0 + p) * C + c;
+      float acc = b + w0 * v.x + w1 * v.y + w2 * v.z + w3 * v.w + Act<T>::ld(h + o);
+      Act<T>::st(out + o, acc);
+      const float r = Act<T>::ld(out + o);
+      s += r; q += r * r;
+    }
+    if (stats) {
+      float* d = stats + (((size_t)n * slots + r0 / 32) * C + c) * 2;
+      d[0] = s; d[1] = q;
+    }
+  }
+}
+
+void launch_combine(cudaStream_t st, const float4* pyr, const float* w, const float* bias, const TensorDesc& h,
+                    TensorDesc& out) {
+  const int HW = h.H * h.W;
+  const int M = h.N * HW;
+  const bool tile_stats = out.stats && HW % 32 == 0;
+  out.slots = tile_stats ? HW / 32 : 0;
+  float* stp = tile_stats ? out.stats : nullptr;
+  const int grid = cdiv(M, 32);
+  if (h.dt == DT_F16)
+    combine_kernel<__half><<<grid, 128, 0, st>>>(pyr, w, bias, (const __half*)h.p, HW, M, h.C, (__half*)out.p, stp, out.slots);
+  else
+    combine_kernel<float><<<grid, 128, 0, st>>>(pyr, w, bias, (const float*)h.p, HW, M, h.C, (float*)out.p, stp, out.slots);
+  CUDA_OK(cudaGetLastError());
+  if (out.stats && !tile_stats) launch_channel_stats(st, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4-channel FIR resample (pyramids, fp32)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
+  a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+}
+
+template <int RS>
+__global__ void fir4_kernel(const float4* __restrict__ in, int N, int Hi, int Wi, float4* __restrict__ out) {
+  const int Ho = RS == RS_DOWN ? Hi / 2 : Hi * 2, Wo = RS == RS_DOWN ? Wi / 2 : Wi * 2;
+  const size_t total = (size_t)N * Ho * Wo;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int X = (int)(idx % Wo), Y = (int)((idx / Wo) % Ho), n = (int)(idx / ((size_t)Wo * Ho));
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto tap = [&](int y, int x, float w) {
+    if ((unsigned)y < (unsigned)Hi && (unsigned)x < (unsigned)Wi) fma4(acc, w, in[((size_t)n * Hi + y) * Wi + x]);
+  };
+  if (RS == RS_DOWN) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tap(2 * Y + i - 1, 2 * X + j - 1, fir_tap(i) * fir_tap(j));
+  } else {
+    const int y0 = Y >> 1, x0 = X >> 1;
+    const int y1 = (Y & 1) ? y0 + 1 : y0 - 1, x1 = (X & 1) ? x0 + 1 : x0 - 1;
+    tap(y0, x0, 0.5625f); tap(y0, x1, 0.1875f); tap(y1, x0, 0.1875f); tap(y1, x1, 0.0625f);
+  }
+  out[idx] = acc;
+}
+
+void launch_fir4(cudaStream_t st, const float4* in, int N, int H, int W, Resample rs, float4* out) {
+  SG_CHECK(rs != RS_NONE, "fir4: nothing to do");
+  const size_t total = rs == RS_DOWN ? (size_t)N * (H / 2) * (W / 2) : (size_t)N * H * 2 * W * 2;
+  const int grid = (int)((total + 255) / 256);
+  if (rs == RS_DOWN) fir4_kernel<RS_DOWN><<<grid, 256, 0, st>>>(in, N, H, W, out);
+  else fir4_kernel<RS_UP><<<grid, 256, 0, st>>>(in, N, H, W, out);
+  CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// progressive output conv3x3 (C -> 4) + bias (+ FIR-up'ed pyramid).  One warp per pixel: lanes
+// split the channels (8 per lane per pass, 128-bit loads), shuffle-reduce the 4 outputs.
+// w [9*C][4] (k = tap*C + cin) as float4 rows.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ act, int N, int H, int W, int C,
+                                                       const float4* __restrict__ w, float4 bias,
+                                                       const float4* __restrict__ addend, float4* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)N * H * W;
+  if (warp >= total) return;
+  const int x = warp % W, y = (warp / W) % H, n = warp / (W * H);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if ((unsigned)yy >= (unsigned)H || (unsigned)xx >= (unsigned)W) continue;
+    const T* row = act + (((size_t)n * H + yy) * W + xx) * C;
+    for (int c = lane * 8; c < C; c += 256) {
+      Vec8<T> v; float f[8];
+      v.load(row + c); v.get(f);
+      const float4* wr = w + (size_t)tap * C + c;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) fma4(acc, f[i], wr[i]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (lane == 0) {
+    acc.x += bias.x; acc.y += bias.y; acc.z += bias.z; acc.w += bias.w;
+    if (addend) { const float4 a = addend[warp]; acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w; }
+    out[warp] = acc;
+  }
+}
+
+void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, const float* bias,
+                     const float4* addend, float4* out) {
+  SG_CHECK(act.C % 8 == 0, "out conv: C must be a multiple of 8");
+  const size_t total = (size_t)act.N * act.H * act.W;
+  const int grid = (int)((total * 32 + 255) / 256);
+  // bias lives on the device: fetch through a tiny kernel argument-free path is overkill; the engine
+  // passes a host copy through `bias` being a *host* pointer to 4 floats.
+  const float4 b = make_float4(bias[0], bias[1], bias[2], bias[3]);
+  if (act.dt == DT_F16)
+    out_conv_kernel<__half><<<grid, 256, 0, st>>>((const __half*)act.p, act.N, act.H, act.W, act.C, (const float4*)w, b, addend, out);
+  else
+    out_conv_kernel<float><<<grid, 256, 0, st>>>((const float*)act.p, act.N, act.H, act.W, act.C, (const float4*)w, b, addend, out);
+  CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace sgmse

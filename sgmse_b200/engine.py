@@ -1,0 +1,305 @@
+"""Python host side of the engine: a thin object over the C-ABI (sgmse_b200/_lib.py).
+
+PyTorch is used here only as the owner of device memory and streams; all arithmetic happens in
+libsgmse_b200.so.  Mirrors the argument names/meaning of the reference interfaces it stands behind
+(``ScoreModel.get_pc_sampler`` /root/reference/sgmse/model.py:348-368, ``ScoreModel.enhance`` :426-465,
+``NCSNpp.forward`` backbones/ncsnpp.py:256).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+MODES = {"fp32": 0, "fp16_direct": 1, "fp16_tc": 2}
+PREDICTORS = {"reverse_diffusion": 0, "euler_maruyama": 1, "none": 2}
+CORRECTORS = {"ald": 0, "langevin": 1, "none": 2}
+PAD_MODES = {"zero_pad": 0, "reflection": 1}
+
+
+def _lookup(table: Dict[str, int], name: str, what: str) -> int:
+    # same error behaviour as Registry.get_by_name (/root/reference/sgmse/util/registry.py:25-30)
+    if name in table:
+        return table[name]
+    raise ValueError(f"{what} with name '{name}' unknown.")
+
+
+@dataclass
+class EngineConfig:
+    backbone: str = "ncsnpp"                       # 'ncsnpp' | 'ncsnpp_48k'
+    nf: int = 128
+    ch_mult: Sequence[int] = (1, 1, 2, 2, 2, 2, 2)
+    num_res_blocks: int = 2
+    attn_resolutions: Sequence[int] = (16,)
+    image_size: int = 256
+    progressive: str = "output_skip"
+    progressive_input: str = "input_skip"
+    scale_by_sigma: bool = True
+    theta: float = 1.5
+    sigma_min: float = 0.05
+    sigma_max: float = 0.5
+    t_eps: float = 0.03
+    n_fft: int = 510
+    hop_length: int = 128
+    window: str = "hann"
+    spec_factor: float = 0.15
+    spec_abs_exponent: float = 0.5
+    sr: int = 16000
+    mode: str = "fp16_tc"
+    max_batch: int = 8
+    use_graphs: bool = True
+
+    @staticmethod
+    def ncsnpp_16k(**kw) -> "EngineConfig":
+        return EngineConfig(**kw)
+
+    @staticmethod
+    def ncsnpp_48k(**kw) -> "EngineConfig":
+        # README.md:89 of the reference (EARS-WHAM): --backbone ncsnpp_48k --n_fft 1534 --hop_length 384 ...
+        base = dict(backbone="ncsnpp_48k", attn_resolutions=(), progressive="none", progressive_input="none",
+                    theta=2.0, sigma_min=0.1, sigma_max=1.0, n_fft=1534, hop_length=384, spec_factor=0.065,
+                    spec_abs_exponent=0.667, sr=48000)
+        base.update(kw)
+        return EngineConfig(**base)
+
+    def to_c(self) -> _lib.Config:
+        if self.backbone not in ("ncsnpp", "ncsnpp_48k"):
+            raise ValueError(f"Backbone with name '{self.backbone}' unknown.")
+        if self.progressive not in ("output_skip", "none") or self.progressive_input not in ("input_skip", "none"):
+            raise NotImplementedError("only progressive in {output_skip, none} / progressive_input in {input_skip, none}")
+        if len(self.ch_mult) > 8 or len(self.attn_resolutions) > 8:
+            raise ValueError("at most 8 levels / attention resolutions")
+        c = _lib.Config()
+        c.backbone = 0 if self.backbone == "ncsnpp" else 1
+        c.nf = self.nf
+        c.num_levels = len(self.ch_mult)
+        for i, m in enumerate(self.ch_mult):
+            c.ch_mult[i] = int(m)
+        c.num_res_blocks = self.num_res_blocks
+        c.num_attn_resolutions = len(self.attn_resolutions)
+        for i, r in enumerate(self.attn_resolutions):
+            c.attn_resolutions[i] = int(r)
+        c.image_size = self.image_size
+        c.progressive_output_skip = int(self.progressive == "output_skip")
+        c.progressive_input_skip = int(self.progressive_input == "input_skip")
+        c.scale_by_sigma = int(self.scale_by_sigma)
+        c.theta, c.sigma_min, c.sigma_max, c.t_eps = self.theta, self.sigma_min, self.sigma_max, self.t_eps
+        c.n_fft, c.hop_length = self.n_fft, self.hop_length
+        c.sqrt_window = int(_lookup({"hann": 0, "sqrthann": 1}, self.window, "Window"))
+        c.spec_factor, c.spec_abs_exponent, c.sample_rate = self.spec_factor, self.spec_abs_exponent, self.sr
+        c.mode = _lookup(MODES, self.mode, "Mode")
+        c.max_batch = self.max_batch
+        c.use_graphs = int(self.use_graphs)
+        return c
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Engine:
+    """One engine per (process, device)."""
+
+    def __init__(self, cfg: EngineConfig, device: Optional[torch.device] = None):
+        self.cfg = cfg
+        self.lib = _lib.load()
+        self.device = torch.device(device) if device is not None else None
+        self._h = C.c_void_p()
+        self._ccfg = cfg.to_c()
+        _lib.check(self.lib.sgmse_b200_create(C.byref(self._ccfg), C.byref(self._h)))
+        self.F = cfg.n_fft // 2 + 1
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.sgmse_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def manifest(self) -> List[Tuple[str, int]]:
+        n = self.lib.sgmse_b200_manifest_count(self._h)
+        out = []
+        buf = C.create_string_buffer(256)
+        num = C.c_longlong()
+        for i in range(n):
+            _lib.check(self.lib.sgmse_b200_manifest_entry(self._h, i, buf, 256, C.byref(num)))
+            out.append((buf.value.decode(), int(num.value)))
+        return out
+
+    def weights_numel(self) -> int:
+        return int(self.lib.sgmse_b200_weights_numel(self._h))
+
+    def flatten_state_dict(self, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """fp32 CPU blob in manifest (= ``state_dict()``) order; verifies names and sizes."""
+        man = self.manifest()
+        missing = [k for k, _ in man if k not in sd]
+        if missing:
+            raise KeyError(f"state dict lacks {len(missing)} keys the engine expects, e.g. {missing[:3]}")
+        extra = [k for k in sd if k not in dict(man)]
+        if extra:
+            raise KeyError(f"state dict has {len(extra)} keys the engine does not know, e.g. {extra[:3]}")
+        parts = []
+        for k, n in man:
+            t = sd[k]
+            if t.numel() != n:
+                raise ValueError(f"{k}: expected {n} elements, state dict has {tuple(t.shape)}")
+            parts.append(t.detach().reshape(-1).to(dtype=torch.float32, device="cpu"))
+        return torch.cat(parts).contiguous()
+
+    def _use_device(self):
+        if self.device is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+
+    def load_blob(self, blob: torch.Tensor):
+        self._use_device()
+        blob = blob.contiguous()
+        if blob.dtype != torch.float32:
+            raise TypeError("weight blob must be float32")
+        if blob.is_cuda:
+            _lib.check(self.lib.sgmse_b200_load_weights_device(self._h, blob.data_ptr(), blob.numel(), _stream_ptr()))
+        else:
+            _lib.check(self.lib.sgmse_b200_load_weights(self._h, blob.data_ptr(), blob.numel()))
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        self.load_blob(self.flatten_state_dict(sd))
+
+    # ---- network ---------------------------------------------------------------------------------
+    @staticmethod
+    def _c64(x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("sgmse_b200: expected a CUDA tensor (there is no CPU path)")
+        return x.to(torch.complex64).contiguous()
+
+    def dnn_forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """Backbone contract: c64 [B,2,F,T], f32 [B] -> c64 [B,1,F,T]."""
+        self._use_device()
+        x = self._c64(x)
+        B, two, F, T = x.shape
+        assert two == 2
+        t = t.to(device=x.device, dtype=torch.float32).contiguous()
+        out = torch.empty((B, 1, F, T), dtype=torch.complex64, device=x.device)
+        _lib.check(self.lib.sgmse_b200_dnn_forward(self._h, x.data_ptr(), t.data_ptr(), out.data_ptr(), B, F, T, _stream_ptr()))
+        return out
+
+    def score(self, x_t: torch.Tensor, y: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """ScoreModel.forward (legacy branch): -dnn(cat[x_t, y], t)."""
+        x_t, y = self._c64(x_t), self._c64(y)
+        self._use_device()
+        B, _, F, T = y.shape
+        t = t.to(device=y.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(y)
+        _lib.check(self.lib.sgmse_b200_score(self._h, x_t.data_ptr(), y.data_ptr(), t.data_ptr(), out.data_ptr(), B, F, T, _stream_ptr()))
+        return out
+
+    # ---- sampler ---------------------------------------------------------------------------------
+    def sampler_struct(self, N=30, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.5,
+                       denoise=True, probability_flow=False, seed=0, utt_offset=0, pad_mode="zero_pad") -> _lib.Sampler:
+        s = _lib.Sampler()
+        s.N = int(N)
+        s.predictor = _lookup(PREDICTORS, predictor, "Predictor")
+        s.corrector = _lookup(CORRECTORS, corrector, "Corrector")
+        s.corrector_steps = int(corrector_steps)
+        s.snr = float(snr)
+        s.denoise = int(bool(denoise))
+        s.probability_flow = int(bool(probability_flow))
+        s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        s.utt_offset = int(utt_offset)
+        s.pad_mode = _lookup(PAD_MODES, pad_mode, "Pad mode")
+        return s
+
+    def noise_draws(self, **kw) -> int:
+        s = self.sampler_struct(**kw)
+        return int(self.lib.sgmse_b200_noise_draws(C.byref(s)))
+
+    def pc_sample(self, y: torch.Tensor, noise: Optional[torch.Tensor] = None, **kw):
+        """y c64 [B,1,F,T] -> (sample c64 [B,1,F,T], nfe).  ``noise``: optional c64 [draws,B,1,F,T]."""
+        self._use_device()
+        y = self._c64(y)
+        B, _, F, T = y.shape
+        s = self.sampler_struct(**kw)
+        nptr = None
+        if noise is not None:
+            noise = self._c64(noise)
+            need = int(self.lib.sgmse_b200_noise_draws(C.byref(s)))
+            if tuple(noise.shape) != (need, B, 1, F, T):
+                raise ValueError(f"noise must have shape {(need, B, 1, F, T)}, got {tuple(noise.shape)}")
+            nptr = noise.data_ptr()
+        out = torch.empty_like(y)
+        nfe = C.c_int()
+        _lib.check(self.lib.sgmse_b200_pc_sample(self._h, y.data_ptr(), B, F, T, C.byref(s), nptr, out.data_ptr(),
+                                                 C.byref(nfe), _stream_ptr()))
+        return out, int(nfe.value)
+
+    # ---- STFT chain ------------------------------------------------------------------------------
+    def padded_frames(self, L: int) -> int:
+        return int(self.lib.sgmse_b200_padded_frames(self._h, int(L)))
+
+    def analysis(self, wav: torch.Tensor, pad_mode="zero_pad"):
+        """wav f32 [B,L] (cuda) -> (Y c64 [B,1,F,Tpad], norm f32 [B])."""
+        self._use_device()
+        wav = wav.to(torch.float32).contiguous()
+        B, L = wav.shape
+        Tp = self.padded_frames(L)
+        Y = torch.empty((B, 1, self.F, Tp), dtype=torch.complex64, device=wav.device)
+        norm = torch.empty((B,), dtype=torch.float32, device=wav.device)
+        _lib.check(self.lib.sgmse_b200_analysis(self._h, wav.data_ptr(), B, L, _lookup(PAD_MODES, pad_mode, "Pad mode"),
+                                                Y.data_ptr(), norm.data_ptr(), _stream_ptr()))
+        return Y, norm
+
+    def synthesis(self, X: torch.Tensor, norm: torch.Tensor, length: int) -> torch.Tensor:
+        self._use_device()
+        X = self._c64(X)
+        B, _, F, Tp = X.shape
+        wav = torch.empty((B, length), dtype=torch.float32, device=X.device)
+        _lib.check(self.lib.sgmse_b200_synthesis(self._h, X.data_ptr(), norm.contiguous().data_ptr(), B, Tp, int(length),
+                                                 wav.data_ptr(), _stream_ptr()))
+        return wav
+
+    def enhance(self, wav: torch.Tensor, noise: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, **kw):
+        """One call: wav f32 [B,L] (host or device) -> enhanced wav [B,L] on the same side.
+        Host tensors (ideally pinned) make the H2D/D2H copies part of the call (sgmse_b200_enhance)."""
+        self._use_device()
+        wav = wav.to(torch.float32).contiguous()
+        B, L = wav.shape
+        host = not wav.is_cuda
+        if out is None:
+            out = torch.empty_like(wav, pin_memory=True) if host else torch.empty_like(wav)
+        s = self.sampler_struct(**kw)
+        nptr = None
+        if noise is not None:
+            noise = self._c64(noise)
+            nptr = noise.data_ptr()
+        _lib.check(self.lib.sgmse_b200_enhance(self._h, wav.data_ptr(), B, L, C.byref(s), nptr, out.data_ptr(), int(host),
+                                               _stream_ptr()))
+        return out
+
+    # ---- introspection ---------------------------------------------------------------------------
+    def set_option(self, key: str, value: int):
+        _lib.check(self.lib.sgmse_b200_set_option(self._h, key.encode(), int(value)))
+
+    def workspace_bytes(self, B: int, F: int, T: int) -> int:
+        n = int(self.lib.sgmse_b200_workspace_bytes(self._h, B, F, T))
+        if n < 0:
+            _lib.check(1)
+        return n
+
+    def counter(self, key: str) -> int:
+        return int(self.lib.sgmse_b200_get_counter(self._h, key.encode()))
+
+    def tap(self, name: str) -> torch.Tensor:
+        shape = (C.c_int * 4)()
+        _lib.check(self.lib.sgmse_b200_get_tap(self._h, name.encode(), None, 0, C.byref(shape)))
+        n = shape[0] * shape[1] * shape[2] * shape[3]
+        out = torch.empty(tuple(shape), dtype=torch.float32)
+        _lib.check(self.lib.sgmse_b200_get_tap(self._h, name.encode(), out.data_ptr(), n, C.byref(shape)))
+        return out

@@ -1,0 +1,205 @@
+"""GPU parity tests: the CUDA engine (through the C-ABI) against the CPU oracle and the committed
+reference golden fixtures.  Run on the B200 box: ``pytest -m gpu``.
+
+Tolerances (stated, per north_star):
+  * mode fp32 (CUDA-core validation path): rel-L2 <= 2e-4 per forward vs the fp32 CPU oracle,
+    <= 1e-3 after an N=3 sampler run;
+  * mode fp16_tc (product path: fp16 activations, tcgen05 MMA with fp32 accumulation -- the same 10-bit
+    mantissa as the TF32 cuDNN path the reference itself takes on a GPU): rel-L2 <= 2e-2 per forward.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ncsnpp as o_net, sde as o_sde, spec as o_spec, pipeline as o_pipe, weights as o_w
+from oracle.arch import NetConfig
+from sgmse_b200 import Engine, EngineConfig
+
+pytestmark = pytest.mark.gpu
+
+SMALL_N = dict(nf=16, ch_mult=(1, 2, 2), image_size=64, num_res_blocks=2)
+SMALL_E = dict(nf=16, ch_mult=(1, 2, 2), image_size=64, num_res_blocks=2, n_fft=126, hop_length=32)
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).cpu(), torch.as_tensor(b).cpu()
+    return (torch.linalg.vector_norm((a - b).reshape(-1)) / torch.linalg.vector_norm(b.reshape(-1))).item()
+
+
+def load_golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w/")}
+    return z, sd
+
+
+def small_engine(kind, mode, **kw):
+    if kind == "ncsnpp_small":
+        return Engine(EngineConfig(attn_resolutions=(16,), mode=mode, **SMALL_E, **kw))
+    return Engine(EngineConfig.ncsnpp_48k(mode=mode, theta=1.5, sigma_min=0.05, sigma_max=0.5, spec_factor=0.15,
+                                          spec_abs_exponent=0.5, **SMALL_E, **kw))
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures (outputs of the unmodified reference), small configs, every arithmetic mode that
+# supports 16/32-channel layers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ncsnpp_small", "ncsnpp48k_small"])
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("fp16_direct", 2e-2)])
+def test_golden_forward_and_score(golden_dir, name, mode, tol):
+    z, sd = load_golden(golden_dir, name)
+    eng = small_engine(name, mode)
+    eng.load_state_dict(sd)
+    x, y, t = (torch.from_numpy(z[k]).cuda() for k in ("x", "y", "t"))
+    out = eng.dnn_forward(torch.cat([x, y], 1), t)
+    assert rel_l2(out, z["dnn_out"]) < tol
+    assert rel_l2(eng.score(x, y, t), z["score"]) < tol
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["ncsnpp_small", "ncsnpp48k_small"])
+@pytest.mark.parametrize("pred,corr", [("reverse_diffusion", "ald"), ("reverse_diffusion", "langevin"),
+                                       ("none", "ald"), ("reverse_diffusion", "none")])
+def test_golden_pc_sampler(golden_dir, name, pred, corr):
+    z, sd = load_golden(golden_dir, name)
+    eng = small_engine(name, "fp32")
+    eng.load_state_dict(sd)
+    y = torch.from_numpy(z["y"]).cuda()
+    N = 3
+    draws = o_sde.make_noise(tuple(y.shape), o_sde.n_noise_draws(N, pred, corr, 1), seed=7)
+    noise = torch.stack(draws).cuda()
+    smp, nfe = eng.pc_sample(y, noise=noise, N=N, predictor=pred, corrector=corr, corrector_steps=1, snr=0.5)
+    assert nfe == int(z[f"nfe_{pred}_{corr}"])
+    assert rel_l2(smp, z[f"pc_{pred}_{corr}"]) < 1e-3
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["ncsnpp_small", "ncsnpp48k_small"])
+def test_golden_enhance_chain(golden_dir, name):
+    z, sd = load_golden(golden_dir, name)
+    eng = small_engine(name, "fp32")
+    eng.load_state_dict(sd)
+    wav = torch.from_numpy(z["wav"])
+    B, N = wav.shape[0], 3
+    draws = o_sde.make_noise((B, 1, 64, 64), o_sde.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=11)
+    Y, norm = eng.analysis(wav.cuda())
+    assert rel_l2(Y, z["Y"]) < 1e-4
+    xh = eng.enhance(wav.cuda(), noise=torch.stack(draws).cuda(), N=N)
+    assert rel_l2(xh, z["enh"]) < 2e-3
+    # host-buffer entry point (H2D/D2H inside the call) gives the same result
+    xh2 = eng.enhance(wav.pin_memory(), noise=torch.stack(draws).cuda(), N=N)
+    assert torch.equal(xh.cpu(), xh2)
+    eng.close()
+
+
+def test_golden_stft_ops(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ops.npz"))
+    eng = Engine(EngineConfig(mode="fp32", **SMALL_E))
+    wav = torch.from_numpy(z["wav"]).cuda()
+    Y, norm = eng.analysis(wav)
+    nrm = torch.from_numpy(z["wav"]).abs().amax(dim=1)
+    assert torch.allclose(norm.cpu(), nrm)
+    # reference chain on the normalised waveform
+    scfg = o_spec.SpecConfig(n_fft=126, hop_length=32)
+    Yo = o_spec.pad_spec(o_spec.spec_fwd(o_spec.stft(torch.from_numpy(z["wav"]) / nrm[:, None], scfg), scfg))[:, None]
+    assert rel_l2(Y, Yo) < 1e-5
+    # synthesis(analysis(x)) == x  (round trip through compression, padding and overlap-add)
+    back = eng.synthesis(Y, norm, 2000)
+    assert rel_l2(back, z["wav"]) < 1e-4
+    eng.close()
+    e48 = Engine(EngineConfig.ncsnpp_48k(mode="fp32"))
+    w48 = torch.from_numpy(z["wav48"]).cuda()
+    Y48, n48 = e48.analysis(w48, pad_mode="reflection")
+    s48 = o_spec.SpecConfig.cfg_48k()
+    nrm48 = torch.from_numpy(z["wav48"]).abs().amax(dim=1)
+    Yo48 = o_spec.pad_spec(o_spec.spec_fwd(o_spec.stft(torch.from_numpy(z["wav48"]) / nrm48[:, None], s48), s48)[:, None], "reflection")
+    assert Y48.shape == Yo48.shape
+    assert rel_l2(Y48, Yo48) < 1e-5
+    assert rel_l2(e48.synthesis(Y48, n48, 6000), z["wav48"]) < 1e-4
+    e48.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# per-module parity (oracle taps) on a mid-size config that exercises the tcgen05 path (C = 64..256)
+# ------------------------------------------------------------------------------------------------
+MID_N = NetConfig.ncsnpp(nf=64, ch_mult=(1, 2, 2), image_size=64, attn_resolutions=(16,), num_res_blocks=1)
+MID_E = dict(nf=64, ch_mult=(1, 2, 2), image_size=64, attn_resolutions=(16,), num_res_blocks=1, n_fft=126, hop_length=32)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("fp16_direct", 2e-2), ("fp16_tc", 2e-2)])
+def test_per_module_taps_mid(mode, tol):
+    sd = o_w.make_state_dict(MID_N, seed=5)
+    eng = Engine(EngineConfig(mode=mode, **MID_E))
+    eng.load_state_dict(sd)
+    eng.set_option("record_taps", 1)
+    g = torch.Generator().manual_seed(3)
+    B, F, T = 3, 64, 128
+    x = torch.complex(torch.randn(B, 2, F, T, generator=g), torch.randn(B, 2, F, T, generator=g)) * 0.4
+    t = torch.tensor([0.9, 0.35, 0.05])
+    taps = {}
+    ref = o_net.forward(sd, MID_N, x, t, taps=taps)
+    out = eng.dnn_forward(x.cuda(), t.cuda())
+    if mode == "fp16_tc":
+        assert eng.counter("tc_convs_last_forward") > 0
+    worst = []
+    for name, v in taps.items():
+        if name == "temb":
+            continue
+        got = eng.tap(name)
+        worst.append((rel_l2(got, v), name))
+    worst.sort(reverse=True)
+    assert worst[0][0] < tol, worst[:5]
+    assert rel_l2(out, ref) < tol
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size network (VoiceBank config, 65.6 M parameters): product path vs oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_sd():
+    return o_w.make_state_dict(NetConfig.ncsnpp(), seed=0)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("fp16_tc", 2e-2)])
+def test_full_size_forward(full_sd, mode, tol):
+    cfg = NetConfig.ncsnpp()
+    eng = Engine(EngineConfig(mode=mode, max_batch=2))
+    eng.load_state_dict(full_sd)
+    g = torch.Generator().manual_seed(11)
+    B, F, T = 1, 256, 128
+    x = torch.complex(torch.randn(B, 2, F, T, generator=g), torch.randn(B, 2, F, T, generator=g)) * 0.3
+    t = torch.tensor([0.5])
+    with torch.no_grad():
+        ref = o_net.forward(full_sd, cfg, x, t)
+    out = eng.dnn_forward(x.cuda(), t.cuda())
+    assert rel_l2(out, ref) < tol
+    if mode == "fp16_tc":
+        assert eng.counter("direct_convs_last_forward") == 0
+    eng.close()
+
+
+def test_full_size_sampler_properties(full_sd):
+    """Size-independent properties at the benchmark shape [B,1,256,512]:
+    graph replay == eager launch sequence (bitwise), outputs do not depend on how the batch is split into
+    micro-batches (noise is keyed by global utterance id), and a different seed changes the result."""
+    eng = Engine(EngineConfig(mode="fp16_tc", max_batch=2, use_graphs=True))
+    eng.load_state_dict(full_sd)
+    g = torch.Generator().manual_seed(1)
+    B, F, T = 3, 256, 512
+    y = (torch.complex(torch.randn(B, 1, F, T, generator=g), torch.randn(B, 1, F, T, generator=g)) * 0.1).cuda()
+    a, nfe = eng.pc_sample(y, N=2, seed=1234)
+    assert nfe == 4 and torch.isfinite(torch.view_as_real(a)).all()
+    b, _ = eng.pc_sample(y, N=2, seed=1234)                  # graph replay
+    assert torch.equal(a, b)
+    eng.set_option("use_graphs", 0)
+    c, _ = eng.pc_sample(y, N=2, seed=1234)                  # eager
+    assert torch.equal(a, c)
+    d, _ = eng.pc_sample(y[1:2], N=2, seed=1234, utt_offset=1)   # utterance 1 alone
+    assert torch.equal(a[1:2], d)
+    e, _ = eng.pc_sample(y, N=2, seed=99)
+    assert not torch.equal(a, e)
+    assert eng.counter("graph_launches") >= 2
+    eng.close()
