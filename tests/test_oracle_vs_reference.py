@@ -1,0 +1,80 @@
+"""Live comparison of the oracle and the host-side boundary with the UNMODIFIED reference imported from
+/root/reference (build container only; skipped on the GPU box where the reference does not exist)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import refshim, ncsnpp as o_net, sde as o_sde, spec as o_spec, pipeline as o_pipe
+from oracle.arch import NetConfig, state_dict_manifest
+
+pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def model16k():
+    return refshim.make_score_model("ncsnpp", seed=0)
+
+
+def test_full_size_forward_matches_reference(model16k):
+    cfg = NetConfig.ncsnpp()
+    sd = model16k.dnn.state_dict()
+    assert [k for k, _ in state_dict_manifest(cfg)] == list(sd.keys())
+    g = torch.Generator().manual_seed(0)
+    x = torch.complex(torch.randn(1, 2, 256, 64, generator=g), torch.randn(1, 2, 256, 64, generator=g)) * 0.3
+    t = torch.tensor([0.4])
+    with torch.no_grad():
+        ref = model16k.dnn(x, t)
+        got = o_net.forward(sd, cfg, x, t)
+    assert ((ref - got).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+def test_sde_scalars_match_reference(model16k):
+    sde = model16k.sde
+    o = o_sde.OUVE()
+    for t in (1.0, 0.5, 0.03):
+        tt = torch.tensor([t])
+        assert abs(float(sde._std(tt)) - o.std(t)) < 1e-6
+        assert abs(float(sde.sde(torch.zeros(1), torch.zeros(1), tt)[1]) - o.diffusion(t)) < 1e-6
+    assert abs(o.std(1.0) - 0.38898) < 1e-4
+
+
+def test_config_is_recovered_from_a_live_score_model(model16k):
+    from sgmse_b200 import config_from_score_model, Engine
+    cfg = config_from_score_model(model16k, mode="fp16_tc", max_batch=4)
+    assert cfg.backbone == "ncsnpp" and cfg.nf == 128 and tuple(cfg.ch_mult) == (1, 1, 2, 2, 2, 2, 2)
+    assert tuple(cfg.attn_resolutions) == (16,) and cfg.image_size == 256 and cfg.num_res_blocks == 2
+    assert (cfg.n_fft, cfg.hop_length, cfg.window) == (510, 128, "hann")
+    assert abs(cfg.theta - 1.5) < 1e-9 and abs(cfg.t_eps - 0.03) < 1e-9
+    eng = Engine(cfg)
+    blob = eng.flatten_state_dict(model16k.dnn.state_dict())      # names, order and sizes all agree
+    assert blob.numel() == sum(p.numel() for p in model16k.dnn.state_dict().values())
+    eng.close()
+
+
+def test_config_48k():
+    from sgmse_b200 import config_from_score_model, Engine
+    m = refshim.make_score_model("ncsnpp_48k", seed=0, n_fft=1534, hop_length=384, spec_factor=0.065,
+                                 spec_abs_exponent=0.667, theta=2.0, sigma_min=0.1, sigma_max=1.0)
+    cfg = config_from_score_model(m)
+    assert cfg.backbone == "ncsnpp_48k" and cfg.progressive == "none" and cfg.progressive_input == "none"
+    assert tuple(cfg.attn_resolutions) == () and cfg.n_fft == 1534
+    eng = Engine(cfg)
+    assert eng.flatten_state_dict(m.dnn.state_dict()).numel() == eng.weights_numel()
+    eng.close()
+
+
+def test_enhance_chain_matches_reference_sequence(model16k):
+    """Oracle pipeline vs the enhancement.py:75-96 sequence of the reference, N=1, injected noise, short clip."""
+    from sgmse.util.other import pad_spec
+    g = torch.Generator().manual_seed(4)
+    L = 8000                                   # 63 frames -> padded to 64
+    wav = 0.1 * torch.randn(1, L, generator=g)
+    draws = o_sde.make_noise((1, 1, 256, 64), 3, seed=5)
+    norm = wav.abs().max()
+    Y = pad_spec(torch.unsqueeze(model16k._forward_transform(model16k._stft(wav / norm)), 0))
+    with refshim.injected_noise(draws):
+        smp, nfe = model16k.get_pc_sampler("reverse_diffusion", "ald", Y, N=1, corrector_steps=1, snr=0.5)()
+    ref = model16k.to_audio(smp.squeeze(), L) * norm
+    got = o_pipe.enhance(model16k.dnn.state_dict(), NetConfig.ncsnpp(), o_spec.SpecConfig(), o_sde.OUVE(), wav, draws, N=1)
+    assert nfe == 2
+    assert ((ref - got[0]).abs().max() / ref.abs().max()).item() < 1e-3
