@@ -90,7 +90,8 @@ def pad_spec(Y: torch.Tensor, mode: str = "zero_pad") -> torch.Tensor:
     if mode == "zero_pad":
         return torch.nn.functional.pad(Y, (0, num_pad))
     if mode == "reflection":
-        re = torch.nn.functional.pad(Y.real, (0, num_pad), mode="reflect")
-        im = torch.nn.functional.pad(Y.imag, (0, num_pad), mode="reflect")
+        pad = (0, num_pad, 0, 0) if Y.dim() == 4 else (0, num_pad)
+        re = torch.nn.functional.pad(Y.real, pad, mode="reflect")
+        im = torch.nn.functional.pad(Y.imag, pad, mode="reflect")
         return torch.complex(re, im)
     raise NotImplementedError(mode)

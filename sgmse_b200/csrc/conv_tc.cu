@@ -315,8 +315,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
 }
 
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------
-// host side
+// host side (tensor-map helpers are shared with conv_tc2.cu)
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -388,6 +390,8 @@ int num_sms() {
   return n;
 }
 
+namespace {
+
 template <int BLOCK_N, int NUM_STAGES>
 void launch_impl(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   using L = SmemLayout<BLOCK_N, NUM_STAGES>;
@@ -435,6 +439,8 @@ void launch_impl(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) 
 
 }  // namespace
 
+int g_tc_variant = 0;   // 0: operand-reuse kernel (conv_tc2.cu) where it applies, 1: always the v1 kernel
+
 bool conv_tc_supported(const ConvArgs& a, const TensorDesc& out) {
   if (out.dt != DT_F16 || out.C % 64 != 0 || a.w_tc == nullptr) return false;
   for (int i = 0; i < a.nseg; ++i)
@@ -450,6 +456,7 @@ void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* db
     SG_CHECK(s.N == out.N && s.H == out.H && s.W == out.W, "conv_tc: segment %d shape mismatch", i);
   }
   if (a.residual) SG_CHECK(a.residual->C == out.C && a.residual->dt == DT_F16, "conv_tc: residual mismatch");
+  if (g_tc_variant != 1 && conv_tc2_supported(a, out)) { launch_conv_tc2(st, a, out, dbg); return; }
   if (out.C % 128 == 0) launch_impl<128, 5>(st, a, out, dbg);
   else launch_impl<64, 6>(st, a, out, dbg);
 }

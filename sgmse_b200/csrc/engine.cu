@@ -892,6 +892,7 @@ int sgmse_b200_create(const sgmse_b200_config* cfg, sgmse_b200_engine** out) {
   std::unique_ptr<Engine> e(new Engine());
   e->cfg = *cfg;
   if (e->cfg.max_batch <= 0) e->cfg.max_batch = 8;
+  if (const char* v = getenv("SGMSE_B200_TC_VARIANT")) sgmse::g_tc_variant = atoi(v);   // A/B switch for profiling
   SG_CHECK(cfg->mode >= 0 && cfg->mode <= 2, "unknown mode %d", cfg->mode);
   build_network(*e);
   *out = e.release();
@@ -1059,6 +1060,7 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
     e->time_convs = value != 0;
   }
   else if (k == "use_graphs") e->cfg.use_graphs = value != 0;
+  else if (k == "tc_variant") { sgmse::g_tc_variant = (int)value; clear_graphs(*e); }
   else if (k == "tc_mask") { e->tc_mask = value; for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec); e->graphs.clear(); }
   else SG_CHECK(false, "unknown option '%s'", key);
   API_END

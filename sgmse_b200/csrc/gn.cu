@@ -107,96 +107,135 @@ void launch_channel_stats(cudaStream_t st, TensorDesc& t) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// gn_apply: one thread = one output pixel x 8 channels.
+// gn_apply (no resampling): y = [silu](a*x + b), optional channel concat of two sources.
+// grid (blocks, N); a thread owns one fixed group of 8 channels (its a/b live in registers) and walks pixels,
+// so the inner loop is 128-bit load -> 8 x (fma, silu) -> 128-bit store with no index arithmetic.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int RS, bool SILU, bool RAW>
+template <typename T, bool SILU>
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1, int C1,
-                const float2* __restrict__ ab, int N, int Hi, int Wi, T* __restrict__ out0,
-                T* __restrict__ out1) {
-  const int Ct = C0 + C1;
-  const int cv_per_px = Ct >> 3;
-  const int Ho = RS == RS_DOWN ? Hi / 2 : (RS == RS_UP ? Hi * 2 : Hi);
-  const int Wo = RS == RS_DOWN ? Wi / 2 : (RS == RS_UP ? Wi * 2 : Wi);
-  const size_t total = (size_t)N * Ho * Wo * cv_per_px;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % cv_per_px);
-    size_t pix = idx / cv_per_px;
-    const int X = (int)(pix % Wo); pix /= Wo;
-    const int Y = (int)(pix % Ho);
-    const int n = (int)(pix / Ho);
-    const int c = cv << 3;
-    const T* src; int Cs, cs;
-    if (c < C0) { src = x0; Cs = C0; cs = c; } else { src = x1; Cs = C1; cs = c - C0; }
-    float a[8], b[8];
-    {
-      const float4* p = reinterpret_cast<const float4*>(ab + (size_t)n * Ct + c);
+gn_apply_plain_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1, int C1,
+                      const float2* __restrict__ ab, int HW, T* __restrict__ out) {
+  const int Ct = C0 + C1, cvpp = Ct >> 3;
+  const int ppb = blockDim.x / cvpp;
+  const int cv = threadIdx.x % cvpp, pl = threadIdx.x / cvpp;
+  if (pl >= ppb) return;
+  const int n = blockIdx.y;
+  const int c = cv << 3;
+  const T* src; int Cs, cs;
+  if (c < C0) { src = x0; Cs = C0; cs = c; } else { src = x1; Cs = C1; cs = c - C0; }
+  float a[8], b[8];
+  {
+    const float4* p = reinterpret_cast<const float4*>(ab + (size_t)n * Ct + c);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { float4 v = p[i]; a[2 * i] = v.x; b[2 * i] = v.y; a[2 * i + 1] = v.z; b[2 * i + 1] = v.w; }
-    }
-    float acc[8], raw[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i] = 0.f; raw[i] = 0.f; }
-    auto tap = [&](int y, int x, float w) {
-      if ((unsigned)y >= (unsigned)Hi || (unsigned)x >= (unsigned)Wi) return;
-      Vec8<T> v; float f[8];
-      v.load(src + (((size_t)n * Hi + y) * Wi + x) * Cs + cs);
-      v.get(f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float h = fmaf(a[i], f[i], b[i]);
-        if (SILU) h = silu_f(h);
-        acc[i] = fmaf(w, h, acc[i]);
-        if (RAW) raw[i] = fmaf(w, f[i], raw[i]);
-      }
-    };
-    if (RS == RS_NONE) {
-      tap(Y, X, 1.f);
-    } else if (RS == RS_DOWN) {
-      // out[Y,X] = sum_{i,j} k[i]k[j] h[2Y+i-1, 2X+j-1], k = [1,3,3,1]/8, zero outside
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tap(2 * Y + i - 1, 2 * X + j - 1, fir_tap(i) * fir_tap(j));
-    } else {
-      // zero-insert x2, pad (2,1), FIR [1,3,3,1]/4 per axis:
-      //   even Y=2y: 3/4 h[y] + 1/4 h[y-1];  odd Y=2y+1: 3/4 h[y] + 1/4 h[y+1]
-      const int y0 = Y >> 1, x0i = X >> 1;
-      const int y1 = (Y & 1) ? y0 + 1 : y0 - 1;
-      const int x1i = (X & 1) ? x0i + 1 : x0i - 1;
-      tap(y0, x0i, 0.5625f);
-      tap(y0, x1i, 0.1875f);
-      tap(y1, x0i, 0.1875f);
-      tap(y1, x1i, 0.0625f);
-    }
-    Vec8<T> o;
-    o.set(acc);
-    o.store(out0 + idx * 8);
-    if (RAW) { o.set(raw); o.store(out1 + idx * 8); }
+    for (int i = 0; i < 4; ++i) { float4 v = p[i]; a[2 * i] = v.x; b[2 * i] = v.y; a[2 * i + 1] = v.z; b[2 * i + 1] = v.w; }
   }
+  const T* sp = src + (size_t)n * HW * Cs + cs;
+  T* op = out + (size_t)n * HW * Ct + c;
+  for (int p = blockIdx.x * ppb + pl; p < HW; p += gridDim.x * ppb) {
+    Vec8<T> v; float f[8];
+    v.load(sp + (size_t)p * Cs);
+    v.get(f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float h = fmaf(a[i], f[i], b[i]);
+      if (SILU) h = silu_f(h);
+      f[i] = h;
+    }
+    v.set(f);
+    v.store(op + (size_t)p * Ct);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gn_apply + FIR up/down: one thread = one output pixel x 8 channels; grid (blocks, N).
+// out0 = FIR(silu(a*x+b)), out1 = FIR(x) (the ResBlock shortcut input), one read of x.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RS>
+__global__ void __launch_bounds__(256)
+gn_apply_fir_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ ab, int Hi, int Wi,
+                    T* __restrict__ out0, T* __restrict__ out1) {
+  const int cvpp = C >> 3;
+  const int Ho = RS == RS_DOWN ? Hi / 2 : Hi * 2;
+  const int Wo = RS == RS_DOWN ? Wi / 2 : Wi * 2;
+  const int n = blockIdx.y;
+  const unsigned total = (unsigned)Ho * Wo * cvpp;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = idx % cvpp;
+  const unsigned pix = idx / cvpp;
+  const int X = pix % Wo, Y = pix / Wo;
+  const int c = cv << 3;
+  float a[8], b[8];
+  {
+    const float4* p = reinterpret_cast<const float4*>(ab + (size_t)n * C + c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float4 v = p[i]; a[2 * i] = v.x; b[2 * i] = v.y; a[2 * i + 1] = v.z; b[2 * i + 1] = v.w; }
+  }
+  const T* src = x0 + (size_t)n * Hi * Wi * C + c;
+  float acc[8], raw[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i] = 0.f; raw[i] = 0.f; }
+  auto tap = [&](int y, int x, float w) {
+    if ((unsigned)y >= (unsigned)Hi || (unsigned)x >= (unsigned)Wi) return;
+    Vec8<T> v; float f[8];
+    v.load(src + ((size_t)y * Wi + x) * C);
+    v.get(f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float h = silu_f(fmaf(a[i], f[i], b[i]));
+      acc[i] = fmaf(w, h, acc[i]);
+      raw[i] = fmaf(w, f[i], raw[i]);
+    }
+  };
+  if (RS == RS_DOWN) {
+    // out[Y,X] = sum_{i,j} k[i]k[j] h[2Y+i-1, 2X+j-1], k = [1,3,3,1]/8, zero outside
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tap(2 * Y + i - 1, 2 * X + j - 1, fir_tap(i) * fir_tap(j));
+  } else {
+    // zero-insert x2, pad (2,1), FIR [1,3,3,1]/4 per axis:
+    //   even Y=2y: 3/4 h[y] + 1/4 h[y-1];  odd Y=2y+1: 3/4 h[y] + 1/4 h[y+1]
+    const int y0 = Y >> 1, x0i = X >> 1;
+    const int y1 = (Y & 1) ? y0 + 1 : y0 - 1;
+    const int x1i = (X & 1) ? x0i + 1 : x0i - 1;
+    tap(y0, x0i, 0.5625f);
+    tap(y0, x1i, 0.1875f);
+    tap(y1, x0i, 0.1875f);
+    tap(y1, x1i, 0.0625f);
+  }
+  const size_t o = ((size_t)n * Ho * Wo + pix) * C + c;
+  Vec8<T> ov;
+  ov.set(acc); ov.store(out0 + o);
+  ov.set(raw); ov.store(out1 + o);
 }
 
 template <typename T>
 static void gn_apply_dispatch(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float2* ab, bool silu,
                               Resample rs, TensorDesc& out0, TensorDesc* out1) {
   const int C1 = x1 ? x1->C : 0;
-  const size_t total = out0.numel() / 8;
-  const int block = 256;
-  const int grid = (int)((total + block - 1) / block);
+  const int Ct = x0.C + C1, cvpp = Ct / 8;
   const T* p0 = (const T*)x0.p; const T* p1 = x1 ? (const T*)x1->p : nullptr;
-  T* o0 = (T*)out0.p; T* o1 = out1 ? (T*)out1->p : nullptr;
-#define GO(RS_, SILU_, RAW_) \
-  gn_apply_kernel<T, RS_, SILU_, RAW_><<<grid, block, 0, st>>>(p0, x0.C, p1, C1, ab, x0.N, x0.H, x0.W, o0, o1)
+  T* o0 = (T*)out0.p;
   if (rs == RS_NONE) {
-    if (silu) GO(RS_NONE, true, false); else GO(RS_NONE, false, false);
-  } else if (rs == RS_DOWN) {
-    SG_CHECK(silu && out1 && !x1, "down-sampling gn_apply expects silu, raw output, one source");
-    GO(RS_DOWN, true, true);
+    SG_CHECK(cvpp <= 256, "gn_apply: %d channels exceed one block", Ct);
+    const int block = (256 / cvpp) * cvpp;
+    const int ppb = block / cvpp;
+    const int HW = x0.H * x0.W;
+    int gx = cdiv(HW, ppb * 4);
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, x0.N);
+    if (silu) gn_apply_plain_kernel<T, true><<<grid, block, 0, st>>>(p0, x0.C, p1, C1, ab, HW, o0);
+    else gn_apply_plain_kernel<T, false><<<grid, block, 0, st>>>(p0, x0.C, p1, C1, ab, HW, o0);
   } else {
-    SG_CHECK(silu && out1 && !x1, "up-sampling gn_apply expects silu, raw output, one source");
-    GO(RS_UP, true, true);
+    SG_CHECK(silu && out1 && !x1, "resampling gn_apply expects silu, a raw output and a single source");
+    const size_t total = (size_t)out0.H * out0.W * cvpp;
+    SG_CHECK(total < (1ull << 31), "gn_apply: tensor too large for 32-bit indexing");
+    dim3 grid((unsigned)((total + 255) / 256), x0.N);
+    T* o1 = (T*)out1->p;
+    if (rs == RS_DOWN) gn_apply_fir_kernel<T, RS_DOWN><<<grid, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+    else gn_apply_fir_kernel<T, RS_UP><<<grid, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
   }
-#undef GO
   CUDA_OK(cudaGetLastError());
 }
 

@@ -54,6 +54,11 @@ void launch_conv_direct(cudaStream_t st, const ConvArgs& a, TensorDesc& out);
 // tcgen05 implicit GEMM; requires fp16 activations, every segment C % 64 == 0, Cout % 128 == 0
 bool conv_tc_supported(const ConvArgs& a, const TensorDesc& out);
 void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
+// second-generation kernel (conv_tc2.cu): activation/weight tiles reused across taps and sub-tiles in smem;
+// needs W % 8 == 0, H % 16 == 0, Cout % 128 == 0.  launch_conv_tc dispatches to it unless g_tc_variant == 1.
+bool conv_tc2_supported(const ConvArgs& a, const TensorDesc& out);
+void launch_conv_tc2(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
+extern int g_tc_variant;
 
 // input layer: state float4 (x.re,x.im,y.re,y.im) -> conv3x3(4->C); w [36][C] (k = tap*4+cin), bias [C]
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,

@@ -152,58 +152,59 @@ void launch_fir4(cudaStream_t st, const float4* in, int N, int H, int W, Resampl
 }
 
 // ------------------------------------------------------------------------------------------------
-// progressive output conv3x3 (C -> 4) + bias (+ FIR-up'ed pyramid).  One warp per pixel: lanes
-// split the channels (8 per lane per pass, 128-bit loads), shuffle-reduce the 4 outputs.
-// w [9*C][4] (k = tap*C + cin) as float4 rows.
+// progressive output conv3x3 (C -> 4) + bias (+ FIR-up'ed pyramid).  N=4 "GEMM": CUDA cores.
+// One thread per output pixel (16x16 pixel tile per block), the [9*C] x 4 weights live in shared memory as
+// float4 rows and are read as warp-wide broadcasts (1 LDS.128 per 4 FMA); activations stream through L1 with
+// 128-bit loads.  w [9*C][4] (k = tap*C + cin).
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ act, int N, int H, int W, int C,
+__global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ act, int H, int W, int C,
                                                        const float4* __restrict__ w, float4 bias,
                                                        const float4* __restrict__ addend, float4* __restrict__ out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const size_t total = (size_t)N * H * W;
-  if (warp >= total) return;
-  const int x = warp % W, y = (warp / W) % H, n = warp / (W * H);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  extern __shared__ float4 wsm[];          // [9*C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  const int n = blockIdx.z;
+  if (x >= W || y >= H) return;
+  float4 acc = bias;
+#pragma unroll 1
   for (int tap = 0; tap < 9; ++tap) {
     const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
     if ((unsigned)yy >= (unsigned)H || (unsigned)xx >= (unsigned)W) continue;
     const T* row = act + (((size_t)n * H + yy) * W + xx) * C;
-    for (int c = lane * 8; c < C; c += 256) {
+    const float4* wr = wsm + tap * C;
+#pragma unroll 2
+    for (int c = 0; c < C; c += 8) {
       Vec8<T> v; float f[8];
       v.load(row + c); v.get(f);
-      const float4* wr = w + (size_t)tap * C + c;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) fma4(acc, f[i], wr[i]);
+      for (int i = 0; i < 8; ++i) fma4(acc, f[i], wr[c + i]);
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-  }
-  if (lane == 0) {
-    acc.x += bias.x; acc.y += bias.y; acc.z += bias.z; acc.w += bias.w;
-    if (addend) { const float4 a = addend[warp]; acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w; }
-    out[warp] = acc;
-  }
+  const size_t o = ((size_t)n * H + y) * W + x;
+  if (addend) { const float4 a = addend[o]; acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w; }
+  out[o] = acc;
 }
 
 void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, const float* bias,
                      const float4* addend, float4* out) {
   SG_CHECK(act.C % 8 == 0, "out conv: C must be a multiple of 8");
-  const size_t total = (size_t)act.N * act.H * act.W;
-  const int grid = (int)((total * 32 + 255) / 256);
-  // bias lives on the device: fetch through a tiny kernel argument-free path is overkill; the engine
-  // passes a host copy through `bias` being a *host* pointer to 4 floats.
+  const size_t smem = (size_t)9 * act.C * sizeof(float4);
+  SG_CHECK(smem <= 96 * 1024, "out conv: %d channels exceed the shared-memory weight buffer", act.C);
+  // `bias` is a HOST pointer to 4 floats (kept with the layer description)
   const float4 b = make_float4(bias[0], bias[1], bias[2], bias[3]);
-  if (act.dt == DT_F16)
-    out_conv_kernel<__half><<<grid, 256, 0, st>>>((const __half*)act.p, act.N, act.H, act.W, act.C, (const float4*)w, b, addend, out);
-  else
-    out_conv_kernel<float><<<grid, 256, 0, st>>>((const float*)act.p, act.N, act.H, act.W, act.C, (const float4*)w, b, addend, out);
+  dim3 grid(cdiv(act.W, 16), cdiv(act.H, 16), act.N);
+  if (act.dt == DT_F16) {
+    auto k = out_conv_kernel<__half>;
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, st>>>((const __half*)act.p, act.H, act.W, act.C, (const float4*)w, b, addend, out);
+  } else {
+    auto k = out_conv_kernel<float>;
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, st>>>((const float*)act.p, act.H, act.W, act.C, (const float4*)w, b, addend, out);
+  }
   CUDA_OK(cudaGetLastError());
 }
 

@@ -191,6 +191,25 @@ def test_full_size_forward(full_sd, mode, tol, T):
     eng.close()
 
 
+def test_tc_kernel_variants_agree(full_sd):
+    """The operand-reuse tcgen05 kernel (conv_tc2.cu) and the first-generation one (conv_tc.cu) compute the same
+    convolutions (different accumulation order only)."""
+    eng = Engine(EngineConfig(mode="fp16_tc", max_batch=2))
+    eng.load_state_dict(full_sd)
+    g = torch.Generator().manual_seed(12)
+    x = (torch.complex(torch.randn(2, 2, 256, 512, generator=g), torch.randn(2, 2, 256, 512, generator=g)) * 0.3).cuda()
+    t = torch.tensor([0.7, 0.1]).cuda()
+    a = eng.dnn_forward(x, t)
+    eng.set_option("tc_variant", 1)
+    b = eng.dnn_forward(x, t)
+    eng.set_option("tc_variant", 0)
+    assert eng.counter("direct_convs_last_forward") == 0
+    err = rel_l2(a, b)
+    print(f"tc variants: rel-L2 {err:.3e}")
+    assert err < 5e-3
+    eng.close()
+
+
 def test_full_size_sampler_properties(full_sd):
     """Size-independent properties at the benchmark shape [B,1,256,512]:
     graph replay == eager launch sequence (bitwise), outputs do not depend on how the batch is split into
