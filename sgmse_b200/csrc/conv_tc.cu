@@ -416,7 +416,7 @@ void launch_impl(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) 
     }
   }
   P.num_k_blocks = kblocks;
-  const CUtensorMap mb = make_w_map(a.w_tc, out.C, a.ktot(), BLOCK_N);
+  const CUtensorMap mb = make_w_map(a.w_tc, out.C, a.w_tc_ld ? a.w_tc_ld : a.ktot(), BLOCK_N);
   const CUtensorMap md = make_act_map(out.p, out.N, out.H, out.W, out.C, bw, bh, bn);
   const TensorDesc& rs = a.residual ? *a.residual : out;
   const CUtensorMap mr = make_act_map(rs.p, rs.N, rs.H, rs.W, rs.C, bw, bh, bn);

@@ -1,17 +1,23 @@
 // tcgen05 implicit-GEMM 3x3/1x1 convolution, second generation: operand reuse in shared memory.
 //
 // Same contract as conv_tc.cu (multi-segment K, fused bias/temb/residual/scale epilogue, GroupNorm partials),
-// but built around the observation that the v1 kernel is bound by L2->SMEM traffic (128 B per MMA clock per
-// SM: every tap re-loads a full activation tile and a full weight tile for 256 MMA clocks of work):
+// but built around two measurements of the v1 kernel (profiles/r01_conv_tc_v1_ncu.txt): it needs 128 B of
+// L2->SMEM traffic per MMA clock per SM, and its epilogue (residual round trip through smem, per-column
+// global loads of bias/temb with a 4 KB L1, serialized phases) is as long as the main loop.
 //
 //   * CTA tile = 8 (W) x 16*SUBS (H) pixels of one utterance = SUBS accumulators of 128 pixels x 128 channels.
 //   * Per (64-channel chunk, dx in {-1,0,1}) ONE TMA box {64 ch, 8 px, 16*SUBS+2 rows} is loaded.  Because a pixel
 //     row of the box is exactly 8 x 128 B = one 1024-B swizzle atom, the three dy taps (and the SUBS sub-tiles) are
 //     the same smem bytes viewed through UMMA descriptors whose start address is advanced by whole atoms
-//     ((sub*16 + dy + 1) * 1024 B) -- the activation traffic drops from 9 to 3*(16*SUBS+2)/(16*SUBS) tile loads.
+//     ((sub*16 + dy + 1) * 1024 B) -- activation traffic drops from 9 to 3*(16*SUBS+2)/(16*SUBS) tile loads.
 //   * Each weight tile (128 cout x 64 cin of one tap) feeds SUBS accumulators.
-//   => L2->SMEM bytes per MMA clock: 128 (v1) -> 53 (SUBS=2).
+//     => L2->SMEM bytes per MMA clock: 128 (v1) -> 53 (SUBS=2).
 //   * Separate smem rings for activations (A_STAGES x 34 KB) and weights (B_STAGES x 16 KB).
+//   * The residual `x` of `(x + conv(h)) / sqrt(2)` enters as one more 1x1 K segment against an identity block
+//     appended to the packed weights (exact: x * 1.0 accumulated in fp32), so the epilogue never reads it.
+//   * Epilogue works in 64-channel halves that ping-pong between two 16 KB staging buffers: tcgen05.ld (64 columns)
+//     -> + (bias + temb) from smem -> * scale -> fp16 -> swizzled smem -> TMA store, while the previous half's store
+//     drains; GroupNorm partials are reduced from the staged half.
 //
 // TMEM: 2 stages x SUBS accumulators x 128 fp32 columns (= all 512 columns for SUBS=2).
 #include "kernels.h"
@@ -30,21 +36,21 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int NUM_EPI_THREADS = 128;
 constexpr int ROW_BYTES = 8 * 128;                 // one pixel row of the box: 8 px x 64 ch fp16 = one swizzle atom
-constexpr int SUB_BYTES = 16 * ROW_BYTES;          // a 128-pixel sub-tile (16 KB)
+constexpr int SUB_BYTES = 16 * ROW_BYTES;          // 128 pixels x 64 channels (16 KB)
 constexpr int B_BYTES = BLOCK_N * 128;             // 16 KB
+constexpr int MAX_SEG = 4;
 
 struct Tc2Params {
   int tiles_w, tiles_h;          // per utterance
   int num_m_tiles, num_tiles, n_tiles_n;
   int N, Cout;
   int nseg;
-  int seg_chunks[3];
-  int seg_taps[3];
-  int seg_kb0[3];                // first K block of the segment
+  int seg_chunks[MAX_SEG];
+  int seg_taps[MAX_SEG];
+  int seg_kb0[MAX_SEG];          // first K block of the segment
   const float* bias;
   const float* temb;
   int temb_stride;
-  int has_residual;
   float scale;
   float* stats;
   int slots;
@@ -56,11 +62,11 @@ struct Smem2 {
   static constexpr int A_ROWS = 16 * SUBS + 2;
   static constexpr int A_BYTES = A_ROWS * ROW_BYTES;
   static constexpr int OFF_B = A_STAGES * A_BYTES;
-  static constexpr int OFF_STAGING = OFF_B + B_STAGES * B_BYTES;
-  static constexpr int STAGING_BYTES = 2 * SUB_BYTES;                    // 128 rows x 128 channels fp16
-  static constexpr int OFF_STATS = OFF_STAGING + STAGING_BYTES;          // float [4][128][2]
-  static constexpr int OFF_BARS = OFF_STATS + 4 * BLOCK_N * 2 * 4;
-  static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 5;
+  static constexpr int OFF_STAGING = OFF_B + B_STAGES * B_BYTES;         // 2 x 16 KB (ping-pong halves)
+  static constexpr int OFF_STATS = OFF_STAGING + 2 * SUB_BYTES;          // float [4][64][2]
+  static constexpr int OFF_BIAS = OFF_STATS + 4 * 64 * 2 * 4;            // float [128]
+  static constexpr int OFF_BARS = OFF_BIAS + BLOCK_N * 4;
+  static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 4;
   static constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM_PTR + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;
@@ -78,11 +84,31 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
 }
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, M128 N128
 
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+        "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+        "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
 template <int SUBS, int A_STAGES, int B_STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
-                const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_r,
+                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
+                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_d,
                 const Tc2Params P) {
   using L = Smem2<SUBS, A_STAGES, B_STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -94,10 +120,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   uint64_t* b_empty = b_full + B_STAGES;
   uint64_t* tmem_full = b_empty + B_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
   uint8_t* staging = smem + L::OFF_STAGING;
   float* stats_sm = reinterpret_cast<float*>(smem + L::OFF_STATS);
+  float* bias_sm = reinterpret_cast<float*>(smem + L::OFF_BIAS);
   constexpr uint32_t TMEM_COLS = 2 * SUBS * BLOCK_N;
 
   const int warp = threadIdx.x >> 5;
@@ -107,11 +133,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     tma_prefetch_desc(&map_a0); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_d);
     if (P.nseg > 1) tma_prefetch_desc(&map_a1);
     if (P.nseg > 2) tma_prefetch_desc(&map_a2);
-    if (P.has_residual) tma_prefetch_desc(&map_r);
+    if (P.nseg > 3) tma_prefetch_desc(&map_a3);
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
-    mbar_init(res_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -131,7 +156,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
         const int x0 = (rem % P.tiles_w) * 8, y0 = (rem / P.tiles_w) * (16 * SUBS);
         for (int s = 0; s < P.nseg; ++s) {
-          const CUtensorMap* ma = s == 0 ? &map_a0 : (s == 1 ? &map_a1 : &map_a2);
+          const CUtensorMap* ma = s == 0 ? &map_a0 : (s == 1 ? &map_a1 : (s == 2 ? &map_a2 : &map_a3));
           const int nd = P.seg_taps[s] == 9 ? 3 : 1;
           const int chunks = P.seg_chunks[s];
           for (int ch = 0; ch < chunks; ++ch)
@@ -204,104 +229,84 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const int e = threadIdx.x - 64;
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
-    int as = 0; uint32_t as_phase = 0; uint32_t res_phase = 0;
+    const int sw = row & 7;
+    int as = 0; uint32_t as_phase = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const int m_tile = tile % P.num_m_tiles, n_tile = tile / P.num_m_tiles;
       const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
       const int tx = rem % P.tiles_w, ty = rem / P.tiles_w;
       const int x0 = tx * 8;
       const int c_tile = n_tile * BLOCK_N;
-      const float* temb_row = P.temb ? P.temb + (size_t)n * P.temb_stride + c_tile : nullptr;
-      const float* bias_row = P.bias ? P.bias + c_tile : nullptr;
-      uint8_t* my_row = staging + row * 128;
-      const int sw = row & 7;
+      {
+        // bias + time-embedding bias of this (utterance, channel tile): one value per thread into smem
+        float bt = P.bias ? __ldg(P.bias + c_tile + e) : 0.f;
+        if (P.temb) bt += __ldg(P.temb + (size_t)n * P.temb_stride + c_tile + e);
+        named_bar_sync(1, NUM_EPI_THREADS);      // previous tile's readers of bias_sm are done
+        bias_sm[e] = bt;
+      }
+      mbar_wait(&tmem_full[as], as_phase, P.dbg, 500 + as);
+      tc_fence_after();
 
 #pragma unroll 1
       for (int sub = 0; sub < SUBS; ++sub) {
         const int y0 = (ty * SUBS + sub) * 16;
-        if (e == 0) tma_store_wait_read0();
-        named_bar_sync(1, NUM_EPI_THREADS);
-        if (P.has_residual) {
-          if (e == 0) {
-            fence_proxy_async_smem();
-            mbar_arrive_expect_tx(res_full, L::STAGING_BYTES);
-            tma_load_4d(staging, &map_r, res_full, c_tile, x0, y0, n);
-            tma_load_4d(staging + SUB_BYTES, &map_r, res_full, c_tile + 64, x0, y0, n);
-          }
-          mbar_wait(res_full, res_phase, P.dbg, 400);
-          res_phase ^= 1;
-        }
-        if (sub == 0) {
-          mbar_wait(&tmem_full[as], as_phase, P.dbg, 500 + as);
-          tc_fence_after();
-        }
-        const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((as * SUBS + sub) * BLOCK_N);
+        const int slot = (ty * SUBS + sub) * P.tiles_w + tx;
 #pragma unroll 1
-        for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + (uint32_t)(c32 * 32), r);
+        for (int half = 0; half < 2; ++half) {
+          uint8_t* buf = staging + half * SUB_BYTES;
+          // buffer `half` was last used two stores ago: at most the other half's store may still be reading smem
+          if (e == 0) tma_store_wait_read1();
+          named_bar_sync(1, NUM_EPI_THREADS);    // ... also: bias_sm visible, stats readers of `buf` done
+          uint32_t r[64];
+          tmem_ld_32x64(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((as * SUBS + sub) * BLOCK_N + half * 64), r);
           tmem_ld_wait();
-          uint8_t* chunk_row = my_row + (c32 >> 1) * SUB_BYTES;
+          if (sub == SUBS - 1 && half == 1) {
+            // accumulator stage fully drained -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
+          uint8_t* my_row = buf + row * 128;
+          const float4* bs = reinterpret_cast<const float4*>(bias_sm + half * 64);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int cb = c32 * 32 + g * 8;
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float x = __uint_as_float(r[g * 8 + i]);
-              if (bias_row) x += __ldg(bias_row + cb + i);
-              if (temb_row) x += __ldg(temb_row + cb + i);
-              v[i] = x;
-            }
-            uint4* sp = reinterpret_cast<uint4*>(chunk_row + ((((c32 & 1) * 4 + g) ^ sw) << 4));
-            if (P.has_residual) {
-              const uint4 rv = *sp;
-              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(rh[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
-            }
+          for (int g = 0; g < 8; ++g) {
+            const float4 b0 = bs[2 * g], b1 = bs[2 * g + 1];
             uint4 ov;
             __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i] * P.scale, v[2 * i + 1] * P.scale);
-            *sp = ov;
+            oh[0] = __floats2half2_rn((__uint_as_float(r[g * 8 + 0]) + b0.x) * P.scale, (__uint_as_float(r[g * 8 + 1]) + b0.y) * P.scale);
+            oh[1] = __floats2half2_rn((__uint_as_float(r[g * 8 + 2]) + b0.z) * P.scale, (__uint_as_float(r[g * 8 + 3]) + b0.w) * P.scale);
+            oh[2] = __floats2half2_rn((__uint_as_float(r[g * 8 + 4]) + b1.x) * P.scale, (__uint_as_float(r[g * 8 + 5]) + b1.y) * P.scale);
+            oh[3] = __floats2half2_rn((__uint_as_float(r[g * 8 + 6]) + b1.z) * P.scale, (__uint_as_float(r[g * 8 + 7]) + b1.w) * P.scale);
+            *reinterpret_cast<uint4*>(my_row + ((g ^ sw) << 4)) = ov;
           }
-        }
-        if (sub == SUBS - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, NUM_EPI_THREADS);
-        if (e == 0) {
-          tma_store_4d(&map_d, staging, c_tile, x0, y0, n);
-          tma_store_4d(&map_d, staging + SUB_BYTES, c_tile + 64, x0, y0, n);
-          tma_store_commit();
-        }
-        if (P.stats) {
-          const int seg = e >> 5;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          fence_proxy_async_smem();
+          named_bar_sync(1, NUM_EPI_THREADS);
+          if (e == 0) {
+            tma_store_4d(&map_d, buf, c_tile + half * 64, x0, y0, n);
+            tma_store_commit();
+          }
+          if (P.stats) {
+            // per-channel (sum, sum^2) over each 32-row segment of the staged half (the fp16 values actually stored)
+            const int seg = e >> 5;
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-            const uint8_t* cbase = staging + c * SUB_BYTES;
 #pragma unroll 8
             for (int rr = 0; rr < 32; ++rr) {
               const int r2 = seg * 32 + rr;
-              const __half2 h = *reinterpret_cast<const __half2*>(cbase + r2 * 128 + ((((lane >> 2) ^ (r2 & 7)) << 4) | ((lane & 3) << 2)));
+              const __half2 h = *reinterpret_cast<const __half2*>(buf + r2 * 128 + ((((lane >> 2) ^ (r2 & 7)) << 4) | ((lane & 3) << 2)));
               const float2 f = __half22float2(h);
               s0 += f.x; q0 += f.x * f.x; s1 += f.y; q1 += f.y * f.y;
             }
-            float* d = stats_sm + ((seg * BLOCK_N) + c * 64 + lane * 2) * 2;
+            float* d = stats_sm + ((seg * 64) + lane * 2) * 2;
             d[0] = s0; d[1] = q0; d[2] = s1; d[3] = q1;
-          }
-          named_bar_sync(1, NUM_EPI_THREADS);
-          const int slot = (ty * SUBS + sub) * P.tiles_w + tx;
-          float s = 0.f, q = 0.f;
+            named_bar_sync(1, NUM_EPI_THREADS);
+            if (e < 64) {
+              float s = 0.f, q = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { s += stats_sm[((j * BLOCK_N) + e) * 2]; q += stats_sm[((j * BLOCK_N) + e) * 2 + 1]; }
-          float* d = P.stats + (((size_t)n * P.slots + slot) * P.Cout + c_tile + e) * 2;
-          d[0] = s; d[1] = q;
+              for (int j = 0; j < 4; ++j) { s += stats_sm[((j * 64) + e) * 2]; q += stats_sm[((j * 64) + e) * 2 + 1]; }
+              float* o = P.stats + (((size_t)n * P.slots + slot) * P.Cout + c_tile + half * 64 + e) * 2;
+              o[0] = s; o[1] = q;
+            }
+          }
         }
       }
       if (++as == 2) { as = 0; as_phase ^= 1; }
@@ -325,23 +330,29 @@ void launch2(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   P.num_m_tiles = P.tiles_w * P.tiles_h * out.N;
   P.n_tiles_n = out.C / BLOCK_N;
   P.num_tiles = P.num_m_tiles * P.n_tiles_n;
-  P.N = out.N; P.Cout = out.C; P.nseg = a.nseg;
-  CUtensorMap ma[3];
+  P.N = out.N; P.Cout = out.C;
+  // segments: the conv's own, plus the residual as a 1x1 segment against the identity tail of the weights
+  const TensorDesc* srcs[MAX_SEG];
+  int taps[MAX_SEG];
+  int nseg = 0;
+  for (int i = 0; i < a.nseg; ++i) { srcs[nseg] = &a.seg[i].src; taps[nseg++] = a.seg[i].taps; }
+  if (a.residual) { srcs[nseg] = a.residual; taps[nseg++] = 1; }
+  P.nseg = nseg;
+  CUtensorMap ma[MAX_SEG];
   int kb = 0;
-  for (int i = 0; i < 3; ++i) {
-    const TensorDesc& s = a.seg[i < a.nseg ? i : 0].src;
+  for (int i = 0; i < MAX_SEG; ++i) {
+    const TensorDesc& s = *srcs[i < nseg ? i : 0];
     ma[i] = make_act_map(s.p, s.N, s.H, s.W, s.C, 8, L::A_ROWS, 1);
-    if (i < a.nseg) {
-      P.seg_chunks[i] = s.C / 64; P.seg_taps[i] = a.seg[i].taps; P.seg_kb0[i] = kb;
-      kb += a.seg[i].taps * (s.C / 64);
+    if (i < nseg) {
+      P.seg_chunks[i] = s.C / 64; P.seg_taps[i] = taps[i]; P.seg_kb0[i] = kb;
+      kb += taps[i] * (s.C / 64);
     }
   }
-  const CUtensorMap mb = make_w_map(a.w_tc, out.C, a.ktot(), BLOCK_N);
+  const int ld = a.w_tc_ld ? a.w_tc_ld : a.ktot();
+  SG_CHECK(kb * 64 <= ld, "conv_tc2: K blocks (%d) exceed the packed weight row (%d)", kb * 64, ld);
+  const CUtensorMap mb = make_w_map(a.w_tc, out.C, ld, BLOCK_N);
   const CUtensorMap md = make_act_map(out.p, out.N, out.H, out.W, out.C, 8, 16, 1);
-  const TensorDesc& rs = a.residual ? *a.residual : out;
-  const CUtensorMap mr = make_act_map(rs.p, rs.N, rs.H, rs.W, rs.C, 8, 16, 1);
   P.bias = a.bias; P.temb = a.temb; P.temb_stride = a.temb_stride;
-  P.has_residual = a.residual ? 1 : 0;
   P.scale = a.scale;
   out.slots = P.tiles_w * P.tiles_h * SUBS;
   P.stats = out.stats; P.slots = out.slots;
@@ -353,7 +364,7 @@ void launch2(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
     attr_set = true;
   }
   const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
-  kern<<<grid, NUM_THREADS, L::DYN_BYTES, st>>>(ma[0], ma[1], ma[2], mb, md, mr, P);
+  kern<<<grid, NUM_THREADS, L::DYN_BYTES, st>>>(ma[0], ma[1], ma[2], ma[3], mb, md, P);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -364,6 +375,7 @@ bool conv_tc2_supported(const ConvArgs& a, const TensorDesc& out) {
   if (out.W % 8 != 0 || out.H % 16 != 0) return false;
   for (int i = 0; i < a.nseg; ++i)
     if (a.seg[i].src.C % 64 != 0 || a.seg[i].src.dt != DT_F16) return false;
+  if (a.residual && (!a.tc_identity_tail || a.nseg >= MAX_SEG || a.residual->C != out.C)) return false;
   return true;
 }
 

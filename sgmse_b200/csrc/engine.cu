@@ -163,7 +163,8 @@ void* upload(Engine& e, const void* host, size_t bytes) {
 
 // rows: list of (pointer to [Cout][Cin][kh*kw] fp32, Cin, taps)
 struct PackSrc { const float* w; int cin; int taps; };
-void pack_conv(Engine& e, const std::vector<PackSrc>& srcs, int cout, bool out_major_src, ConvW& cw) {
+void pack_conv(Engine& e, const std::vector<PackSrc>& srcs, int cout, bool out_major_src, ConvW& cw,
+               bool identity_tail = false) {
   // out_major_src: true for Conv2d weights [Cout][Cin][taps]; false for NIN weights [Cin][Cout]
   int ktot = 0;
   for (auto& s : srcs) ktot += s.taps * s.cin;
@@ -189,10 +190,18 @@ void pack_conv(Engine& e, const std::vector<PackSrc>& srcs, int cout, bool out_m
     for (size_t i = 0; i < kd.size(); ++i) hd[i] = __float2half_rn(kd[i]);
     cw.w_direct = upload(e, hd.data(), hd.size() * 2);
     if (e.cfg.mode == SGMSE_B200_MODE_FP16_TC && cout % 64 == 0 && ktot % 64 == 0) {
-      std::vector<__half> ht((size_t)cout * ktot);
+      // [Cout][ld]; with `identity_tail` an extra Cout x Cout identity block follows the real K columns so that the
+      // tensor-core kernel can take the residual `x` as one more 1x1 K segment (acc += x * I, exact in fp32)
+      // instead of re-reading it in the epilogue.
+      const int ld = ktot + (identity_tail ? cout : 0);
+      std::vector<__half> ht((size_t)cout * ld, __float2half_rn(0.f));
       for (int k = 0; k < ktot; ++k)
-        for (int co = 0; co < cout; ++co) ht[(size_t)co * ktot + k] = hd[(size_t)k * cout + co];
+        for (int co = 0; co < cout; ++co) ht[(size_t)co * ld + k] = hd[(size_t)k * cout + co];
+      if (identity_tail)
+        for (int co = 0; co < cout; ++co) ht[(size_t)co * ld + ktot + co] = __float2half_rn(1.f);
       cw.w_tc = (__half*)upload(e, ht.data(), ht.size() * 2);
+      cw.w_tc_ld = ld;
+      cw.identity_tail = identity_tail;
     }
   }
 }
@@ -225,7 +234,7 @@ void load_weights(Engine& e, const float* blob) {
       pack_conv(e, {{blob + l.conv0_w, l.cin, 9}}, l.cout, true, l.c0);
       std::vector<PackSrc> s1{{blob + l.conv1_w, l.cout, 9}};
       if (l.shortcut) s1.push_back({blob + l.conv2_w, l.cin, 1});
-      pack_conv(e, s1, l.cout, true, l.c1);
+      pack_conv(e, s1, l.cout, true, l.c1, /*identity_tail=*/!l.shortcut);
       std::vector<float> b1(blob + l.conv1_b, blob + l.conv1_b + l.cout);
       if (l.shortcut) for (int i = 0; i < l.cout; ++i) b1[i] += blob[l.conv2_b + i];
       l.c1.bias = (float*)upload(e, b1.data(), b1.size() * 4);
@@ -242,7 +251,7 @@ void load_weights(Engine& e, const float* blob) {
       }
       pack_conv(e, {{wq.data(), C, 1}}, 3 * C, false, l.c0);
       l.c0.bias = (float*)upload(e, bq.data(), bq.size() * 4);
-      pack_conv(e, {{blob + l.nin_w[3], C, 1}}, C, false, l.c1);
+      pack_conv(e, {{blob + l.nin_w[3], C, 1}}, C, false, l.c1, /*identity_tail=*/true);
       l.c1.bias = e.blob_dev + l.nin_b[3];
     } else if (l.kind == LK_COMBINE) {
       const int C = l.cout;
@@ -357,7 +366,7 @@ struct Fwd {
     {
       ConvArgs a;
       a.nseg = 1; a.seg[0].src = h0; a.seg[0].taps = 9;
-      a.w_direct = l.c0.w_direct; a.w_tc = l.c0.w_tc;
+      a.w_direct = l.c0.w_direct; a.w_tc = l.c0.w_tc; a.w_tc_ld = l.c0.w_tc_ld;
       a.temb = temb + l.temb_off; a.temb_stride = temb_stride;   // Conv_0.bias is folded into the table
       conv(a, h1, 0);
     }
@@ -377,7 +386,8 @@ struct Fwd {
       } else {
         a.residual = &x0;
       }
-      a.w_direct = l.c1.w_direct; a.w_tc = l.c1.w_tc; a.bias = l.c1.bias; a.scale = INV_SQRT2;
+      a.w_direct = l.c1.w_direct; a.w_tc = l.c1.w_tc; a.w_tc_ld = l.c1.w_tc_ld; a.tc_identity_tail = l.c1.identity_tail;
+      a.bias = l.c1.bias; a.scale = INV_SQRT2;
       conv(a, out, 1);
     }
     tap("m" + std::to_string(l.idx), out);
@@ -394,7 +404,7 @@ struct Fwd {
     {
       ConvArgs a;
       a.nseg = 1; a.seg[0].src = hn; a.seg[0].taps = 1;
-      a.w_direct = l.c0.w_direct; a.w_tc = l.c0.w_tc; a.bias = l.c0.bias;
+      a.w_direct = l.c0.w_direct; a.w_tc = l.c0.w_tc; a.w_tc_ld = l.c0.w_tc_ld; a.bias = l.c0.bias;
       conv(a, qkv, 2);
     }
     TensorDesc av = act(x.N, x.H, x.W, C, false);
@@ -403,7 +413,8 @@ struct Fwd {
     {
       ConvArgs a;
       a.nseg = 1; a.seg[0].src = av; a.seg[0].taps = 1;
-      a.w_direct = l.c1.w_direct; a.w_tc = l.c1.w_tc; a.bias = l.c1.bias;
+      a.w_direct = l.c1.w_direct; a.w_tc = l.c1.w_tc; a.w_tc_ld = l.c1.w_tc_ld; a.tc_identity_tail = l.c1.identity_tail;
+      a.bias = l.c1.bias;
       a.residual = &x; a.scale = INV_SQRT2;
       conv(a, out, 3);
     }
@@ -816,6 +827,8 @@ void analysis(Engine& e, const float* wav, int B, int L, int pad_mode, float2* Y
   const sgmse_b200_config& c = e.cfg;
   const int nT = frames_of(e, L), Tpad = padded_frames(e, L), F = c.n_fft / 2 + 1;
   SG_CHECK(L > c.n_fft / 2, "waveform too short for reflect padding");
+  SG_CHECK(pad_mode != SGMSE_B200_PAD_REFLECTION || Tpad - nT < nT,
+           "reflection padding of %d frames needs more than %d input frames (torch ReflectionPad2d contract)", Tpad - nT, nT);
   ensure_stft_buf(e, 0, (size_t)B * nT * c.n_fft * 4);
   ensure_stft_buf(e, 1, (size_t)B * nT * F * 8);
   launch_absmax(st, wav, B, L, norm);

@@ -21,7 +21,9 @@ struct ParamRef {       // one state_dict() entry
 
 struct ConvW {          // packed convolution weights (K ordering: segment, tap, cin)
   void* w_direct = nullptr;   // [Ktot][Cout] float or half
-  __half* w_tc = nullptr;     // [Cout][Ktot]
+  __half* w_tc = nullptr;     // [Cout][w_tc_ld], K-major; optional identity tail (see pack_conv)
+  int w_tc_ld = 0;
+  bool identity_tail = false;
   float* bias = nullptr;      // [Cout] fp32 (device)
   int ktot = 0, cout = 0;
 };

@@ -42,7 +42,9 @@ struct ConvArgs {
   int nseg = 0;
   ConvSeg seg[3];
   const void* w_direct = nullptr;  // [Ktot][Cout], element type of the activations
-  const __half* w_tc = nullptr;    // [Cout][Ktot]
+  const __half* w_tc = nullptr;    // [Cout][w_tc_ld] (K-major rows)
+  int w_tc_ld = 0;                 // row length in elements (>= ktot())
+  bool tc_identity_tail = false;   // columns [ktot, ktot+Cout) hold I: the residual may be fed as a K segment
   const float* bias = nullptr;     // [Cout] (nullable)
   const float* temb = nullptr;     // per-(row, channel) additive bias table (nullable)
   int temb_stride = 0;             // floats between consecutive samples' rows (0: all samples share)

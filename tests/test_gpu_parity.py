@@ -114,14 +114,24 @@ def test_golden_stft_ops(golden_dir):
     eng.close()
     e48 = Engine(EngineConfig.ncsnpp_48k(mode="fp32"))
     w48 = torch.from_numpy(z["wav48"]).cuda()
-    Y48, n48 = e48.analysis(w48, pad_mode="reflection")
+    Y48, n48 = e48.analysis(w48)
     s48 = o_spec.SpecConfig.cfg_48k()
     nrm48 = torch.from_numpy(z["wav48"]).abs().amax(dim=1)
-    Yo48 = o_spec.pad_spec(o_spec.spec_fwd(o_spec.stft(torch.from_numpy(z["wav48"]) / nrm48[:, None], s48), s48)[:, None], "reflection")
+    Yo48 = o_spec.pad_spec(o_spec.spec_fwd(o_spec.stft(torch.from_numpy(z["wav48"]) / nrm48[:, None], s48), s48)[:, None])
     assert Y48.shape == Yo48.shape
     assert rel_l2(Y48, Yo48) < 1e-5
     want48 = o_spec.istft(o_spec.spec_back(Yo48[:, 0], s48), s48, 6000) * nrm48[:, None]
     assert rel_l2(e48.synthesis(Y48, n48, 6000), want48) < 1e-4
+    # reflection padding (enhancement.py:46-54 uses it for ncsnpp_48k): 79 frames -> 128
+    g = torch.Generator().manual_seed(9)
+    wl = 0.1 * torch.randn(2, 30000, generator=g)
+    Yr, nr = e48.analysis(wl.cuda(), pad_mode="reflection")
+    nl = wl.abs().amax(dim=1)
+    Yor = o_spec.pad_spec(o_spec.spec_fwd(o_spec.stft(wl / nl[:, None], s48), s48)[:, None], "reflection")
+    assert Yr.shape == Yor.shape and rel_l2(Yr, Yor) < 1e-5
+    # like ReflectionPad2d, padding by more than the signal has frames is an error, not garbage
+    with pytest.raises(RuntimeError, match="reflection"):
+        e48.analysis(w48, pad_mode="reflection")
     e48.close()
 
 
