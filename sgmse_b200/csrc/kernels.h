@@ -60,7 +60,10 @@ void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* db
 // needs W % 8 == 0, H % 16 == 0, Cout % 128 == 0.  launch_conv_tc dispatches to it unless g_tc_variant == 1.
 bool conv_tc2_supported(const ConvArgs& a, const TensorDesc& out);
 void launch_conv_tc2(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
-extern int g_tc_variant;
+// third generation (conv_tc3.cu): CTA pairs, cta_group::2 M256 UMMAs; needs W % 16 == 0, H % 32 == 0 on top of v2.
+bool conv_tc3_supported(const ConvArgs& a, const TensorDesc& out);
+void launch_conv_tc3(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
+extern int g_tc_variant;   // 0: newest applicable kernel, 1: v1 only, 2: v2/v1 (no CTA pairs)
 
 // input layer: state float4 (x.re,x.im,y.re,y.im) -> conv3x3(4->C); w [36][C] (k = tap*4+cin), bias [C]
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,

@@ -188,24 +188,102 @@ __global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ act
   out[o] = acc;
 }
 
+// Warp-cooperative variant for C = 8*LP (LP = lanes per pixel, a power of two <= 32): a warp owns a strip of 16
+// pixels of one row; the LP lanes of a pixel split its channels (one fully coalesced 128-bit load each), keep the
+// tap's 8x4 weights in registers across the strip, and shuffle-reduce the 4 outputs at the end.
+template <typename T, int LP>
+__global__ void __launch_bounds__(256) out_conv_coop_kernel(const T* __restrict__ act, int H, int W,
+                                                            const float4* __restrict__ w, float4 bias,
+                                                            const float4* __restrict__ addend, float4* __restrict__ out) {
+  constexpr int C = LP * 8;
+  constexpr int PPL = 32 / LP;       // pixels per warp-wide load
+  constexpr int P = 16 / PPL;        // loads per 16-pixel strip
+  extern __shared__ float4 wsm[];    // [9][8][LP]: conflict-free when lanes read consecutive float4
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    const int tap = i / C, c = i % C;
+    wsm[(tap * 8 + (c & 7)) * LP + (c >> 3)] = w[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LP, cl = lane % LP;
+  const int x0 = blockIdx.x * 16, y = blockIdx.y * 8 + warp, n = blockIdx.z;
+  if (y >= H) return;
+  float4 acc[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, dx = tap % 3 - 1;
+    if ((unsigned)yy >= (unsigned)H) continue;
+    float4 wr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wr[i] = wsm[(tap * 8 + i) * LP + cl];
+    const T* rowp = act + ((size_t)n * H + yy) * W * C + cl * 8;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int xx = x0 + p * PPL + sub + dx;
+      if ((unsigned)xx < (unsigned)W) {
+        Vec8<T> v; float f[8];
+        v.load(rowp + (size_t)xx * C); v.get(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fma4(acc[p], f[i], wr[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+#pragma unroll
+    for (int o = LP / 2; o > 0; o >>= 1) {
+      acc[p].x += __shfl_xor_sync(0xffffffffu, acc[p].x, o);
+      acc[p].y += __shfl_xor_sync(0xffffffffu, acc[p].y, o);
+      acc[p].z += __shfl_xor_sync(0xffffffffu, acc[p].z, o);
+      acc[p].w += __shfl_xor_sync(0xffffffffu, acc[p].w, o);
+    }
+    const int x = x0 + p * PPL + sub;
+    if (cl == 0 && x < W) {
+      float4 r = acc[p];
+      r.x += bias.x; r.y += bias.y; r.z += bias.z; r.w += bias.w;
+      const size_t o = ((size_t)n * H + y) * W + x;
+      if (addend) { const float4 a = addend[o]; r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w; }
+      out[o] = r;
+    }
+  }
+}
+
+template <typename T>
+static void out_conv_dispatch(cudaStream_t st, const TensorDesc& act, const float4* w, float4 b, const float4* addend,
+                              float4* out) {
+  const size_t smem = (size_t)9 * act.C * sizeof(float4);
+  const T* ap = (const T*)act.p;
+  const int LP = act.C / 8;
+  dim3 gridc(cdiv(act.W, 16), cdiv(act.H, 8), act.N);
+#define COOP(LP_) \
+  do { auto k = out_conv_coop_kernel<T, LP_>; \
+       if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+       k<<<gridc, 256, smem, st>>>(ap, act.H, act.W, w, b, addend, out); } while (0)
+  if (LP == 32) COOP(32);
+  else if (LP == 16) COOP(16);
+  else if (LP == 8) COOP(8);
+  else if (LP == 4) COOP(4);
+  else if (LP == 2) COOP(2);
+  else {
+    auto k = out_conv_kernel<T>;
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(act.W, 16), cdiv(act.H, 16), act.N);
+    k<<<grid, 256, smem, st>>>(ap, act.H, act.W, act.C, w, b, addend, out);
+  }
+#undef COOP
+  CUDA_OK(cudaGetLastError());
+}
+
 void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, const float* bias,
                      const float4* addend, float4* out) {
   SG_CHECK(act.C % 8 == 0, "out conv: C must be a multiple of 8");
-  const size_t smem = (size_t)9 * act.C * sizeof(float4);
-  SG_CHECK(smem <= 96 * 1024, "out conv: %d channels exceed the shared-memory weight buffer", act.C);
+  SG_CHECK((size_t)9 * act.C * sizeof(float4) <= 96 * 1024, "out conv: %d channels exceed the shared-memory weight buffer", act.C);
   // `bias` is a HOST pointer to 4 floats (kept with the layer description)
   const float4 b = make_float4(bias[0], bias[1], bias[2], bias[3]);
-  dim3 grid(cdiv(act.W, 16), cdiv(act.H, 16), act.N);
-  if (act.dt == DT_F16) {
-    auto k = out_conv_kernel<__half>;
-    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, st>>>((const __half*)act.p, act.H, act.W, act.C, (const float4*)w, b, addend, out);
-  } else {
-    auto k = out_conv_kernel<float>;
-    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, st>>>((const float*)act.p, act.H, act.W, act.C, (const float4*)w, b, addend, out);
-  }
-  CUDA_OK(cudaGetLastError());
+  if (act.dt == DT_F16) out_conv_dispatch<__half>(st, act, (const float4*)w, b, addend, out);
+  else out_conv_dispatch<float>(st, act, (const float4*)w, b, addend, out);
 }
 
 }  // namespace sgmse
