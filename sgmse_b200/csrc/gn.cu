@@ -4,6 +4,8 @@
 // ResnetBlockBigGANpp.forward (/root/reference/sgmse/backbones/ncsnpp_utils/layerspp.py:242-258)
 // and the FIR resamplers upsample_2d / downsample_2d (up_or_down_sampling.py:195-257).
 // HBM-bound elementwise work: 128-bit accesses, one read of x, one write per output.
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace sgmse {
@@ -210,6 +212,84 @@ gn_apply_fir_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ 
   ov.set(raw); ov.store(out1 + o);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shared-memory tiled FIR variants: silu(gn(x)) is evaluated ONCE per input element (the generic kernel above
+// re-evaluates it per tap: 4x for up-, 16x for down-sampling, which makes it MUFU-bound instead of HBM-bound).
+// Phase 1 stages h = silu(a*x+b) and the raw x of an input tile (+1 pixel halo) in smem as fp32->half pairs;
+// phase 2 applies the separable [1,3,3,1] FIR from smem and writes both outputs with 128-bit stores.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RS, int TIN, int CV>   // TIN: input tile edge incl. halo; CV: 8-channel vectors per block
+__global__ void __launch_bounds__(256)
+gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ ab, int Hi, int Wi,
+                          T* __restrict__ out0, T* __restrict__ out1) {
+  constexpr int TOUT = RS == RS_UP ? (TIN - 2) * 2 : (TIN - 2) / 2;   // output tile edge
+  __shared__ __align__(16) __half hs[TIN * TIN][CV * 8];
+  __shared__ __align__(16) __half xs[TIN * TIN][CV * 8];
+  const int Ho = RS == RS_DOWN ? Hi / 2 : Hi * 2, Wo = RS == RS_DOWN ? Wi / 2 : Wi * 2;
+  const int cblocks = C / (CV * 8);
+  const int n = blockIdx.z / cblocks, cb = blockIdx.z % cblocks;
+  const int cv = threadIdx.x % CV;
+  const int c = (cb * CV + cv) * 8;
+  // input tile origin (top-left halo pixel)
+  const int iy0 = RS == RS_UP ? blockIdx.y * (TIN - 2) - 1 : blockIdx.y * (TIN - 2) - 1;
+  const int ix0 = RS == RS_UP ? blockIdx.x * (TIN - 2) - 1 : blockIdx.x * (TIN - 2) - 1;
+  float a[8], b[8];
+  {
+    const float4* p = reinterpret_cast<const float4*>(ab + (size_t)n * C + c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float4 v = p[i]; a[2 * i] = v.x; b[2 * i] = v.y; a[2 * i + 1] = v.z; b[2 * i + 1] = v.w; }
+  }
+  const T* src = x0 + (size_t)n * Hi * Wi * C + c;
+  for (int item = threadIdx.x; item < TIN * TIN * CV; item += 256) {
+    const int px = item / CV;
+    const int y = iy0 + px / TIN, x = ix0 + px % TIN;
+    float f[8], h[8];
+    if ((unsigned)y < (unsigned)Hi && (unsigned)x < (unsigned)Wi) {
+      Vec8<T> v; v.load(src + ((size_t)y * Wi + x) * C); v.get(f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = silu_f(fmaf(a[i], f[i], b[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { f[i] = 0.f; h[i] = 0.f; }   // zero padding applies AFTER the activation
+    }
+    Vec8<__half> o;
+    o.set(h); o.store(&hs[px][cv * 8]);
+    o.set(f); o.store(&xs[px][cv * 8]);
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < TOUT * TOUT * CV; item += 256) {
+    const int opx = item / CV;
+    const int oy = opx / TOUT, ox = opx % TOUT;
+    float acc[8], raw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] = 0.f; raw[i] = 0.f; }
+    auto tap = [&](int ly, int lx, float w) {
+      float fh[8], fx[8];
+      Vec8<__half> v;
+      v.load(&hs[ly * TIN + lx][cv * 8]); v.get(fh);
+      v.load(&xs[ly * TIN + lx][cv * 8]); v.get(fx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[i] = fmaf(w, fh[i], acc[i]); raw[i] = fmaf(w, fx[i], raw[i]); }
+    };
+    if (RS == RS_UP) {
+      // local input coords (incl. halo offset 1): even out 2y: 3/4 h[y] + 1/4 h[y-1]; odd 2y+1: 3/4 h[y] + 1/4 h[y+1]
+      const int ly0 = (oy >> 1) + 1, lx0 = (ox >> 1) + 1;
+      const int ly1 = (oy & 1) ? ly0 + 1 : ly0 - 1, lx1 = (ox & 1) ? lx0 + 1 : lx0 - 1;
+      tap(ly0, lx0, 0.5625f); tap(ly0, lx1, 0.1875f); tap(ly1, lx0, 0.1875f); tap(ly1, lx1, 0.0625f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tap(2 * oy + i, 2 * ox + j, fir_tap(i) * fir_tap(j));   // (2Y+i-1) - iy0
+    }
+    const int Y = blockIdx.y * TOUT + oy, X = blockIdx.x * TOUT + ox;
+    const size_t o = (((size_t)n * Ho + Y) * Wo + X) * C + c;
+    Vec8<T> ov;
+    ov.set(acc); ov.store(out0 + o);
+    ov.set(raw); ov.store(out1 + o);
+  }
+}
+
 template <typename T>
 static void gn_apply_dispatch(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float2* ab, bool silu,
                               Resample rs, TensorDesc& out0, TensorDesc* out1) {
@@ -233,6 +313,13 @@ static void gn_apply_dispatch(cudaStream_t st, const TensorDesc& x0, const Tenso
     SG_CHECK(total < (1ull << 31), "gn_apply: tensor too large for 32-bit indexing");
     dim3 grid((unsigned)((total + 255) / 256), x0.N);
     T* o1 = (T*)out1->p;
+    if (std::is_same<T, __half>::value && rs == RS_UP && x0.H % 8 == 0 && x0.W % 8 == 0 && x0.C % 64 == 0) {
+      dim3 g(x0.W / 8, x0.H / 8, x0.N * (x0.C / 64));
+      gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+    } else if (std::is_same<T, __half>::value && rs == RS_DOWN && out0.H % 8 == 0 && out0.W % 8 == 0 && x0.C % 32 == 0) {
+      dim3 g(out0.W / 8, out0.H / 8, x0.N * (x0.C / 32));
+      gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+    } else
     if (rs == RS_DOWN) gn_apply_fir_kernel<T, RS_DOWN><<<grid, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
     else gn_apply_fir_kernel<T, RS_UP><<<grid, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
   }

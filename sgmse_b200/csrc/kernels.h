@@ -63,7 +63,10 @@ void launch_conv_tc2(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* d
 // third generation (conv_tc3.cu): CTA pairs, cta_group::2 M256 UMMAs; needs W % 16 == 0, H % 32 == 0 on top of v2.
 bool conv_tc3_supported(const ConvArgs& a, const TensorDesc& out);
 void launch_conv_tc3(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
-extern int g_tc_variant;   // 0: newest applicable kernel, 1: v1 only, 2: v2/v1 (no CTA pairs)
+// fourth generation (conv_tc4.cu): operands swapped (channels = UMMA M, pixels = UMMA N = 256), half the MMA issues
+bool conv_tc4_supported(const ConvArgs& a, const TensorDesc& out);
+void launch_conv_tc4(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
+extern int g_tc_variant;   // 0: newest applicable kernel (v4), 1: v1 only, 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1)
 
 // input layer: state float4 (x.re,x.im,y.re,y.im) -> conv3x3(4->C); w [36][C] (k = tap*4+cin), bias [C]
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,

@@ -15,7 +15,7 @@ template <typename T, int TP>
 __global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restrict__ state, int H, int W, int C,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          T* __restrict__ out, float* __restrict__ stats, int slots) {
-  __shared__ float in[TP][36];
+  __shared__ __align__(16) float in[TP][36];
   const int HW = H * W;
   const int m0 = blockIdx.x * TP;
   const int n = m0 / HW;
@@ -37,8 +37,13 @@ __global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restric
     float s = 0.f, q = 0.f;
     for (int p = 0; p < TP; ++p) {
       float acc = b;
+      const float4* ip = reinterpret_cast<const float4*>(&in[p][0]);   // warp-wide broadcast, 128-bit
 #pragma unroll
-      for (int k = 0; k < 36; ++k) acc = fmaf(wr[k], in[p][k], acc);
+      for (int k = 0; k < 9; ++k) {
+        const float4 v = ip[k];
+        acc = fmaf(wr[4 * k], v.x, acc); acc = fmaf(wr[4 * k + 1], v.y, acc);
+        acc = fmaf(wr[4 * k + 2], v.z, acc); acc = fmaf(wr[4 * k + 3], v.w, acc);
+      }
       T* op = out + (size_t)(m0 + p) * C + c;
       Act<T>::st(op, acc);
       const float r = Act<T>::ld(op);
