@@ -143,9 +143,150 @@ static void run(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int S, 
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// fp16 tensor-core path (mma.sync m16n8k16, fp32 accumulate), flash-style online softmax.
+// One block = 64 queries of one utterance (4 warps x 16 queries); keys/values stream through smem in tiles of 64.
+// This is the legacy HMMA path on purpose: attention is 0.16 % of the network FLOPs and its tiles (S <= 512 tokens,
+// head dim 128/256) are too small to amortise a TMEM/tcgen05 pipeline; the convolutions own the tcgen05 kernels.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+namespace {
+template <int C>
+__global__ void __launch_bounds__(128) attention_tc_kernel(const __half* __restrict__ qkv, int S, float scale_log2e,
+                                                           __half* __restrict__ out) {
+  constexpr int LD = C + 8;                       // padded row (halfs): 16-byte aligned rows, conflict-free fragments
+  extern __shared__ __align__(16) __half smh[];
+  __half* Qs = smh;                               // [64][LD]
+  __half* Ks = Qs + 64 * LD;
+  __half* Vs = Ks + 64 * LD;
+  const int n = blockIdx.y, q0 = blockIdx.x * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const __half* base = qkv + (size_t)n * S * 3 * C;
+
+  auto load_tile = [&](__half* dst, int row0, int col0) {
+    for (int i = tid; i < 64 * (C / 8); i += 128) {
+      const int r = i / (C / 8), cv = i % (C / 8);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row0 + r < S) v = *reinterpret_cast<const uint4*>(base + (size_t)(row0 + r) * 3 * C + col0 + cv * 8);
+      *reinterpret_cast<uint4*>(dst + r * LD + cv * 8) = v;
+    }
+  };
+  load_tile(Qs, q0, 0);
+
+  float oacc[C / 8][4];
+#pragma unroll
+  for (int j = 0; j < C / 8; ++j) { oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;     // rows g and g+8 of this warp's 16 queries
+
+  for (int k0 = 0; k0 < S; k0 += 64) {
+    __syncthreads();
+    load_tile(Ks, k0, C);
+    load_tile(Vs, k0, 2 * C);
+    __syncthreads();
+    float sacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f; }
+#pragma unroll 4
+    for (int kk = 0; kk < C / 16; ++kk) {
+      uint32_t a[4];
+      ldsm_x4(a, Qs + (warp * 16 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __half* kr = Ks + (j * 8 + g) * LD + kk * 16 + 2 * t;
+        mma_16816(sacc[j], a, *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+      }
+    }
+    // online softmax in the log2 domain
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int key = k0 + j * 8 + 2 * t + (i & 1);
+        sacc[j][i] = key < S ? sacc[j][i] * scale_log2e : -INFINITY;
+      }
+      mx0 = fmaxf(mx0, fmaxf(sacc[j][0], sacc[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(sacc[j][2], sacc[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float al0 = exp2f(m0 - mx0), al1 = exp2f(m1 - mx1);
+    m0 = mx0; m1 = mx1;
+    l0 *= al0; l1 *= al1;
+#pragma unroll
+    for (int j = 0; j < C / 8; ++j) { oacc[j][0] *= al0; oacc[j][1] *= al0; oacc[j][2] *= al1; oacc[j][3] *= al1; }
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f(sacc[j][0] - m0), p1 = exp2f(sacc[j][1] - m0);
+      const float p2 = exp2f(sacc[j][2] - m1), p3 = exp2f(sacc[j][3] - m1);
+      l0 += p0 + p1; l1 += p2 + p3;
+      // S accumulator tiles 2kk, 2kk+1 -> A fragment of the P V product (k = keys)
+      pa[j >> 1][(j & 1) * 2 + 0] = pack_half2(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_half2(p2, p3);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int jn = 0; jn < C / 8; jn += 2) {
+        uint32_t b[4];
+        // V tile is [key][channel]: transposed 8x8 loads give the k-major B fragments of two channel octets
+        ldsm_x4_trans(b, Vs + (kk * 16 + (lane & 15)) * LD + (jn + (lane >> 4)) * 8);
+        mma_16816(oacc[jn], pa[kk], b[0], b[1]);
+        mma_16816(oacc[jn + 1], pa[kk], b[2], b[3]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int qa = q0 + warp * 16 + g, qb = qa + 8;
+#pragma unroll
+  for (int j = 0; j < C / 8; ++j) {
+    const int c = j * 8 + 2 * t;
+    if (qa < S) *reinterpret_cast<__half2*>(out + ((size_t)n * S + qa) * C + c) = __floats2half2_rn(oacc[j][0] * i0, oacc[j][1] * i0);
+    if (qb < S) *reinterpret_cast<__half2*>(out + ((size_t)n * S + qb) * C + c) = __floats2half2_rn(oacc[j][2] * i1, oacc[j][3] * i1);
+  }
+}
+
+template <int C>
+void run_tc(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int S) {
+  const size_t smem = (size_t)3 * 64 * (C + 8) * sizeof(__half);
+  auto kern = attention_tc_kernel<C>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(S, 64), qkv.N);
+  kern<<<grid, 128, smem, st>>>((const __half*)qkv.p, S, 1.4426950408889634f / sqrtf((float)C), (__half*)out.p);
+  CUDA_OK(cudaGetLastError());
+}
+}  // namespace
+
+int g_attn_variant = 0;   // 0: tensor-core kernel where it applies, 1: always the fp32 CUDA-core kernel
+
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out) {
   const int C = out.C, S = qkv.H * qkv.W;
   SG_CHECK(qkv.C == 3 * C && C % 8 == 0, "attention: qkv must have 3C channels");
+  if (qkv.dt == DT_F16 && g_attn_variant == 0) {
+    if (C == 256) { run_tc<256>(st, qkv, out, S); return; }
+    if (C == 128) { run_tc<128>(st, qkv, out, S); return; }
+  }
   auto smem_for = [&](int QT) { return (size_t)((QT + KT) * (C + 1) + QT * (S + 1)) * sizeof(float); };
   const size_t lim = 220 * 1024;
   int QT = 32;

@@ -1074,6 +1074,7 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   }
   else if (k == "use_graphs") e->cfg.use_graphs = value != 0;
   else if (k == "tc_variant") { sgmse::g_tc_variant = (int)value; clear_graphs(*e); }
+  else if (k == "attn_variant") { sgmse::g_attn_variant = (int)value; clear_graphs(*e); }
   else if (k == "tc_mask") { e->tc_mask = value; for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec); e->graphs.clear(); }
   else SG_CHECK(false, "unknown option '%s'", key);
   API_END

@@ -82,6 +82,7 @@ void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, con
 
 // ---- attention: qkv [N,H,W,3C] (q|k|v), out [N,H,W,C] = softmax(q k^T / sqrt(C)) v over H*W tokens
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out);
+extern int g_attn_variant;   // 0: fp16 mma.sync flash kernel where it applies (C in {128,256}), 1: fp32 CUDA-core kernel
 
 // ---- time embedding ----
 struct TembWeights {
