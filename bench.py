@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=16)
     ap.add_argument("--N", type=int, default=30)
     ap.add_argument("--mode", default="fp16_tc")
+    ap.add_argument("--lanes", type=int, default=2, help="concurrent launch sequences inside the sampler graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
@@ -187,7 +188,7 @@ def workload_config(args):
     return {"workload": f"SGMSE+ NCSN++ (VoiceBank-DEMAND config, 65.6 M params, random init), 16 kHz, 4-s clips, "
                         f"batch {args.batch} per GPU, PC sampler reverse_diffusion+ald N={args.N} snr 0.5 "
                         f"({2 * args.N} network evaluations), STFT 510/128",
-            "global_batch": args.batch * args.gpus, "per_gpu_batch": args.batch, "micro_batch": args.micro_batch,
+            "global_batch": args.batch * args.gpus, "per_gpu_batch": args.batch, "micro_batch": args.micro_batch, "lanes": args.lanes,
             "parallelism": f"dp{args.gpus} (batch sharded, no data-path collective)",
             "l2": "working set per step (>10 GB of activations per micro-batch) exceeds the 126 MB L2; no flush needed"}
 
@@ -211,6 +212,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     eng = Engine(EngineConfig(mode=args.mode, max_batch=args.micro_batch, use_graphs=True), device=dev)
+    eng.set_option("lanes", args.lanes)
     # weights: rank 0 creates them, NCCL broadcast over NVLink, packed per rank
     n = eng.weights_numel()
     if rank == 0:

@@ -206,7 +206,28 @@ void pack_conv(Engine& e, const std::vector<PackSrc>& srcs, int cout, bool out_m
   }
 }
 
+void ensure_lanes(Engine& e, int want);
+
+void free_workspace(Engine& e) {
+  for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec);
+  e.graphs.clear();
+  for (auto& p : e.fft_plans) cufftDestroy(p.second);
+  e.fft_plans.clear();
+  cudaFree(e.arena.base); e.arena = Arena{};
+  cudaFree(e.state); cudaFree(e.xmean); cudaFree(e.temb_table); cudaFree(e.temb_scratch); cudaFree(e.t_dev);
+  cudaFree(e.coef_dev); cudaFree(e.rng_dev); cudaFree(e.lv_scratch); cudaFree(e.dbg_flag);
+  e.state = nullptr; e.xmean = nullptr; e.temb_table = nullptr; e.temb_scratch = nullptr; e.t_dev = nullptr;
+  e.coef_dev = nullptr; e.rng_dev = nullptr; e.lv_scratch = nullptr; e.dbg_flag = nullptr;
+  e.persist_px = 0; e.persist_rows = 0;
+  for (int i = 0; i < 4; ++i) { cudaFree(e.stft_buf[i]); e.stft_buf[i] = nullptr; e.stft_cap[i] = 0; }
+  if (e.own_stream) { cudaStreamDestroy(e.own_stream); e.own_stream = nullptr; }
+  for (auto& c : e.conv_events) { cudaEventDestroy(c.start); cudaEventDestroy(c.stop); }
+  e.conv_events.clear();
+}
+
 void free_weights(Engine& e) {
+  if (!e.owns_weights) return;
+  if (e.lanes.size() > 1) ensure_lanes(e, 1);   // shadow engines hold pointers into the weights being freed
   for (void* p : e.dev_allocs) cudaFree(p);
   e.dev_allocs.clear();
   if (e.blob_dev) { cudaFree(e.blob_dev); e.blob_dev = nullptr; }
@@ -520,6 +541,50 @@ struct Fwd {
 void clear_graphs(Engine& e) {
   for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec);
   e.graphs.clear();
+  ++e.generation;
+}
+
+void free_workspace(Engine& e);
+
+// Shadow engines for concurrent lanes (see engine.h): same weights, private workspace.
+void ensure_lanes(Engine& e, int want) {
+  if (e.lanes.empty()) { e.lanes.push_back(&e); e.lane_streams.push_back(nullptr); }
+  if ((int)e.lanes.size() > want) {          // shrink
+    CUDA_OK(cudaDeviceSynchronize());
+    clear_graphs(e);
+    while ((int)e.lanes.size() > want) {
+      Engine* l = e.lanes.back();
+      free_workspace(*l);
+      delete l;
+      cudaStreamDestroy(e.lane_streams.back());
+      e.lanes.pop_back(); e.lane_streams.pop_back();
+    }
+  }
+  while ((int)e.lanes.size() < want) {
+    Engine* l = new Engine(e);               // copies config, layer table and (shared) weight pointers
+    l->owns_weights = false;
+    l->dev_allocs.clear();
+    l->arena = Arena{};
+    l->state = nullptr; l->xmean = nullptr; l->temb_table = nullptr; l->temb_scratch = nullptr; l->t_dev = nullptr;
+    l->coef_dev = nullptr; l->rng_dev = nullptr; l->lv_scratch = nullptr; l->dbg_flag = nullptr;
+    l->persist_px = 0; l->persist_rows = 0;
+    l->graphs.clear(); l->fft_plans.clear();
+    for (int i = 0; i < 4; ++i) { l->stft_buf[i] = nullptr; l->stft_cap[i] = 0; }
+    l->own_stream = nullptr;
+    l->lanes.clear(); l->lane_streams.clear(); l->lane_events.clear();
+    l->taps.clear(); l->taps4.clear(); l->conv_events.clear();
+    l->record_taps = false; l->time_convs = false;
+    l->kernel_launches = 0; l->graph_launches = 0; l->generation = 0;
+    cudaStream_t s = nullptr;
+    CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    e.lanes.push_back(l);
+    e.lane_streams.push_back(s);
+  }
+  while ((int)e.lane_events.size() < want + 1) {
+    cudaEvent_t ev;
+    CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e.lane_events.push_back(ev);
+  }
 }
 
 // Workspace for one forward pass of (B, F, T).  The bump allocation is replayed identically by every
@@ -719,6 +784,8 @@ void sample_chunk(Engine& e, const float2* y, int Bc, int F, int T, const sgmse_
   (void)inside_capture;
 }
 
+void ensure_stft_buf(Engine& e, int slot, size_t bytes);
+
 void prepare_tables(Engine& e, const sgmse_b200_sampler& s, cudaStream_t st) {
   const SamplerTables tb = make_tables(e, s);
   CUDA_OK(cudaMemcpyAsync(e.t_dev, tb.ts.data(), tb.ts.size() * 4, cudaMemcpyHostToDevice, st));
@@ -758,23 +825,59 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
       sample_chunk(e, y + b0 * px1, Bc, F, T, s, nchunk, (size_t)B * px1, out + b0 * px1, st, false);
       continue;
     }
-    // graph path: the graph works on engine-owned staging (state <- ystage, xmean/out via ostage)
-    GraphKey key{Bc, F, T, s.N, s.predictor, s.corrector, csteps, s.denoise, s.probability_flow, s.snr};
+    // graph path: the micro-batch is split over concurrent lanes; every lane's launch sequence works on
+    // lane-owned staging (pointer-stable), forked from / joined into the caller's stream inside ONE graph.
+    const int L = std::max(1, std::min(e.num_lanes, Bc));
+    ensure_lanes(e, std::max(L, (int)e.lanes.size()));
+    const int per = (Bc + L - 1) / L;
+    int lb[16], ln[16];
+    for (int i = 0; i < L; ++i) { lb[i] = std::min(Bc, i * per); ln[i] = std::min(Bc, lb[i] + per) - lb[i]; }
+    for (int i = 0; i < L; ++i) {
+      if (ln[i] <= 0) continue;
+      Engine& le = *e.lanes[i];
+      ensure_arena(le, ln[i], F, T);
+      ensure_persistent(le, (size_t)per * px1, std::max({mb, 64, s.N * (csteps + 1) + 1}));
+      ensure_stft_buf(le, 3, (size_t)per * px1 * 8);
+      if (i > 0) prepare_tables(le, s, st);                       // lane 0's tables were prepared above
+      RngParams lrp{s.seed, s.utt_offset + b0 + lb[i], 0};
+      CUDA_OK(cudaMemcpyAsync(le.rng_dev, &lrp, sizeof(lrp), cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      CUDA_OK(cudaMemcpyAsync(le.stft_buf[3], y + (b0 + lb[i]) * px1, ln[i] * px1 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    }
+    long long gen = 0;
+    for (int i = 0; i < L; ++i) gen += e.lanes[i]->generation;
+    if (gen != e.lanes_generation_seen) {          // some lane re-allocated a buffer a captured graph points to
+      for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec);
+      e.graphs.clear();
+      e.lanes_generation_seen = gen;
+    }
+    GraphKey key{Bc * 64 + L, F, T, s.N, s.predictor, s.corrector, csteps, s.denoise, s.probability_flow, s.snr};
     auto it = e.graphs.find(key);
     if (it == e.graphs.end()) {
       // one eager network evaluation first: sets function attributes and surfaces launch errors early
       {
-        launch_pack_state(st, y + b0 * px1, y + b0 * px1, Bc, F, T, e.state);
+        launch_pack_state(st, y + b0 * px1, y + b0 * px1, ln[0], F, T, e.state);
         Fwd f{e, st, e.temb_table, 0, false, e.cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
-        f.run(e.state, Bc, F, T);
+        f.run(e.state, ln[0], F, T);
         CUDA_OK(cudaStreamSynchronize(st));
       }
       cudaGraph_t g = nullptr;
-      const long long launches_before = e.kernel_launches;
+      long long before = 0;
+      for (int i = 0; i < L; ++i) before += e.lanes[i]->kernel_launches;
+      std::vector<long long> saved(L);
+      for (int i = 0; i < L; ++i) saved[i] = e.lanes[i]->kernel_launches;
       CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       try {
-        // y is read from / the result written to engine-owned buffers so the graph is pointer-stable
-        sample_chunk(e, (const float2*)e.stft_buf[3], Bc, F, T, s, nullptr, 0, (float2*)e.stft_buf[3], st, true);
+        CUDA_OK(cudaEventRecord(e.lane_events[0], st));
+        for (int i = 1; i < L; ++i) if (ln[i] > 0) CUDA_OK(cudaStreamWaitEvent(e.lane_streams[i], e.lane_events[0], 0));
+        for (int i = 0; i < L; ++i) {
+          if (ln[i] <= 0) continue;
+          Engine& le = *e.lanes[i];
+          cudaStream_t ls = i == 0 ? st : e.lane_streams[i];
+          sample_chunk(le, (const float2*)le.stft_buf[3], ln[i], F, T, s, nullptr, 0, (float2*)le.stft_buf[3], ls, true);
+          if (i > 0) CUDA_OK(cudaEventRecord(e.lane_events[i], ls));
+        }
+        for (int i = 1; i < L; ++i) if (ln[i] > 0) CUDA_OK(cudaStreamWaitEvent(st, e.lane_events[i], 0));
       } catch (...) {
         cudaStreamEndCapture(st, &g);
         if (g) cudaGraphDestroy(g);
@@ -784,15 +887,16 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
       cudaGraphExec_t ge = nullptr;
       CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
       cudaGraphDestroy(g);
-      const long long nodes = e.kernel_launches - launches_before;   // kernels recorded, not executed
-      e.kernel_launches = launches_before;
-      it = e.graphs.emplace(key, GraphEntry{ge, nodes}).first;
+      long long after = 0;
+      for (int i = 0; i < L; ++i) { after += e.lanes[i]->kernel_launches; e.lanes[i]->kernel_launches = saved[i]; }
+      it = e.graphs.emplace(key, GraphEntry{ge, after - before}).first;   // kernels recorded, not executed
     }
-    CUDA_OK(cudaMemcpyAsync(e.stft_buf[3], y + b0 * px1, Bc * px1 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaGraphLaunch(it->second.exec, st));
     ++e.graph_launches;
     e.kernel_launches += it->second.kernel_nodes;
-    CUDA_OK(cudaMemcpyAsync(out + b0 * px1, e.stft_buf[3], Bc * px1 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    for (int i = 0; i < L; ++i)
+      if (ln[i] > 0)
+        CUDA_OK(cudaMemcpyAsync(out + (b0 + lb[i]) * px1, e.lanes[i]->stft_buf[3], ln[i] * px1 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
   }
   if (nfe) *nfe = s.N * (csteps + 1);
 }
@@ -805,7 +909,7 @@ void ensure_stft_buf(Engine& e, int slot, size_t bytes) {
   if (e.stft_buf[slot]) { CUDA_OK(cudaDeviceSynchronize()); cudaFree(e.stft_buf[slot]); e.stft_buf[slot] = nullptr; }
   CUDA_OK(cudaMalloc(&e.stft_buf[slot], bytes));
   e.stft_cap[slot] = bytes;
-  if (slot == 3) { for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec); e.graphs.clear(); }
+  if (slot == 3) clear_graphs(e);
 }
 
 cufftHandle fft_plan(Engine& e, bool inverse, int n_fft, int batch) {
@@ -915,13 +1019,10 @@ int sgmse_b200_create(const sgmse_b200_config* cfg, sgmse_b200_engine** out) {
 void sgmse_b200_destroy(sgmse_b200_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
-  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec);
-  for (auto& p : e->fft_plans) cufftDestroy(p.second);
+  try { if (e->lanes.size() > 1) ensure_lanes(*e, 1); } catch (...) {}
+  for (cudaEvent_t ev : e->lane_events) cudaEventDestroy(ev);
   free_weights(*e);
-  cudaFree(e->arena.base);
-  cudaFree(e->state); cudaFree(e->xmean); cudaFree(e->temb_table); cudaFree(e->temb_scratch); cudaFree(e->t_dev);
-  cudaFree(e->coef_dev); cudaFree(e->rng_dev); cudaFree(e->lv_scratch); cudaFree(e->dbg_flag);
-  for (int i = 0; i < 4; ++i) cudaFree(e->stft_buf[i]);
+  free_workspace(*e);
   delete e;
 }
 
@@ -1075,6 +1176,11 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "use_graphs") e->cfg.use_graphs = value != 0;
   else if (k == "tc_variant") { sgmse::g_tc_variant = (int)value; clear_graphs(*e); }
   else if (k == "attn_variant") { sgmse::g_attn_variant = (int)value; clear_graphs(*e); }
+  else if (k == "lanes") {
+    SG_CHECK(value >= 1 && value <= 8, "lanes must be in 1..8");
+    e->num_lanes = (int)value;
+    clear_graphs(*e);
+  }
   else if (k == "tc_mask") { e->tc_mask = value; for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec); e->graphs.clear(); }
   else SG_CHECK(false, "unknown option '%s'", key);
   API_END

@@ -126,6 +126,18 @@ struct sgmse_b200_engine {
   void* stft_buf[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t stft_cap[4] = {0, 0, 0, 0};
 
+  // Concurrent lanes: inside a captured sampler graph the micro-batch is split over `num_lanes` independent
+  // launch sequences on forked streams, so that the HBM-bound kernels of one lane (GroupNorm apply, FIR, PC
+  // update) overlap the tensor-bound convolutions of the other.  A lane is a shadow engine: it shares the
+  // packed weights (owns_weights == false) and owns its workspace, state and staging buffers.
+  int num_lanes = 2;
+  bool owns_weights = true;
+  std::vector<sgmse_b200_engine*> lanes;      // lanes[0] == this
+  std::vector<cudaStream_t> lane_streams;     // lane_streams[0] unused (lane 0 runs on the caller's stream)
+  std::vector<cudaEvent_t> lane_events;       // [0] fork, [i] join of lane i
+  long long generation = 0;                   // bumped whenever a graph-visible buffer is re-allocated
+  long long lanes_generation_seen = -1;
+
   // options / counters
   bool record_taps = false;
   bool time_convs = false;
