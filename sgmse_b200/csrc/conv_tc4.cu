@@ -350,8 +350,16 @@ bool conv_tc4_supported(const ConvArgs& a, const TensorDesc& out) { return conv_
 
 void launch_conv_tc4(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   SG_CHECK(conv_tc4_supported(a, out), "conv_tc4: unsupported shape");
-  if (out.H % 32 == 0) launch4<2, 3, 5>(st, a, out, dbg);
-  else launch4<1, 4, 6>(st, a, out, dbg);
+  // Ring depths trade prefetch distance against shared memory left for co-resident blocks of the HBM-bound kernels
+  // that the other lane of the sampler graph runs concurrently (each needs 1 KB of reserved smem per block).
+  static const int ring_cfg = [] { const char* v = getenv("SGMSE_B200_TC4_RINGS"); return v ? atoi(v) : 0; }();
+  if (out.H % 32 == 0) {
+    if (ring_cfg == 1) launch4<2, 2, 5>(st, a, out, dbg);
+    else if (ring_cfg == 2) launch4<2, 2, 4>(st, a, out, dbg);
+    else launch4<2, 3, 5>(st, a, out, dbg);
+  } else {
+    launch4<1, 4, 6>(st, a, out, dbg);
+  }
 }
 
 }  // namespace sgmse

@@ -255,6 +255,100 @@ __global__ void __launch_bounds__(256) out_conv_coop_kernel(const T* __restrict_
   }
 }
 
+// fp16 tensor-core variant (mma.sync m16n8k16, N = 8 with the 4 real outputs in columns 0..3): a block stages a
+// 16x16 pixel tile (+1 halo) of the activation in shared memory once, every warp computes two 16-pixel rows with
+// 9 taps x C/16 MMAs each.  ~15x fewer instructions than the CUDA-core kernels above; HBM/L2-bound.
+__device__ __forceinline__ void oc_ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void oc_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int C>
+__global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restrict__ act, int H, int W,
+                                                           const float* __restrict__ w, float4 bias,
+                                                           const float4* __restrict__ addend, float4* __restrict__ out) {
+  constexpr int LD = C + 8;            // halfs per staged pixel (16-byte aligned, conflict-free ldmatrix rows)
+  constexpr int KS = C / 16;
+  extern __shared__ __align__(16) uint8_t oc_smem[];
+  __half* tile = reinterpret_cast<__half*>(oc_smem);                       // [18*18][LD]
+  uint2* wfrag = reinterpret_cast<uint2*>(oc_smem + (size_t)18 * 18 * LD * 2);   // [9*KS][32] B fragments
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16, n = blockIdx.z;
+  // B fragments: b0 = (k = 2t, 2t+1 ; n = g), b1 = (k = 2t+8, 2t+9 ; n = g); output columns >= 4 are zero padding
+  for (int i = tid; i < 9 * KS * 32; i += 256) {
+    const int l = i & 31, blk = i >> 5;
+    const int tap = blk / KS, kk = blk % KS, gg = l >> 2, tt = l & 3;
+    uint2 v = make_uint2(0u, 0u);
+    if (gg < 4) {
+      const float* wp = w + ((size_t)tap * C + kk * 16 + 2 * tt) * 4 + gg;
+      const __half2 b0 = __floats2half2_rn(wp[0], wp[4]);
+      const __half2 b1 = __floats2half2_rn(wp[32], wp[36]);
+      v.x = *reinterpret_cast<const uint32_t*>(&b0);
+      v.y = *reinterpret_cast<const uint32_t*>(&b1);
+    }
+    wfrag[i] = v;
+  }
+  for (int i = tid; i < 18 * 18 * (C / 8); i += 256) {
+    const int px = i / (C / 8), cv = i % (C / 8);
+    const int y = y0 - 1 + px / 18, x = x0 - 1 + px % 18;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W)
+      v = *reinterpret_cast<const uint4*>(act + (((size_t)n * H + y) * W + x) * C + cv * 8);
+    *reinterpret_cast<uint4*>(tile + (size_t)px * LD + cv * 8) = v;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int rr = 0; rr < 2; ++rr) {
+    const int ly = warp * 2 + rr;                 // row inside the 16x16 tile
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      // A fragment rows = the 16 pixels (ly + dy, 0..15 + dx) of the staged tile (halo offset 1)
+      const __half* arow = tile + (size_t)((ly + tap / 3) * 18 + (tap % 3) + (lane & 15)) * LD + (lane >> 4) * 8;
+      const uint2* wf = wfrag + (size_t)tap * KS * 32 + lane;
+#pragma unroll 4
+      for (int kk = 0; kk < KS; ++kk) {
+        uint32_t a[4];
+        oc_ldsm_x4(a, arow + kk * 16);
+        const uint2 b = wf[kk * 32];
+        oc_mma(acc, a, b.x, b.y);
+      }
+    }
+    // C fragment: (row g, cols 2t, 2t+1) and (row g+8, same cols); real outputs are columns 0..3 -> lanes with t < 2
+    if (t < 2) {
+      const int y = y0 + ly;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int x = x0 + g + h * 8;
+        if (y < H && x < W) {
+          const size_t o = ((size_t)n * H + y) * W + x;
+          float2 r = make_float2(acc[2 * h] + (t == 0 ? bias.x : bias.z), acc[2 * h + 1] + (t == 0 ? bias.y : bias.w));
+          if (addend) { const float2 ad = reinterpret_cast<const float2*>(addend + o)[t]; r.x += ad.x; r.y += ad.y; }
+          reinterpret_cast<float2*>(out + o)[t] = r;
+        }
+      }
+    }
+  }
+}
+
+template <int C>
+static void out_conv_mma_launch(cudaStream_t st, const TensorDesc& act, const float* w, float4 b, const float4* addend,
+                                float4* out) {
+  const size_t smem = (size_t)18 * 18 * (C + 8) * 2 + (size_t)9 * (C / 16) * 32 * sizeof(uint2);
+  auto k = out_conv_mma_kernel<C>;
+  CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(act.W, 16), cdiv(act.H, 16), act.N);
+  k<<<grid, 256, smem, st>>>((const __half*)act.p, act.H, act.W, w, b, addend, out);
+  CUDA_OK(cudaGetLastError());
+}
+
+int g_outconv_variant = 0;   // 0: mma.sync kernel for fp16 C in {128, 256}; 1: CUDA-core kernels
+
 template <typename T>
 static void out_conv_dispatch(cudaStream_t st, const TensorDesc& act, const float4* w, float4 b, const float4* addend,
                               float4* out) {
@@ -287,6 +381,11 @@ void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, con
   SG_CHECK((size_t)9 * act.C * sizeof(float4) <= 96 * 1024, "out conv: %d channels exceed the shared-memory weight buffer", act.C);
   // `bias` is a HOST pointer to 4 floats (kept with the layer description)
   const float4 b = make_float4(bias[0], bias[1], bias[2], bias[3]);
+  if (act.dt == DT_F16 && g_outconv_variant == 0 && (act.C == 128 || act.C == 256)) {
+    if (act.C == 128) out_conv_mma_launch<128>(st, act, w, b, addend, out);
+    else out_conv_mma_launch<256>(st, act, w, b, addend, out);
+    return;
+  }
   if (act.dt == DT_F16) out_conv_dispatch<__half>(st, act, (const float4*)w, b, addend, out);
   else out_conv_dispatch<float>(st, act, (const float4*)w, b, addend, out);
 }

@@ -201,6 +201,44 @@ def test_full_size_forward(full_sd, mode, tol, T):
     eng.close()
 
 
+def test_full_size_48k_forward():
+    """BASELINE config 3 backbone (ncsnpp_48k defaults: no progressive skips, attention only in the bottleneck,
+    output_layer before /t), 64.7 M parameters, F = 768."""
+    cfg = NetConfig.ncsnpp_48k()
+    sd = o_w.make_state_dict(cfg, seed=4)
+    eng = Engine(EngineConfig.ncsnpp_48k(mode="fp16_tc", max_batch=1))
+    eng.load_state_dict(sd)
+    g = torch.Generator().manual_seed(13)
+    x = torch.complex(torch.randn(1, 2, 768, 128, generator=g), torch.randn(1, 2, 768, 128, generator=g)) * 0.3
+    t = torch.tensor([0.31])
+    with torch.no_grad():
+        ref = o_net.forward(sd, cfg, x, t)
+    out = eng.dnn_forward(x.cuda(), t.cuda())
+    err = rel_l2(out, ref)
+    print(f"full-size 48k forward fp16_tc: rel-L2 {err:.3e}")
+    assert err < 2e-2 and eng.counter("tc_convs_last_forward") > 0
+    eng.close()
+
+
+def test_end_to_end_si_sdr(full_sd):
+    """Waveform-level agreement of the product path with the oracle on the full-size network (N=2, injected noise):
+    SI-SDR(oracle, engine) as defined in the reference (util/other.py:64-68).  PESQ is not installable offline."""
+    cfg = NetConfig.ncsnpp()
+    eng = Engine(EngineConfig(mode="fp16_tc", max_batch=1))
+    eng.load_state_dict(full_sd)
+    g = torch.Generator().manual_seed(21)
+    L, N = 16000, 2                                  # 1-s clip -> 126 frames -> padded to 128
+    wav = 0.1 * torch.randn(1, L, generator=g)
+    Tp = eng.padded_frames(L)
+    draws = o_sde.make_noise((1, 1, 256, Tp), o_sde.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=8)
+    ref = o_pipe.enhance(full_sd, cfg, o_spec.SpecConfig(), o_sde.OUVE(), wav, draws, N=N)[0].numpy()
+    got = eng.enhance(wav.cuda(), noise=torch.stack(draws).cuda(), N=N)[0].cpu().numpy()
+    sdr = o_pipe.si_sdr(ref, got)
+    print(f"end-to-end SI-SDR(oracle, engine) = {sdr:.1f} dB")
+    assert sdr > 35.0
+    eng.close()
+
+
 def test_tc_kernel_variants_agree(full_sd):
     """The operand-reuse tcgen05 kernel (conv_tc2.cu) and the first-generation one (conv_tc.cu) compute the same
     convolutions (different accumulation order only)."""
