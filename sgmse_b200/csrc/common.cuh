@@ -45,10 +45,12 @@ template <typename T> struct Act;
 template <> struct Act<float> {
   static __device__ __forceinline__ float ld(const float* p) { return *p; }
   static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+  static __device__ __forceinline__ float rnd(float v) { return v; }       // value as it will be read back
 };
 template <> struct Act<__half> {
   static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
   static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+  static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
 };
 
 // 8-element vectors (16 B of half / 32 B of float)

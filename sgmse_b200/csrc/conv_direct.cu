@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams P) 
         v *= P.scale;
         T* op = (T*)P.out + (size_t)m * P.Cout + c;
         Act<T>::st(op, v);
-        const float r = Act<T>::ld(op);
+        const float r = Act<T>::rnd(v);
         ssum[j] += r; ssq[j] += r * r;
       }
     }

@@ -39,7 +39,7 @@ constexpr int MAX_SEG = 4;
 
 struct Tc4Params {
   int tiles_w, tiles_h;
-  int num_m_tiles, num_tiles;
+  int num_m_tiles, num_tiles, n_cblk;
   int N, Cout;
   int nseg;
   int seg_chunks[MAX_SEG];
@@ -167,7 +167,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       int sa = 0; uint32_t pa = 0;
       int sb = 0; uint32_t pb = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const int m_tile = tile % P.num_m_tiles, c_blk = tile / P.num_m_tiles;
+        const int c_blk = tile % P.n_cblk, m_tile = tile / P.n_cblk;   // channel tiles of one pixel tile run back to back (L2 reuse)
         const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
         const int x0 = (rem % P.tiles_w) * 8, y0 = (rem / P.tiles_w) * (16 * SUBS);
         for (int s = 0; s < P.nseg; ++s) {
@@ -242,7 +242,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const int ch_c16 = (ch & 63) >> 3;
     int as = 0; uint32_t as_phase = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-      const int m_tile = tile % P.num_m_tiles, c_blk = tile / P.num_m_tiles;
+      const int c_blk = tile % P.n_cblk, m_tile = tile / P.n_cblk;   // channel tiles of one pixel tile run back to back (L2 reuse)
       const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
       const int tx = rem % P.tiles_w, ty = rem / P.tiles_w;
       const int x0 = tx * 8, y0 = ty * (16 * SUBS);
@@ -306,7 +306,8 @@ void launch4(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   Tc4Params P{};
   P.tiles_w = out.W / 8; P.tiles_h = out.H / (16 * SUBS);
   P.num_m_tiles = P.tiles_w * P.tiles_h * out.N;
-  P.num_tiles = P.num_m_tiles * (out.C / BLOCK_C);
+  P.n_cblk = out.C / BLOCK_C;
+  P.num_tiles = P.num_m_tiles * P.n_cblk;
   P.N = out.N; P.Cout = out.C;
   const TensorDesc* srcs[MAX_SEG];
   int taps[MAX_SEG];

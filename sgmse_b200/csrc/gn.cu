@@ -133,7 +133,28 @@ gn_apply_plain_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1
   }
   const T* sp = src + (size_t)n * HW * Cs + cs;
   T* op = out + (size_t)n * HW * Ct + c;
-  for (int p = blockIdx.x * ppb + pl; p < HW; p += gridDim.x * ppb) {
+  // 4 independent 128-bit loads in flight per thread (grid is sized for 4 pixels per thread)
+  const int stride = gridDim.x * ppb;
+  int p = blockIdx.x * ppb + pl;
+  for (; p + 3 * stride < HW; p += 4 * stride) {
+    Vec8<T> v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u].load(sp + (size_t)(p + u * stride) * Cs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      v[u].get(f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float h = fmaf(a[i], f[i], b[i]);
+        if (SILU) h = silu_f(h);
+        f[i] = h;
+      }
+      v[u].set(f);
+      v[u].store(op + (size_t)(p + u * stride) * Ct);
+    }
+  }
+  for (; p < HW; p += stride) {
     Vec8<T> v; float f[8];
     v.load(sp + (size_t)p * Cs);
     v.get(f);

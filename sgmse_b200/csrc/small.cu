@@ -44,9 +44,8 @@ __global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restric
         acc = fmaf(wr[4 * k], v.x, acc); acc = fmaf(wr[4 * k + 1], v.y, acc);
         acc = fmaf(wr[4 * k + 2], v.z, acc); acc = fmaf(wr[4 * k + 3], v.w, acc);
       }
-      T* op = out + (size_t)(m0 + p) * C + c;
-      Act<T>::st(op, acc);
-      const float r = Act<T>::ld(op);
+      Act<T>::st(out + (size_t)(m0 + p) * C + c, acc);
+      const float r = Act<T>::rnd(acc);
       s += r; q += r * r;
     }
     if (stats) {
@@ -90,7 +89,7 @@ __global__ void __launch_bounds__(128) combine_kernel(const float4* __restrict__
       const size_t o = (size_t)(m0 + p) * C + c;
       float acc = b + w0 * v.x + w1 * v.y + w2 * v.z + w3 * v.w + Act<T>::ld(h + o);
       Act<T>::st(out + o, acc);
-      const float r = Act<T>::ld(out + o);
+      const float r = Act<T>::rnd(acc);
       s += r; q += r * r;
     }
     if (stats) {
