@@ -342,7 +342,7 @@ struct Fwd {
   void conv(const ConvArgs& a, TensorDesc& out, int cls) {
     if (dry) return;
     const bool want_tc = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && ((e.tc_mask >> cls) & 1);
-    const bool tc = want_tc && conv_tc_supported(a, out);
+    const bool tc = a.gn_ab != nullptr || (want_tc && conv_tc_supported(a, out));
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e.time_convs) {
       CUDA_OK(cudaEventCreate(&ev0)); CUDA_OK(cudaEventCreate(&ev1));
@@ -374,30 +374,49 @@ struct Fwd {
     const int Ho = l.up ? x0.H * 2 : (l.down ? x0.H / 2 : x0.H);
     const int Wo = l.up ? x0.W * 2 : (l.down ? x0.W / 2 : x0.W);
     float2* ab0 = gn(x0, x1, l.gn0_w, l.gn0_b);
-    TensorDesc h0 = act(N, Ho, Wo, Ct, false);
+    // Fused path (conv_tc5): the 3x3 convs read the RAW tensor and apply GroupNorm+SiLU on the way into shared
+    // memory, so the gn_apply pass (one read + one write of the tensor) and its buffer disappear.
+    const bool fuse_ok = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && g_tc_variant == 0 && ((e.tc_mask >> 8) & 1);
+    const bool fuse0 = fuse_ok && rs == RS_NONE && l.c0.w_tc && conv_tc5_shape_ok(Ho, Wo, x0.C, x1 ? x1->C : 0, l.cout, 0);
+    const int nraw1 = l.shortcut ? ((rs == RS_NONE && x1) ? 2 : 1) : 1;
+    const bool fuse1 = fuse_ok && l.c1.w_tc && conv_tc5_shape_ok(Ho, Wo, l.cout, 0, l.cout, nraw1) &&
+                       (l.shortcut || l.c1.identity_tail);
+    TensorDesc h0;
     TensorDesc xr;                                 // FIR-resampled raw input (up/down blocks)
     if (rs != RS_NONE) {
       SG_CHECK(!x1, "resampling resblock with concatenated input");
+      h0 = act(N, Ho, Wo, Ct, false);
       xr = act(N, Ho, Wo, Ct, false);
       if (!dry) { launch_gn_apply(st, x0, nullptr, ab0, true, rs, h0, &xr); count(); }
-    } else if (!dry) {
-      launch_gn_apply(st, x0, x1, ab0, true, RS_NONE, h0, nullptr); count();
+    } else if (!fuse0) {
+      h0 = act(N, Ho, Wo, Ct, false);
+      if (!dry) { launch_gn_apply(st, x0, x1, ab0, true, RS_NONE, h0, nullptr); count(); }
     }
     TensorDesc h1 = act(N, Ho, Wo, l.cout, true);
     {
       ConvArgs a;
-      a.nseg = 1; a.seg[0].src = h0; a.seg[0].taps = 9;
+      a.nseg = 1; a.seg[0].taps = 9;
+      if (fuse0) {
+        a.seg[0].src = x0; a.gn_ab = ab0;
+        if (x1) { a.gn_has_cat = true; a.gn_cat = *x1; }
+      } else {
+        a.seg[0].src = h0;
+      }
       a.w_direct = l.c0.w_direct; a.w_tc = l.c0.w_tc; a.w_tc_ld = l.c0.w_tc_ld;
       a.temb = temb + l.temb_off; a.temb_stride = temb_stride;   // Conv_0.bias is folded into the table
       conv(a, h1, 0);
     }
     float2* ab1 = gn(h1, nullptr, l.gn1_w, l.gn1_b);
-    TensorDesc h2 = act(N, Ho, Wo, l.cout, false);
-    if (!dry) { launch_gn_apply(st, h1, nullptr, ab1, true, RS_NONE, h2, nullptr); count(); }
+    TensorDesc h2;
+    if (!fuse1) {
+      h2 = act(N, Ho, Wo, l.cout, false);
+      if (!dry) { launch_gn_apply(st, h1, nullptr, ab1, true, RS_NONE, h2, nullptr); count(); }
+    }
     TensorDesc out = act(N, Ho, Wo, l.cout, true);
     {
       ConvArgs a;
-      a.nseg = 1; a.seg[0].src = h2; a.seg[0].taps = 9;
+      a.nseg = 1; a.seg[0].taps = 9;
+      if (fuse1) { a.seg[0].src = h1; a.gn_ab = ab1; } else { a.seg[0].src = h2; }
       if (l.shortcut) {
         if (rs != RS_NONE) { a.seg[a.nseg].src = xr; a.seg[a.nseg++].taps = 1; }
         else {
@@ -1174,14 +1193,25 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
     e->time_convs = value != 0;
   }
   else if (k == "use_graphs") e->cfg.use_graphs = value != 0;
-  else if (k == "tc_variant") { sgmse::g_tc_variant = (int)value; clear_graphs(*e); }
+  else if (k == "tc_variant") {
+    // changes which intermediate buffers a forward needs: drop cached workspace sizes, graphs and shadow lanes
+    sgmse::g_tc_variant = (int)value;
+    if (e->lanes.size() > 1) ensure_lanes(*e, 1);
+    e->arena_need.clear();
+    clear_graphs(*e);
+  }
   else if (k == "attn_variant") { sgmse::g_attn_variant = (int)value; clear_graphs(*e); }
   else if (k == "lanes") {
     SG_CHECK(value >= 1 && value <= 8, "lanes must be in 1..8");
     e->num_lanes = (int)value;
     clear_graphs(*e);
   }
-  else if (k == "tc_mask") { e->tc_mask = value; for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec); e->graphs.clear(); }
+  else if (k == "tc_mask") {
+    e->tc_mask = value;
+    if (e->lanes.size() > 1) ensure_lanes(*e, 1);
+    e->arena_need.clear();
+    clear_graphs(*e);
+  }
   else SG_CHECK(false, "unknown option '%s'", key);
   API_END
 }

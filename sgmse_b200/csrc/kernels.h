@@ -50,7 +50,16 @@ struct ConvArgs {
   int temb_stride = 0;             // floats between consecutive samples' rows (0: all samples share)
   const TensorDesc* residual = nullptr;
   float scale = 1.f;               // out = (acc + bias + temb + residual) * scale
-  int ktot() const { int k = 0; for (int i = 0; i < nseg; ++i) k += seg[i].taps * seg[i].src.C; return k; }
+  // Fused GroupNorm-apply + SiLU (conv_tc5 only): seg[0] (3x3) reads RAW tensors -- seg[0].src, concatenated with
+  // gn_cat when gn_has_cat -- and applies silu(a*x+b) with (a, b) = gn_ab[n][channel] on the way into shared memory.
+  const float2* gn_ab = nullptr;
+  bool gn_has_cat = false;
+  TensorDesc gn_cat;
+  int ktot() const {
+    int k = 0;
+    for (int i = 0; i < nseg; ++i) k += seg[i].taps * (seg[i].src.C + (i == 0 && gn_has_cat ? gn_cat.C : 0));
+    return k;
+  }
 };
 void launch_conv_direct(cudaStream_t st, const ConvArgs& a, TensorDesc& out);
 // tcgen05 implicit GEMM; requires fp16 activations, every segment C % 64 == 0, Cout % 128 == 0
@@ -66,7 +75,11 @@ void launch_conv_tc3(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* d
 // fourth generation (conv_tc4.cu): operands swapped (channels = UMMA M, pixels = UMMA N = 256), half the MMA issues
 bool conv_tc4_supported(const ConvArgs& a, const TensorDesc& out);
 void launch_conv_tc4(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
-extern int g_tc_variant;   // 0: newest applicable kernel (v4), 1: v1 only, 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1)
+// fifth generation (conv_tc5.cu): v4 + GroupNorm-apply/SiLU of the 3x3 input fused into a software operand producer
+bool conv_tc5_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
+void launch_conv_tc5(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
+extern int g_tc_variant;   // 0: newest applicable kernels (v5 fused GN where possible, else v4), 1: v1 only, 2: v2 (+v1),
+                           // 3: v3 CTA pairs (+v2, v1), 4: v4 (+v1) without GroupNorm fusion
 
 // input layer: state float4 (x.re,x.im,y.re,y.im) -> conv3x3(4->C); w [36][C] (k = tap*4+cin), bias [C]
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,

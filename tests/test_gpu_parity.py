@@ -248,13 +248,14 @@ def test_tc_kernel_variants_agree(full_sd):
     x = (torch.complex(torch.randn(2, 2, 256, 512, generator=g), torch.randn(2, 2, 256, 512, generator=g)) * 0.3).cuda()
     t = torch.tensor([0.7, 0.1]).cuda()
     outs = {}
-    for variant in (1, 2, 3, 0):        # v1 only; v2 (+v1); v3 CTA pairs; newest applicable (v4: swapped operands)
+    # v1 only; v2 (+v1); v3 CTA pairs; v4 swapped operands; 0 = newest (v5: v4 + GroupNorm/SiLU fused into the conv)
+    for variant in (1, 2, 3, 4, 0):
         eng.set_option("tc_variant", variant)
         outs[variant] = eng.dnn_forward(x, t)
         assert eng.counter("direct_convs_last_forward") == 0
         assert torch.isfinite(torch.view_as_real(outs[variant])).all()
-    errs = {v: rel_l2(outs[v], outs[1]) for v in (2, 3, 0)}
-    print("tc variants vs v1: " + ", ".join(f"v{v if v else 4} rel-L2 {e:.3e}" for v, e in errs.items()))
+    errs = {v: rel_l2(outs[v], outs[1]) for v in (2, 3, 4, 0)}
+    print("tc variants vs v1: " + ", ".join(f"v{v if v else 5} rel-L2 {e:.3e}" for v, e in errs.items()))
     assert all(e < 5e-3 for e in errs.values())
     eng.set_option("tc_variant", 0)
     eng.close()
