@@ -28,12 +28,18 @@ struct Error {
     }                                                                              \
   } while (0)
 
+// Pinned, device-mapped word that a kernel's bounded barrier wait writes its code into before it traps; host memory
+// survives the trap, so the error message can say which wait timed out.
+extern volatile int* g_wait_code_host;
 #define CUDA_OK(expr)                                                              \
   do {                                                                             \
     cudaError_t _e = (expr);                                                       \
     if (_e != cudaSuccess)                                                         \
       throw ::sgmse::Error{std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + #expr + \
-                           " -> " + cudaGetErrorString(_e)};                       \
+                           " -> " + cudaGetErrorString(_e) +                      \
+                           ((::sgmse::g_wait_code_host && *::sgmse::g_wait_code_host)                   \
+                                ? " [kernel barrier wait code " + std::to_string(*::sgmse::g_wait_code_host) + "]" \
+                                : std::string())};                                 \
   } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -439,7 +439,8 @@ void launch_impl(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) 
 
 }  // namespace
 
-int g_tc_variant = 0;   // 0: operand-reuse kernel (conv_tc2.cu) where it applies, 1: always the v1 kernel
+int g_tc_variant = 0;   // see kernels.h
+volatile int* g_wait_code_host = nullptr;
 
 bool conv_tc_supported(const ConvArgs& a, const TensorDesc& out) {
   if (out.dt != DT_F16 || out.C % 64 != 0 || a.w_tc == nullptr) return false;
@@ -456,8 +457,12 @@ void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* db
     SG_CHECK(s.N == out.N && s.H == out.H && s.W == out.W, "conv_tc: segment %d shape mismatch", i);
   }
   if (a.residual) SG_CHECK(a.residual->C == out.C && a.residual->dt == DT_F16, "conv_tc: residual mismatch");
-  if (a.gn_ab) { launch_conv_tc5(st, a, out, dbg); return; }          // the engine only asks for fusion when it applies
-  if ((g_tc_variant == 0 || g_tc_variant == 4) && conv_tc4_supported(a, out)) { launch_conv_tc4(st, a, out, dbg); return; }
+  if (a.gn_ab) {                                                      // the engine only asks for fusion when it applies
+    if (g_tc_variant == 5) launch_conv_tc5(st, a, out, dbg); else launch_conv_tc6(st, a, out, dbg);
+    return;
+  }
+  if ((g_tc_variant == 0 || g_tc_variant == 6 || g_tc_variant == 7) && conv_tc6_supported(a, out)) { launch_conv_tc6(st, a, out, dbg); return; }
+  if ((g_tc_variant == 0 || g_tc_variant >= 4) && conv_tc4_supported(a, out)) { launch_conv_tc4(st, a, out, dbg); return; }
   if (g_tc_variant == 3 && conv_tc3_supported(a, out)) { launch_conv_tc3(st, a, out, dbg); return; }
   if (g_tc_variant != 1 && conv_tc2_supported(a, out)) { launch_conv_tc2(st, a, out, dbg); return; }
   if (out.C % 128 == 0) launch_impl<128, 5>(st, a, out, dbg);

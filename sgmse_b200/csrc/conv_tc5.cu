@@ -2,7 +2,7 @@
 //
 // conv_tc4 reads a *normalised* activation tensor that a separate HBM-bound pass (gn_apply_plain_kernel: read x, write
 // silu(a*x+b)) produced: 2 extra tensor passes per convolution, 22 % of a forward (profiles/r01_launches_*_v4).
-// Here the 3x3 segment's pixel operand is produced by software instead of TMA: four producer warps load the RAW
+// Here the 3x3 segment's pixel operand is produced by software instead of TMA: eight producer warps load the RAW
 // tensor (x, or the two sources of a skip concat) with 128-bit loads, apply  y = silu(a[n,c]*x + b[n,c])  in registers
 // and store the result straight into the SWIZZLE_128B operand stage the UMMA descriptors expect.  Shared-memory
 // traffic is unchanged (the stores replace the TMA's writes); out-of-image pixels are written as zeros, i.e. the
@@ -27,9 +27,11 @@ namespace {
 constexpr int BLOCK_C = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 320;                   // TMA, MMA, 4 epilogue warps, 4 activation-producer warps
+constexpr int NUM_PROD_GROUPS = 2;                 // producer groups alternate over the fused operand stages
+constexpr int NUM_PROD_THREADS = 128;              // per group
+constexpr int NUM_THREADS = 192 + NUM_PROD_GROUPS * NUM_PROD_THREADS;   // TMA, MMA, 4 epilogue warps, producers
 constexpr int NUM_EPI_THREADS = 128;
-constexpr int NUM_PROD_THREADS = 128;
+constexpr int PREFETCH_DIST = 4;                   // L2 prefetch distance in operand stages
 constexpr int SUBS = 2;
 constexpr int ROW_BYTES = 8 * 128;
 constexpr int A_ROWS = 16 * SUBS + 2;              // 34 pixel rows of 8 pixels
@@ -126,9 +128,9 @@ __device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-// two activations: silu(z) = hz*tanh(hz) + hz, hz = z/2   (fp16 pair in, fp16 pair out)
-__device__ __forceinline__ uint32_t silu_pair(float z0, float z1) {
-  const __half2 hz = __floats2half2_rn(0.5f * z0, 0.5f * z1);
+// two activations: silu(z) = hz*tanh(hz) + hz with hz = z/2 given   (fp16 pair out)
+__device__ __forceinline__ uint32_t silu_half_pair(float hz0, float hz1) {
+  const __half2 hz = __floats2half2_rn(hz0, hz1);
   uint32_t hzu = *reinterpret_cast<const uint32_t*>(&hz), tu, yu;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hzu));
   asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(yu) : "r"(hzu), "r"(tu));
@@ -163,7 +165,8 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     if (P.C1 > 0) tma_prefetch_desc(&map_x1);
     if (P.nraw > 0) tma_prefetch_desc(&map_r0);
     if (P.nraw > 1) tma_prefetch_desc(&map_r1);
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    // every stage needs TWO arrivals on a_full: its filler's and the bystander role's (see conv_tc6.cu's header)
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     mbar_fence_init();
@@ -192,12 +195,16 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
           if (cg < P.C0) tma_prefetch_4d(&map_x0, cg, x0 + dx, y0 - 1, n);
           else tma_prefetch_4d(&map_x1, cg - P.C0, x0 + dx, y0 - 1, n);
         };
-        prefetch_stage(0); prefetch_stage(1);
+        for (int i = 0; i < PREFETCH_DIST; ++i) prefetch_stage(i);
         // ---- segment 0 (software-produced activations): only the weights come from here ----
         for (int i = 0; i < fused_stages; ++i) {
-          prefetch_stage(i + 2);
+          prefetch_stage(i + PREFETCH_DIST);
           const int ch = i / 3, dxi = i % 3;
-          if (++sa == A_STAGES) { sa = 0; pa ^= 1; }          // the stage itself belongs to the producer warps
+          // The stage itself belongs to the producer warps.  Still wait for its release: a role that skips phases of
+          // a ring barrier can run two phases ahead, and a parity wait cannot tell phase k from phase k-2.
+          mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 110 + sa);
+          mbar_arrive(&a_full[sa]);                            // bystander arrival
+          if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
           for (int dyi = 0; dyi < 3; ++dyi) {
             const int kb = (dyi * 3 + dxi) * P.chunks0 + ch;
             mbar_wait(&w_empty[sb], pb ^ 1, P.dbg, 150 + sb);
@@ -313,66 +320,81 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
     }
     if (e == 0) tma_store_wait_all0();
   } else {
-    // =========================== activation producers (warps 6..9): raw x -> silu(a*x+b) -> operand stage ======
-    const int pt = threadIdx.x - 192;              // 0..127
+    // =========================== activation producers (warps 6..): raw x -> silu(a*x+b) -> operand stage ======
+    // Two groups of four warps take alternate fused stages: while one group evaluates the activation of stage i the
+    // other already has the loads of stage i+1 in flight.
+    const int grp = (threadIdx.x - 192) / NUM_PROD_THREADS;
+    const int pt = (threadIdx.x - 192) % NUM_PROD_THREADS;   // 0..127
     const int cv = pt & 7;                         // 8-channel vector inside the 64-channel chunk
     const int prow = pt >> 3;                      // 0..15
     const int Ct = P.C0 + P.C1;
     const int raw_stages = (P.nraw > 0 ? P.raw_chunks[0] : 0) + (P.nraw > 1 ? P.raw_chunks[1] : 0);
     int sa = 0; uint32_t pa = 0;
+    uint32_t turn = 0;                             // running fused-stage counter (ownership = turn % groups)
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / P.n_cblk;
       const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
       const int x0 = (rem % P.tiles_w) * 8, y0 = (rem / P.tiles_w) * (16 * SUBS);
-      for (int ch = 0; ch < P.chunks0; ++ch) {
+      for (int i = 0; i < fused_stages; ++i, ++turn) {
+        if ((int)(turn % NUM_PROD_GROUPS) != grp) {          // the other group's stage
+          if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+          continue;
+        }
+        const int ch = i / 3, dx = i % 3 - 1;
         const int cg = ch * 64 + cv * 8;           // channel of the concatenated input
         const __half* src; int Cs, cs;
         if (cg < P.C0) { src = P.src0; Cs = P.C0; cs = cg; } else { src = P.src1; Cs = P.C1; cs = cg - P.C0; }
         src += (size_t)n * P.H * P.W * Cs + cs;
-        float a[8], b[8];
+        uint4 v[ITEMS];
+        // all loads first (17 x 128 bit in flight per thread); out-of-image pixels stay zero
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+          const int px = prow + 16 * j;
+          const int y = y0 - 1 + (px >> 3), x = x0 + dx + (px & 7);
+          v[j] = make_uint4(0u, 0u, 0u, 0u);
+          if ((unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W)
+            v[j] = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y * P.W + x) * Cs));
+        }
+        float a[8], b[8];                          // (a, b)/2: the half argument of the tanh form of silu
         {
           const float4* q = reinterpret_cast<const float4*>(P.ab + (size_t)n * Ct + cg);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { const float4 v = __ldg(q + i); a[2 * i] = v.x; b[2 * i] = v.y; a[2 * i + 1] = v.z; b[2 * i + 1] = v.w; }
-        }
-        for (int dxi = 0; dxi < 3; ++dxi) {
-          const int dx = dxi - 1;
-          uint4 v[ITEMS];
-          // all loads first (17 x 128 bit in flight per thread); out-of-image pixels stay zero
-#pragma unroll
-          for (int j = 0; j < ITEMS; ++j) {
-            const int px = prow + 16 * j;
-            const int y = y0 - 1 + (px >> 3), x = x0 + dx + (px & 7);
-            v[j] = make_uint4(0u, 0u, 0u, 0u);
-            if ((unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W)
-              v[j] = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y * P.W + x) * Cs));
+          for (int k = 0; k < 4; ++k) {
+            const float4 w = __ldg(q + k);
+            a[2 * k] = 0.5f * w.x; b[2 * k] = 0.5f * w.y; a[2 * k + 1] = 0.5f * w.z; b[2 * k + 1] = 0.5f * w.w;
           }
-          mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 600 + sa);
-          uint8_t* stage = smem + sa * A_BYTES;
+        }
+        mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 600 + sa);
+        uint8_t* stage = smem + sa * A_BYTES;
 #pragma unroll
-          for (int j = 0; j < ITEMS; ++j) {
-            const int px = prow + 16 * j;
-            const int y = y0 - 1 + (px >> 3), x = x0 + dx + (px & 7);
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if ((unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W) {
-              const __half2* h = reinterpret_cast<const __half2*>(&v[j]);
-              uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+        for (int j = 0; j < ITEMS; ++j) {
+          const int px = prow + 16 * j;
+          const int y = y0 - 1 + (px >> 3), x = x0 + dx + (px & 7);
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if ((unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[j]);
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h[i]);
-                ow[i] = silu_pair(fmaf(a[2 * i], f.x, b[2 * i]), fmaf(a[2 * i + 1], f.y, b[2 * i + 1]));
-              }
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(h[k]);
+              ow[k] = silu_half_pair(fmaf(a[2 * k], f.x, b[2 * k]), fmaf(a[2 * k + 1], f.y, b[2 * k + 1]));
             }
-            *reinterpret_cast<uint4*>(stage + px * 128 + ((cv ^ (px & 7)) << 4)) = o;
           }
-          fence_proxy_async_smem();                // generic-proxy stores -> visible to the tensor core's async proxy
-          named_bar_sync(2, NUM_PROD_THREADS);
-          if (pt == 0) mbar_arrive(&a_full[sa]);
-          if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+          *reinterpret_cast<uint4*>(stage + px * 128 + ((cv ^ (px & 7)) << 4)) = o;
         }
+        fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
+        named_bar_sync(2 + grp, NUM_PROD_THREADS);
+        if (pt == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
       }
-      // stages of the raw segments belong to the TMA warp
-      for (int i = 0; i < raw_stages; ++i) if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+      // Stages of the raw segments belong to the TMA warp; wait for each release so that this role never runs two
+      // phases ahead of a ring barrier (see the TMA warp).
+      for (int i = 0; i < raw_stages; ++i) {
+        mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 610 + sa);
+        named_bar_sync(4, NUM_PROD_GROUPS * NUM_PROD_THREADS);
+        if (grp == 0 && pt == 0) mbar_arrive(&a_full[sa]);    // bystander arrival: both groups have seen the release
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+      }
     }
   }
 

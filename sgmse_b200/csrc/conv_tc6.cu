@@ -1,0 +1,509 @@
+// tcgen05 implicit-GEMM 3x3/1x1 convolution, sixth generation: one halo tile per 64-channel chunk.
+//
+// conv_tc4 stages the pixel operand of a 3x3 segment as THREE boxes per 64-channel chunk (one per dx shift, 34 rows of
+// 8 pixels each) because a SWIZZLE_128B operand row group is 8 consecutive 128-byte rows.  Here the chunk is staged
+// ONCE as a dense [34 rows][10 pixels] x 128 B halo tile and each of the nine taps is the same tile addressed through
+// a shifted descriptor: start = tile + (dy*10 + dx)*128 B, stride between 8-pixel groups (SBO) = 10*128 B.  The 128-byte
+// swizzle is a function of the shared-memory address bits (chunk bits 4..6 ^= row bits 7..9), so a start that is a
+// multiple of 128 B and an SBO that is not a multiple of 1024 B still address the rows the way TMA (or a software
+// producer using the same function) wrote them.
+//   * operand bytes written to shared memory per chunk: 43.5 KB instead of 102 KB (weights unchanged: 9 x 16 KB);
+//   * with the optional fused GroupNorm-apply + SiLU (ConvArgs::gn_ab; see conv_tc5.cu for the first version), the
+//     software producer now evaluates every activation once instead of three times: 2720 128-bit vectors per chunk for
+//     2304 tensor clocks of MMA work, 11 per producer thread, loaded one stage ahead of the slot they go into.
+// Everything else (swapped operands, N = 256 pixel UMMAs, channel-per-lane epilogue, identity residual segment) is
+// conv_tc4's.
+// Ring barriers in fused mode, where a slot is filled by the producer warps (3x3 segment) or by TMA (1x1 segments):
+// a parity wait cannot tell phase k from phase k+-2, so a role must neither skip phases of a_empty (it could run two
+// phases ahead and overwrite a live slot) nor be lapped (it would spin on a phase that is long gone).  Therefore
+// EVERY role waits on a_empty for EVERY stage, and a_full needs two arrivals per stage: the filler's and the
+// bystander's "I have seen this slot's release" -- the MMA warp cannot consume a stage, hence cannot release the
+// slot again, before both roles have observed the previous release.
+#include "kernels.h"
+
+namespace sgmse {
+
+CUtensorMap make_act_map(const void* p, int N, int H, int W, int C, int bw, int bh, int bn);
+CUtensorMap make_w_map(const void* p, int Cout, int Ktot, int block_n);
+int num_sms();
+
+namespace {
+
+constexpr int BLOCK_C = 128;                       // output channels per tile (UMMA M)
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int NUM_PROD_THREADS = 256;
+constexpr int NUM_THREADS = 192 + NUM_PROD_THREADS;   // TMA, MMA, 4 epilogue warps, 8 activation-producer warps
+constexpr int NUM_EPI_THREADS = 128;
+constexpr int TILE_H = 32, TILE_W = 8;             // output pixels of a tile (UMMA N = 256)
+constexpr int HALO_H = TILE_H + 2, HALO_W = TILE_W + 2;
+constexpr int HALO_ROWS = HALO_H * HALO_W;         // 340 pixels of 128 B
+constexpr int A_BYTES = HALO_ROWS * 128;           // 43520 bytes arrive per stage
+constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
+constexpr int SBO_BYTES = HALO_W * 128;            // 8-pixel group stride = one halo row
+constexpr int PROD_ITEMS = (HALO_ROWS * 8 + NUM_PROD_THREADS - 1) / NUM_PROD_THREADS;   // 11 vectors per producer thread
+constexpr int W_BYTES = BLOCK_C * 128;             // 16 KB
+constexpr int TILE_PX = TILE_H * TILE_W;
+constexpr int GROUP_PX = 64;
+constexpr int GROUP_BYTES = 2 * GROUP_PX * 128;
+constexpr int GROUPS = TILE_PX / GROUP_PX;
+constexpr int MAX_SEG = 4;
+
+struct Tc6Params {
+  int tiles_w, tiles_h;
+  int num_m_tiles, num_tiles, n_cblk;
+  int N, H, W, Cout;
+  int nseg;
+  int seg_chunks[MAX_SEG];
+  int seg_taps[MAX_SEG];
+  int seg_kb0[MAX_SEG];
+  // fused GroupNorm+SiLU on segment 0 (3x3 over concat(src0, src1))
+  int fused;
+  const __half* src0; const __half* src1;
+  int C0, C1;
+  const float2* ab;              // [N][C0+C1] (a, b)
+  const float* bias;
+  const float* temb;
+  int temb_stride;
+  float scale;
+  float* stats;
+  int slots;
+  int desc_mode;                 // 0: base_offset field 0; 1: base_offset = (start >> 7) & 7
+  int* dbg;
+};
+
+template <int A_STAGES, int B_STAGES>
+struct Smem6 {
+  static constexpr int OFF_W = A_STAGES * A_STRIDE;
+  static constexpr int OFF_STAGING = OFF_W + B_STAGES * W_BYTES;
+  static constexpr int OFF_BARS = OFF_STAGING + 2 * GROUP_BYTES;
+  static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
+  static constexpr int TOTAL = OFF_TMEM_PTR + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+  static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes, int mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t IDESC6 = (1u << 4) | ((uint32_t)(TILE_PX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // M128 N256
+
+__device__ __forceinline__ void mma_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+        "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+        "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// two activations: silu(z) = hz*tanh(hz) + hz with hz = z/2 given   (fp16 pair out)
+__device__ __forceinline__ uint32_t silu_half_pair(float hz0, float hz1) {
+  const __half2 hz = __floats2half2_rn(hz0, hz1);
+  uint32_t hzu = *reinterpret_cast<const uint32_t*>(&hz), tu, yu;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hzu));
+  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(yu) : "r"(hzu), "r"(tu));
+  return yu;
+}
+
+template <int A_STAGES, int B_STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
+                const __grid_constant__ CUtensorMap map_cat,
+                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_d,
+                const Tc6Params P) {
+  using L = Smem6<A_STAGES, B_STAGES>;
+  constexpr uint32_t TMEM_COLS = 2 * TILE_PX;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BARS);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + A_STAGES;
+  uint64_t* w_full = a_empty + A_STAGES;
+  uint64_t* w_empty = w_full + B_STAGES;
+  uint64_t* tmem_full = w_empty + B_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
+  uint8_t* staging = smem + L::OFF_STAGING;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_d);
+    if (P.nseg > 1) tma_prefetch_desc(&map_a1);
+    if (P.nseg > 2) tma_prefetch_desc(&map_a2);
+    if (P.nseg > 3) tma_prefetch_desc(&map_a3);
+    if (P.fused && P.C1 > 0) tma_prefetch_desc(&map_cat);
+    // fused mode: every stage needs TWO arrivals on a_full -- its filler's and the bystander's (see the header)
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], P.fused ? 2 : 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int tiles_per_utt = P.tiles_w * P.tiles_h;
+
+  if (warp == 0) {
+    // =========================== TMA producer: weights, TMA-fed halo tiles, L2 prefetch of the fused ones ====
+    if (lane == 0) {
+      int sa = 0; uint32_t pa = 0;
+      int sb = 0; uint32_t pb = 0;
+      const int nfused = P.fused ? P.seg_chunks[0] : 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const int c_blk = tile % P.n_cblk, m_tile = tile / P.n_cblk;
+        const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
+        const int x0 = (rem % P.tiles_w) * TILE_W, y0 = (rem / P.tiles_w) * TILE_H;
+        // L2 prefetch of the halo tile `i` chunks ahead in the fused segment (continuing into this CTA's next tile)
+        auto prefetch_chunk = [&](int i) {
+          int t = tile;
+          if (i >= nfused) { i -= nfused; t += gridDim.x; }
+          if (i >= nfused || t >= P.num_tiles) return;
+          const int mt = t / P.n_cblk;
+          const int pn = mt / tiles_per_utt, prem = mt % tiles_per_utt;
+          const int px0 = (prem % P.tiles_w) * TILE_W, py0 = (prem / P.tiles_w) * TILE_H;
+          const int cg = i * 64;
+          if (cg < P.C0) tma_prefetch_4d(&map_a0, cg, px0 - 1, py0 - 1, pn);
+          else tma_prefetch_4d(&map_cat, cg - P.C0, px0 - 1, py0 - 1, pn);
+        };
+        if (tile == (int)blockIdx.x) for (int i = 0; i < 3; ++i) prefetch_chunk(i);
+        for (int s = 0; s < P.nseg; ++s) {
+          const CUtensorMap* ma = s == 0 ? &map_a0 : (s == 1 ? &map_a1 : (s == 2 ? &map_a2 : &map_a3));
+          const int ntap = P.seg_taps[s];
+          const int chunks = P.seg_chunks[s];
+          const bool soft = P.fused && s == 0;
+          for (int ch = 0; ch < chunks; ++ch) {
+            mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 100 + sa);
+            if (soft) {
+              mbar_arrive(&a_full[sa]);            // bystander arrival: this role has seen the slot's release
+              prefetch_chunk(ch + 3);
+            } else {
+              mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
+              tma_load_4d(smem + sa * A_STRIDE, ma, &a_full[sa], ch * BLOCK_K, x0 - 1, y0 - 1, n);
+            }
+            if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+            for (int tap = 0; tap < ntap; ++tap) {
+              const int kb = P.seg_kb0[s] + tap * chunks + ch;
+              mbar_wait(&w_empty[sb], pb ^ 1, P.dbg, 150 + sb);
+              mbar_arrive_expect_tx(&w_full[sb], W_BYTES);
+              tma_load_2d(smem + L::OFF_W + sb * W_BYTES, &map_w, &w_full[sb], kb * BLOCK_K, c_blk * BLOCK_C);
+              if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer: whole warp, warp-uniform control flow ===========================
+    int sa = 0; uint32_t pa = 0;
+    int sb = 0; uint32_t pb = 0;
+    int as = 0; uint32_t as_phase = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[as], as_phase ^ 1, P.dbg, 200 + as);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_PX);
+      uint32_t acc = 0;
+      for (int s = 0; s < P.nseg; ++s) {
+        const int ntap = P.seg_taps[s];
+        const int chunks = P.seg_chunks[s];
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(&a_full[sa], pa, P.dbg, 300 + sa);
+          const uint32_t a_base = smem_u32(smem + sa * A_STRIDE);
+          for (int tap = 0; tap < ntap; ++tap) {
+            mbar_wait(&w_full[sb], pb, P.dbg, 350 + sb);
+            tc_fence_after();
+            // halo pixel of output pixel (0,0) under this tap: (dy, dx) for 3x3, the centre (1, 1) for 1x1
+            const int off = ntap == 9 ? (tap / 3) * HALO_W + tap % 3 : HALO_W + 1;
+            const uint64_t wdesc = desc_sw128(smem_u32(smem + L::OFF_W + sb * W_BYTES), 1024, 0);          // A operand: weights
+            const uint64_t pdesc = desc_sw128(a_base + (uint32_t)(off * 128), SBO_BYTES, P.desc_mode);     // B operand: pixels
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              mma_elect(d_tmem, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), IDESC6, acc);
+              acc = 1;
+            }
+            commit_elect(&w_empty[sb]);
+            if (tap == ntap - 1) commit_elect(&a_empty[sa]);
+            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+          }
+          if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+        }
+      }
+      commit_elect(&tmem_full[as]);
+      if (++as == 2) { as = 0; as_phase ^= 1; }
+    }
+  } else if (warp < 6) {
+    // =========================== epilogue (warps 2..5): thread = output channel ===========================
+    const int e = threadIdx.x - 64;
+    const int lg = warp & 3;
+    const int ch = lg * 32 + lane;
+    const int ch_chunk_off = (ch >> 6) * (GROUP_PX * 128) + (ch & 7) * 2;
+    const int ch_c16 = (ch & 63) >> 3;
+    int as = 0; uint32_t as_phase = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const int c_blk = tile % P.n_cblk, m_tile = tile / P.n_cblk;
+      const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
+      const int tx = rem % P.tiles_w, ty = rem / P.tiles_w;
+      const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+      const int c_tile = c_blk * BLOCK_C;
+      float bt = P.bias ? __ldg(P.bias + c_tile + ch) : 0.f;
+      if (P.temb) bt += __ldg(P.temb + (size_t)n * P.temb_stride + c_tile + ch);
+      float ssum = 0.f, ssq = 0.f;
+      mbar_wait(&tmem_full[as], as_phase, P.dbg, 500 + as);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < GROUPS; ++g) {
+        uint8_t* buf = staging + (g & 1) * GROUP_BYTES;
+        if (e == 0) tma_store_wait_read1();
+        named_bar_sync(1, NUM_EPI_THREADS);
+        uint32_t r[64];
+        tmem_ld_32x64(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * TILE_PX + g * GROUP_PX), r);
+        tmem_ld_wait();
+        if (g == GROUPS - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        uint8_t* base = buf + ch_chunk_off;
+#pragma unroll
+        for (int p = 0; p < GROUP_PX; ++p) {
+          const __half h = __float2half_rn((__uint_as_float(r[p]) + bt) * P.scale);
+          const float f = __half2float(h);
+          ssum += f; ssq = fmaf(f, f, ssq);
+          *reinterpret_cast<__half*>(base + p * 128 + ((ch_c16 ^ (p & 7)) << 4)) = h;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, NUM_EPI_THREADS);
+        if (e == 0) {
+          tma_store_4d(&map_d, buf, c_tile, x0, y0 + g * 8, n);
+          tma_store_4d(&map_d, buf + GROUP_PX * 128, c_tile + 64, x0, y0 + g * 8, n);
+          tma_store_commit();
+        }
+      }
+      if (P.stats) {
+        float2* o = reinterpret_cast<float2*>(P.stats + (((size_t)n * P.slots + (ty * P.tiles_w + tx)) * P.Cout + c_tile + ch) * 2);
+        *o = make_float2(ssum, ssq);
+      }
+      if (++as == 2) { as = 0; as_phase ^= 1; }
+    }
+    if (e == 0) tma_store_wait_all0();
+  } else if (P.fused) {
+    // =========================== activation producers (warps 6..13): raw x -> silu(a*x+b) -> halo tile ======
+    // 256 threads share one stage (11 x 128-bit vectors each, all loads in flight at once).  The loads of the NEXT
+    // fused stage are issued right after the stores of the current one, i.e. before waiting for its slot, so the
+    // time between "slot released" and "stage full" is only the evaluation of 11 vectors per thread.
+    const int pt = threadIdx.x - 192;              // 0..255
+    const int cv = pt & 7;                         // 8-channel vector inside the 64-channel chunk
+    const int Ct = P.C0 + P.C1;
+    const int nfused = P.seg_chunks[0];
+    int other_stages = 0;
+    for (int s = 1; s < P.nseg; ++s) other_stages += P.seg_chunks[s];
+    int sa = 0; uint32_t pa = 0;
+    uint4 v[PROD_ITEMS];
+    auto issue_loads = [&](int tile, int ch) {
+      const int m_tile = tile / P.n_cblk;
+      const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
+      const int x0 = (rem % P.tiles_w) * TILE_W, y0 = (rem / P.tiles_w) * TILE_H;
+      const int cg = ch * 64 + cv * 8;             // channel of the concatenated input
+      const __half* src; int Cs, cs;
+      if (cg < P.C0) { src = P.src0; Cs = P.C0; cs = cg; } else { src = P.src1; Cs = P.C1; cs = cg - P.C0; }
+      src += (size_t)n * P.H * P.W * Cs + cs;
+#pragma unroll
+      for (int j = 0; j < PROD_ITEMS; ++j) {
+        const int row = (pt >> 3) + 32 * j;        // halo pixel 0..339 (351 with the guard)
+        const int yy = row / HALO_W, xx = row - yy * HALO_W;
+        const int y = y0 - 1 + yy, x = x0 - 1 + xx;
+        v[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (row < HALO_ROWS && (unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W)
+          v[j] = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y * P.W + x) * Cs));
+      }
+    };
+    if ((int)blockIdx.x < P.num_tiles) issue_loads(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / P.n_cblk;
+      const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
+      const int x0 = (rem % P.tiles_w) * TILE_W, y0 = (rem / P.tiles_w) * TILE_H;
+      for (int ch = 0; ch < nfused; ++ch) {
+        const int cg = ch * 64 + cv * 8;
+        float a[8], b[8];                          // (a, b)/2: the half argument of the tanh form of silu
+        {
+          const float4* q = reinterpret_cast<const float4*>(P.ab + (size_t)n * Ct + cg);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 w = __ldg(q + k);
+            a[2 * k] = 0.5f * w.x; b[2 * k] = 0.5f * w.y; a[2 * k + 1] = 0.5f * w.z; b[2 * k + 1] = 0.5f * w.w;
+          }
+        }
+        mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 600 + sa);
+        uint8_t* stage = smem + sa * A_STRIDE;
+#pragma unroll
+        for (int j = 0; j < PROD_ITEMS; ++j) {
+          const int row = (pt >> 3) + 32 * j;
+          const int yy = row / HALO_W, xx = row - yy * HALO_W;
+          const int y = y0 - 1 + yy, x = x0 - 1 + xx;
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);    // out-of-image pixels: the conv's zero padding
+          if (row < HALO_ROWS && (unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[j]);
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(h[k]);
+              ow[k] = silu_half_pair(fmaf(a[2 * k], f.x, b[2 * k]), fmaf(a[2 * k + 1], f.y, b[2 * k + 1]));
+            }
+          }
+          if (row < HALO_ROWS) *reinterpret_cast<uint4*>(stage + row * 128 + ((cv ^ (row & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
+        named_bar_sync(2, NUM_PROD_THREADS);
+        if (pt == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+        // loads of the next fused stage (this tile's next chunk or the first chunk of this CTA's next tile)
+        if (ch + 1 < nfused) issue_loads(tile, ch + 1);
+        else if (tile + (int)gridDim.x < P.num_tiles) issue_loads(tile + gridDim.x, 0);
+      }
+      // stages of the TMA-fed segments: see each release, then tell the MMA warp so (bystander arrival)
+      for (int i = 0; i < other_stages; ++i) {
+        mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 610 + sa);
+        named_bar_sync(3, NUM_PROD_THREADS);
+        if (pt == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int A_STAGES, int B_STAGES>
+void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
+  using L = Smem6<A_STAGES, B_STAGES>;
+  Tc6Params P{};
+  P.tiles_w = out.W / TILE_W; P.tiles_h = out.H / TILE_H;
+  P.num_m_tiles = P.tiles_w * P.tiles_h * out.N;
+  P.n_cblk = out.C / BLOCK_C;
+  P.num_tiles = P.num_m_tiles * P.n_cblk;
+  P.N = out.N; P.H = out.H; P.W = out.W; P.Cout = out.C;
+  const TensorDesc* srcs[MAX_SEG];
+  int taps[MAX_SEG];
+  int nseg = 0;
+  for (int i = 0; i < a.nseg; ++i) { srcs[nseg] = &a.seg[i].src; taps[nseg++] = a.seg[i].taps; }
+  if (a.residual) { srcs[nseg] = a.residual; taps[nseg++] = 1; }
+  P.nseg = nseg;
+  P.fused = a.gn_ab ? 1 : 0;
+  const TensorDesc* cat = (a.gn_ab && a.gn_has_cat) ? &a.gn_cat : nullptr;
+  CUtensorMap ma[MAX_SEG];
+  int kb = 0;
+  for (int i = 0; i < MAX_SEG; ++i) {
+    const TensorDesc& s = *srcs[i < nseg ? i : 0];
+    ma[i] = make_act_map(s.p, s.N, s.H, s.W, s.C, HALO_W, HALO_H, 1);
+    if (i < nseg) {
+      const int C = s.C + ((i == 0 && cat) ? cat->C : 0);
+      P.seg_chunks[i] = C / 64; P.seg_taps[i] = taps[i]; P.seg_kb0[i] = kb;
+      kb += taps[i] * (C / 64);
+    }
+  }
+  const CUtensorMap mcat = cat ? make_act_map(cat->p, cat->N, cat->H, cat->W, cat->C, HALO_W, HALO_H, 1) : ma[0];
+  if (P.fused) {
+    P.src0 = (const __half*)srcs[0]->p; P.C0 = srcs[0]->C;
+    P.src1 = cat ? (const __half*)cat->p : nullptr; P.C1 = cat ? cat->C : 0;
+    P.ab = a.gn_ab;
+  }
+  const int ld = a.w_tc_ld ? a.w_tc_ld : a.ktot();
+  SG_CHECK(kb * 64 <= ld, "conv_tc6: K blocks (%d) exceed the packed weight row (%d)", kb * 64, ld);
+  const CUtensorMap mw = make_w_map(a.w_tc, out.C, ld, BLOCK_C);
+  const CUtensorMap md = make_act_map(out.p, out.N, out.H, out.W, out.C, 8, 8, 1);
+  P.bias = a.bias; P.temb = a.temb; P.temb_stride = a.temb_stride;
+  P.scale = a.scale;
+  out.slots = P.tiles_w * P.tiles_h;
+  P.stats = out.stats; P.slots = out.slots;
+  static const int desc_mode = [] { const char* v = getenv("SGMSE_B200_TC6_DESC"); return v ? atoi(v) : 0; }();
+  P.desc_mode = desc_mode;
+  P.dbg = dbg;
+  auto kern = conv_tc6_kernel<A_STAGES, B_STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    attr_set = true;
+  }
+  const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
+  kern<<<grid, NUM_THREADS, L::DYN_BYTES, st>>>(ma[0], ma[1], ma[2], ma[3], mcat, mw, md, P);
+  CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace
+
+// Shape test usable before the tensors exist (fused GroupNorm 3x3 over c0 [+ c1] raw channels, `nraw` extra 1x1
+// segments incl. the residual).
+bool conv_tc6_fuse_shape_ok(int H, int W, int c0, int c1, int cout, int nraw) {
+  return H % TILE_H == 0 && W % TILE_W == 0 && c0 % 64 == 0 && c1 % 64 == 0 && cout % 128 == 0 && nraw <= MAX_SEG - 1;
+}
+
+bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out) {
+  if (!conv_tc4_supported(a, out) || out.H % TILE_H != 0) return false;
+  return a.nseg + (a.residual ? 1 : 0) <= MAX_SEG;
+}
+
+void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
+  if (a.gn_ab) {
+    const int nraw = (a.nseg - 1) + (a.residual ? 1 : 0);
+    SG_CHECK(a.nseg >= 1 && a.seg[0].taps == 9 &&
+                 conv_tc6_fuse_shape_ok(out.H, out.W, a.seg[0].src.C, a.gn_has_cat ? a.gn_cat.C : 0, out.C, nraw) &&
+                 out.dt == DT_F16 && a.w_tc != nullptr && (!a.residual || a.tc_identity_tail),
+             "conv_tc6: unsupported fused shape");
+  } else {
+    SG_CHECK(conv_tc6_supported(a, out), "conv_tc6: unsupported shape");
+  }
+  static const int ring_cfg = [] { const char* v = getenv("SGMSE_B200_TC6_RINGS"); return v ? atoi(v) : 0; }();
+  if (ring_cfg == 1) launch6<3, 4>(st, a, out, dbg);
+  else launch6<2, 6>(st, a, out, dbg);
+}
+
+}  // namespace sgmse

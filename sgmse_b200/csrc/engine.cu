@@ -215,7 +215,7 @@ void free_workspace(Engine& e) {
   e.fft_plans.clear();
   cudaFree(e.arena.base); e.arena = Arena{};
   cudaFree(e.state); cudaFree(e.xmean); cudaFree(e.temb_table); cudaFree(e.temb_scratch); cudaFree(e.t_dev);
-  cudaFree(e.coef_dev); cudaFree(e.rng_dev); cudaFree(e.lv_scratch); cudaFree(e.dbg_flag);
+  cudaFree(e.coef_dev); cudaFree(e.rng_dev); cudaFree(e.lv_scratch);
   e.state = nullptr; e.xmean = nullptr; e.temb_table = nullptr; e.temb_scratch = nullptr; e.t_dev = nullptr;
   e.coef_dev = nullptr; e.rng_dev = nullptr; e.lv_scratch = nullptr; e.dbg_flag = nullptr;
   e.persist_px = 0; e.persist_rows = 0;
@@ -376,10 +376,11 @@ struct Fwd {
     float2* ab0 = gn(x0, x1, l.gn0_w, l.gn0_b);
     // Fused path (conv_tc5): the 3x3 convs read the RAW tensor and apply GroupNorm+SiLU on the way into shared
     // memory, so the gn_apply pass (one read + one write of the tensor) and its buffer disappear.
-    const bool fuse_ok = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && g_tc_variant == 0 && ((e.tc_mask >> 8) & 1);
-    const bool fuse0 = fuse_ok && rs == RS_NONE && l.c0.w_tc && conv_tc5_shape_ok(Ho, Wo, x0.C, x1 ? x1->C : 0, l.cout, 0);
+    const bool fuse_ok = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && (g_tc_variant == 0 || g_tc_variant == 5 || g_tc_variant == 7);
+    auto shape_ok = g_tc_variant == 5 ? conv_tc5_shape_ok : conv_tc6_fuse_shape_ok;
+    const bool fuse0 = fuse_ok && ((e.tc_mask >> 8) & 1) && rs == RS_NONE && l.c0.w_tc && shape_ok(Ho, Wo, x0.C, x1 ? x1->C : 0, l.cout, 0);
     const int nraw1 = l.shortcut ? ((rs == RS_NONE && x1) ? 2 : 1) : 1;
-    const bool fuse1 = fuse_ok && l.c1.w_tc && conv_tc5_shape_ok(Ho, Wo, l.cout, 0, l.cout, nraw1) &&
+    const bool fuse1 = fuse_ok && ((e.tc_mask >> 9) & 1) && l.c1.w_tc && shape_ok(Ho, Wo, l.cout, 0, l.cout, nraw1) &&
                        (l.shortcut || l.c1.identity_tail);
     TensorDesc h0;
     TensorDesc xr;                                 // FIR-resampled raw input (up/down blocks)
@@ -659,8 +660,13 @@ void ensure_persistent(Engine& e, size_t px, int rows) {
   if (!e.rng_dev) {
     CUDA_OK(cudaMalloc((void**)&e.rng_dev, sizeof(RngParams)));
     CUDA_OK(cudaMalloc((void**)&e.lv_scratch, (size_t)std::max(e.cfg.max_batch, 1) * 64 * 2 * 4));
-    CUDA_OK(cudaMalloc((void**)&e.dbg_flag, 4));
-    CUDA_OK(cudaMemset(e.dbg_flag, 0, 4));
+    if (!g_wait_code_host) {
+      int* h = nullptr;
+      CUDA_OK(cudaHostAlloc((void**)&h, 4, cudaHostAllocMapped));
+      *h = 0;
+      g_wait_code_host = h;
+    }
+    e.dbg_flag = const_cast<int*>(g_wait_code_host);      // one process-wide word (UVA: same pointer on the device)
   }
 }
 
@@ -1040,8 +1046,7 @@ void sgmse_b200_destroy(sgmse_b200_engine* e) {
   cudaDeviceSynchronize();
   try { if (e->lanes.size() > 1) ensure_lanes(*e, 1); } catch (...) {}
   for (cudaEvent_t ev : e->lane_events) cudaEventDestroy(ev);
-  free_weights(*e);
-  free_workspace(*e);
+  try { free_weights(*e); free_workspace(*e); } catch (...) {}   // a dead context must not terminate the host process
   delete e;
 }
 
@@ -1226,6 +1231,7 @@ long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key) {
   if (k == "tc_convs_last_forward") return e->tc_convs;
   if (k == "direct_convs_last_forward") return e->direct_convs;
   if (k == "launches_last_forward") return e->launches_this_forward;
+  if (k == "barrier_wait_code") return sgmse::g_wait_code_host ? (long long)*sgmse::g_wait_code_host : 0;   // readable after a trap
   if (k == "timed_conv_tc_us" || k == "timed_conv_tc_mflop" || k == "timed_conv_tc_count" || k == "timed_conv_tc_kbytes" ||
       k == "timed_conv_direct_us") {
     cudaDeviceSynchronize();

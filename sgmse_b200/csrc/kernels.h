@@ -78,8 +78,14 @@ void launch_conv_tc4(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* d
 // fifth generation (conv_tc5.cu): v4 + GroupNorm-apply/SiLU of the 3x3 input fused into a software operand producer
 bool conv_tc5_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
 void launch_conv_tc5(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
-extern int g_tc_variant;   // 0: newest applicable kernels (v5 fused GN where possible, else v4), 1: v1 only, 2: v2 (+v1),
-                           // 3: v3 CTA pairs (+v2, v1), 4: v4 (+v1) without GroupNorm fusion
+// sixth generation (conv_tc6.cu): one [34][10]-pixel halo tile per chunk, nine taps through shifted descriptors; optional
+// fused GroupNorm-apply/SiLU producer that evaluates each activation once
+bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out);
+bool conv_tc6_fuse_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
+void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
+extern int g_tc_variant;   // 0 (= 7): newest applicable kernels (v6 with fused GN where possible, else v4/v1), 1: v1 only,
+                           // 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1), 4: v4 (+v1) without GroupNorm fusion,
+                           // 5: v5 fused GN (+v4), 6: v6 without fusion (+v4)
 
 // input layer: state float4 (x.re,x.im,y.re,y.im) -> conv3x3(4->C); w [36][C] (k = tap*4+cin), bias [C]
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,

@@ -240,22 +240,23 @@ def test_end_to_end_si_sdr(full_sd):
 
 
 def test_tc_kernel_variants_agree(full_sd):
-    """The operand-reuse tcgen05 kernel (conv_tc2.cu) and the first-generation one (conv_tc.cu) compute the same
-    convolutions (different accumulation order only)."""
+    """All generations of the tcgen05 convolution compute the same convolutions (different accumulation order; the
+    fused GroupNorm+SiLU producers of v5/v6 round the activation through tanh.approx.f16x2 instead of __expf)."""
     eng = Engine(EngineConfig(mode="fp16_tc", max_batch=2))
     eng.load_state_dict(full_sd)
     g = torch.Generator().manual_seed(12)
     x = (torch.complex(torch.randn(2, 2, 256, 512, generator=g), torch.randn(2, 2, 256, 512, generator=g)) * 0.3).cuda()
     t = torch.tensor([0.7, 0.1]).cuda()
     outs = {}
-    # v1 only; v2 (+v1); v3 CTA pairs; v4 swapped operands; 0 = newest (v5: v4 + GroupNorm/SiLU fused into the conv)
-    for variant in (1, 2, 3, 4, 0):
+    # v1 only; v2 (+v1); v3 CTA pairs; v4 swapped operands; 5: v4 + GroupNorm/SiLU fused into the conv (conv_tc5);
+    # 6: halo-tile kernel (conv_tc6) without fusion; 0 = default = conv_tc6 with the fusion
+    for variant in (1, 2, 3, 4, 5, 6, 0):
         eng.set_option("tc_variant", variant)
         outs[variant] = eng.dnn_forward(x, t)
         assert eng.counter("direct_convs_last_forward") == 0
         assert torch.isfinite(torch.view_as_real(outs[variant])).all()
-    errs = {v: rel_l2(outs[v], outs[1]) for v in (2, 3, 4, 0)}
-    print("tc variants vs v1: " + ", ".join(f"v{v if v else 5} rel-L2 {e:.3e}" for v, e in errs.items()))
+    errs = {v: rel_l2(outs[v], outs[1]) for v in (2, 3, 4, 5, 6, 0)}
+    print("tc variants vs v1: " + ", ".join(f"v{v if v else '6-fused'} rel-L2 {e:.3e}" for v, e in errs.items()))
     assert all(e < 5e-3 for e in errs.values())
     eng.set_option("tc_variant", 0)
     eng.close()
