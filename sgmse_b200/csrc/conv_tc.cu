@@ -461,7 +461,7 @@ void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* db
     if (g_tc_variant == 5) launch_conv_tc5(st, a, out, dbg); else launch_conv_tc6(st, a, out, dbg);
     return;
   }
-  if ((g_tc_variant == 0 || g_tc_variant == 6 || g_tc_variant == 7) && conv_tc6_supported(a, out)) { launch_conv_tc6(st, a, out, dbg); return; }
+  if ((g_tc_variant == 0 || g_tc_variant >= 6) && conv_tc6_supported(a, out)) { launch_conv_tc6(st, a, out, dbg); return; }
   if ((g_tc_variant == 0 || g_tc_variant >= 4) && conv_tc4_supported(a, out)) { launch_conv_tc4(st, a, out, dbg); return; }
   if (g_tc_variant == 3 && conv_tc3_supported(a, out)) { launch_conv_tc3(st, a, out, dbg); return; }
   if (g_tc_variant != 1 && conv_tc2_supported(a, out)) { launch_conv_tc2(st, a, out, dbg); return; }

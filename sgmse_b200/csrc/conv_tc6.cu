@@ -13,12 +13,20 @@
 //     2304 tensor clocks of MMA work, 11 per producer thread, loaded one stage ahead of the slot they go into.
 // Everything else (swapped operands, N = 256 pixel UMMAs, channel-per-lane epilogue, identity residual segment) is
 // conv_tc4's.
+// Fused mode 2 (default): the RAW halo tile of a fused chunk is brought in by TMA (a_raw barrier) as soon as its slot
+// is released, and the producer warps transform it IN PLACE (LDS -> silu(a*x+b) -> STS to the same swizzled address,
+// out-of-image rows keep TMA's zero fill = the conv's zero padding) before arriving on a_full.  Global-load latency
+// is off the producers' critical path (mode 1 issues its LDGs only one stage ahead, so once the producers are the
+// bottleneck every chunk pays a full L2/HBM round trip), v[] registers disappear, and only the TMA warp ever waits
+// on a_empty -- the producers wait on a_raw with a per-slot phase bit, so no bystander arrivals are needed.
 // Ring barriers in fused mode, where a slot is filled by the producer warps (3x3 segment) or by TMA (1x1 segments):
 // a parity wait cannot tell phase k from phase k+-2, so a role must neither skip phases of a_empty (it could run two
 // phases ahead and overwrite a live slot) nor be lapped (it would spin on a phase that is long gone).  Therefore
 // EVERY role waits on a_empty for EVERY stage, and a_full needs two arrivals per stage: the filler's and the
 // bystander's "I have seen this slot's release" -- the MMA warp cannot consume a stage, hence cannot release the
 // slot again, before both roles have observed the previous release.
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace sgmse {
@@ -62,6 +70,7 @@ struct Tc6Params {
   const __half* src0; const __half* src1;
   int C0, C1;
   const float2* ab;              // [N][C0+C1] (a, b)
+  const uint4* ab16;             // [N][(C0+C1)/2] {m_hi, m_lo, a/2, beta/2} as half2 per channel pair (mode 3)
   const float* bias;
   const float* temb;
   int temb_stride;
@@ -77,7 +86,7 @@ struct Smem6 {
   static constexpr int OFF_W = A_STAGES * A_STRIDE;
   static constexpr int OFF_STAGING = OFF_W + B_STAGES * W_BYTES;
   static constexpr int OFF_BARS = OFF_STAGING + 2 * GROUP_BYTES;
-  static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int NUM_BARS = 3 * A_STAGES + 2 * B_STAGES + 4;
   static constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM_PTR + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;
@@ -135,6 +144,24 @@ __device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// half2 GroupNorm + SiLU of a channel pair: hz = (a/2) * ((x - m_hi) - m_lo) + beta/2 ; silu = hz * tanh(hz) + hz
+__device__ __forceinline__ uint32_t gn_silu_h2(uint32_t x, uint32_t m_hi, uint32_t m_lo, uint32_t a2, uint32_t b2) {
+  uint32_t d, hz, t, y;
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(m_hi));
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(d), "r"(m_lo));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(hz) : "r"(a2), "r"(d), "r"(b2));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(hz));
+  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(hz), "r"(t));
+  return y;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // two activations: silu(z) = hz*tanh(hz) + hz with hz = z/2 given   (fp16 pair out)
 __device__ __forceinline__ uint32_t silu_half_pair(float hz0, float hz1) {
   const __half2 hz = __floats2half2_rn(hz0, hz1);
@@ -158,7 +185,8 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BARS);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + A_STAGES;
-  uint64_t* w_full = a_empty + A_STAGES;
+  uint64_t* a_raw = a_empty + A_STAGES;            // fused mode 2: raw halo tile landed (TMA complete_tx)
+  uint64_t* w_full = a_raw + A_STAGES;
   uint64_t* w_empty = w_full + B_STAGES;
   uint64_t* tmem_full = w_empty + B_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -174,8 +202,8 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     if (P.nseg > 2) tma_prefetch_desc(&map_a2);
     if (P.nseg > 3) tma_prefetch_desc(&map_a3);
     if (P.fused && P.C1 > 0) tma_prefetch_desc(&map_cat);
-    // fused mode: every stage needs TWO arrivals on a_full -- its filler's and the bystander's (see the header)
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], P.fused ? 2 : 1); mbar_init(&a_empty[i], 1); }
+    // fused mode 1: every stage needs TWO arrivals on a_full -- its filler's and the bystander's (see the header)
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], P.fused == 1 ? 2 : 1); mbar_init(&a_empty[i], 1); mbar_init(&a_raw[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     mbar_fence_init();
@@ -209,7 +237,7 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           if (cg < P.C0) tma_prefetch_4d(&map_a0, cg, px0 - 1, py0 - 1, pn);
           else tma_prefetch_4d(&map_cat, cg - P.C0, px0 - 1, py0 - 1, pn);
         };
-        if (tile == (int)blockIdx.x) for (int i = 0; i < 3; ++i) prefetch_chunk(i);
+        if (tile == (int)blockIdx.x) for (int i = 0; i < (P.fused == 1 ? 3 : 1); ++i) prefetch_chunk(i);
         for (int s = 0; s < P.nseg; ++s) {
           const CUtensorMap* ma = s == 0 ? &map_a0 : (s == 1 ? &map_a1 : (s == 2 ? &map_a2 : &map_a3));
           const int ntap = P.seg_taps[s];
@@ -217,9 +245,15 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           const bool soft = P.fused && s == 0;
           for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 100 + sa);
-            if (soft) {
+            if (soft && P.fused == 1) {
               mbar_arrive(&a_full[sa]);            // bystander arrival: this role has seen the slot's release
               prefetch_chunk(ch + 3);
+            } else if (soft) {                     // mode 2: raw tile by TMA, transformed in place by the producers
+              const int cg = ch * BLOCK_K;
+              mbar_arrive_expect_tx(&a_raw[sa], A_BYTES);
+              if (cg < P.C0) tma_load_4d(smem + sa * A_STRIDE, &map_a0, &a_raw[sa], cg, x0 - 1, y0 - 1, n);
+              else tma_load_4d(smem + sa * A_STRIDE, &map_cat, &a_raw[sa], cg - P.C0, x0 - 1, y0 - 1, n);
+              prefetch_chunk(ch + 1);
             } else {
               mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
               tma_load_4d(smem + sa * A_STRIDE, ma, &a_full[sa], ch * BLOCK_K, x0 - 1, y0 - 1, n);
@@ -329,6 +363,95 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       if (++as == 2) { as = 0; as_phase ^= 1; }
     }
     if (e == 0) tma_store_wait_all0();
+  } else if (P.fused >= 2) {
+    // =========================== activation producers (warps 6..13), in place: TMA-landed raw tile -> silu(a*x+b) ===
+    // thread = (8-channel vector cv, rows (pt >> 3) + 32 j): its (a, b) live in registers, prefetched one chunk ahead
+    const int pt = threadIdx.x - 192;              // 0..255
+    const int cv = pt & 7;
+    const int Ct = P.C0 + P.C1;
+    const int nfused = P.seg_chunks[0];
+    int other_stages = 0;
+    for (int s = 1; s < P.nseg; ++s) other_stages += P.seg_chunks[s];
+    int sa = 0;
+    uint32_t raw_phase = 0;                        // bit i: parity this role expects next on a_raw[i]
+    // which of this thread's rows lie on the tile's halo border (bit j <-> row (pt >> 3) + 32 j); a border row is
+    // outside the image exactly when the tile touches that image edge
+    uint32_t m_rows = 0, m_left = 0, m_right = 0, m_top = 0, m_bot = 0;
+#pragma unroll
+    for (int j = 0; j < PROD_ITEMS; ++j) {
+      const int row = (pt >> 3) + 32 * j;
+      const int yy = row / HALO_W, xx = row - yy * HALO_W;
+      if (row < HALO_ROWS) {
+        m_rows |= 1u << j;
+        if (xx == 0) m_left |= 1u << j;
+        if (xx == HALO_W - 1) m_right |= 1u << j;
+        if (yy == 0) m_top |= 1u << j;
+        if (yy == HALO_H - 1) m_bot |= 1u << j;
+      }
+    }
+    const uint32_t cell0 = (uint32_t)((pt >> 3) * 128 + ((cv ^ ((pt >> 3) & 7)) << 4));   // + 4096 j: same swizzle phase
+    auto produce = [&](auto h2tag) {
+      constexpr bool H2 = decltype(h2tag)::value;  // mode 3: half2 math on {m_hi, m_lo, a/2, beta/2}; mode 2: fp32 (a, b)
+      float4 abn[4];
+      auto load_ab = [&](int tile, int ch) {
+        const int n = (tile / P.n_cblk) / tiles_per_utt;
+        const float4* q = H2 ? reinterpret_cast<const float4*>(P.ab16 + (((size_t)n * Ct + ch * 64 + cv * 8) >> 1))
+                             : reinterpret_cast<const float4*>(P.ab + (size_t)n * Ct + ch * 64 + cv * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) abn[k] = __ldg(q + k);
+      };
+      if ((int)blockIdx.x < P.num_tiles) load_ab(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / P.n_cblk;
+        const int rem = m_tile % tiles_per_utt;
+        const int x0 = (rem % P.tiles_w) * TILE_W, y0 = (rem / P.tiles_w) * TILE_H;
+        const uint32_t live = m_rows & ~((x0 == 0 ? m_left : 0u) | (x0 + TILE_W == P.W ? m_right : 0u) |
+                                         (y0 == 0 ? m_top : 0u) | (y0 + TILE_H == P.H ? m_bot : 0u));
+        for (int ch = 0; ch < nfused; ++ch) {
+          float4 c4[4];                            // this chunk's constants; abn is refilled for the next chunk
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            c4[k] = abn[k];
+            if (!H2) { c4[k].x *= 0.5f; c4[k].y *= 0.5f; c4[k].z *= 0.5f; c4[k].w *= 0.5f; }   // tanh form takes z/2
+          }
+          if (ch + 1 < nfused) load_ab(tile, ch + 1);
+          else if (tile + (int)gridDim.x < P.num_tiles) load_ab(tile + gridDim.x, 0);
+          mbar_wait(&a_raw[sa], (raw_phase >> sa) & 1u, P.dbg, 620 + sa);
+          raw_phase ^= 1u << sa;
+          const uint32_t cell = smem_u32(smem + sa * A_STRIDE) + cell0;
+          uint4 v[PROD_ITEMS];
+#pragma unroll
+          for (int j = 0; j < PROD_ITEMS; ++j)
+            if ((live >> j) & 1u) v[j] = lds128(cell + 4096 * j);
+#pragma unroll
+          for (int j = 0; j < PROD_ITEMS; ++j) {
+            // out-of-image pixels keep TMA's zero fill: the conv pads AFTER the activation
+            if ((live >> j) & 1u) {
+              const uint32_t* xw = reinterpret_cast<const uint32_t*>(&v[j]);
+              uint4 o;
+              uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (H2) {
+                  const uint4 q = *reinterpret_cast<const uint4*>(&c4[k]);
+                  ow[k] = gn_silu_h2(xw[k], q.x, q.y, q.z, q.w);
+                } else {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xw[k]));
+                  ow[k] = silu_half_pair(fmaf(c4[k].x, f.x, c4[k].y), fmaf(c4[k].z, f.y, c4[k].w));
+                }
+              }
+              sts128(cell + 4096 * j, o);
+            }
+          }
+          fence_proxy_async_smem();                // generic-proxy stores -> visible to the tensor core's async proxy
+          named_bar_sync(2, NUM_PROD_THREADS);
+          if (pt == 0) mbar_arrive(&a_full[sa]);
+          if (++sa == A_STAGES) sa = 0;
+        }
+        sa = (sa + other_stages) % A_STAGES;       // TMA-fed stages are none of this role's business
+      }
+    };
+    if (P.fused == 3) produce(std::true_type{}); else produce(std::false_type{});
   } else if (P.fused) {
     // =========================== activation producers (warps 6..13): raw x -> silu(a*x+b) -> halo tile ======
     // 256 threads share one stage (11 x 128-bit vectors each, all loads in flight at once).  The loads of the NEXT
@@ -437,7 +560,9 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   for (int i = 0; i < a.nseg; ++i) { srcs[nseg] = &a.seg[i].src; taps[nseg++] = a.seg[i].taps; }
   if (a.residual) { srcs[nseg] = a.residual; taps[nseg++] = 1; }
   P.nseg = nseg;
-  P.fused = a.gn_ab ? 1 : 0;
+  // fused producers: 3 = in place, half2 math (default); 2 = in place, fp32 math (variant 9, or no half2 table);
+  // 1 = LDG-fed, fp32 math (variant 8, the first fused version)
+  P.fused = a.gn_ab ? (g_tc_variant == 8 ? 1 : ((g_tc_variant == 9 || !a.gn_ab16) ? 2 : 3)) : 0;
   const TensorDesc* cat = (a.gn_ab && a.gn_has_cat) ? &a.gn_cat : nullptr;
   CUtensorMap ma[MAX_SEG];
   int kb = 0;
@@ -454,7 +579,7 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   if (P.fused) {
     P.src0 = (const __half*)srcs[0]->p; P.C0 = srcs[0]->C;
     P.src1 = cat ? (const __half*)cat->p : nullptr; P.C1 = cat ? cat->C : 0;
-    P.ab = a.gn_ab;
+    P.ab = a.gn_ab; P.ab16 = a.gn_ab16;
   }
   const int ld = a.w_tc_ld ? a.w_tc_ld : a.ktot();
   SG_CHECK(kb * 64 <= ld, "conv_tc6: K blocks (%d) exceed the packed weight row (%d)", kb * 64, ld);

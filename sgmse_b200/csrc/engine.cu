@@ -362,8 +362,11 @@ struct Fwd {
 
   float2* gn(const TensorDesc& x0, const TensorDesc* x1, long long g_off, long long b_off) {
     const int Ct = x0.C + (x1 ? x1->C : 0);
-    float2* ab = (float2*)e.arena.alloc((size_t)x0.N * Ct * 8);
-    if (!dry) { launch_gn_finalize(st, x0, x1, e.blob_dev + g_off, e.blob_dev + b_off, gn_groups(Ct), ab); count(); }
+    // (a, b) as float2 [N][Ct], followed by the half2 table [N][Ct/2] x 16 B of the in-conv producers (ab16_of)
+    float2* ab = (float2*)e.arena.alloc((size_t)x0.N * Ct * 16);
+    const int groups = gn_groups(Ct);
+    uint4* ab16 = (Ct / groups) % 2 == 0 ? (uint4*)(ab + (size_t)x0.N * Ct) : nullptr;
+    if (!dry) { launch_gn_finalize(st, x0, x1, e.blob_dev + g_off, e.blob_dev + b_off, groups, ab, ab16); count(); }
     return ab;
   }
 
@@ -376,7 +379,7 @@ struct Fwd {
     float2* ab0 = gn(x0, x1, l.gn0_w, l.gn0_b);
     // Fused path (conv_tc5): the 3x3 convs read the RAW tensor and apply GroupNorm+SiLU on the way into shared
     // memory, so the gn_apply pass (one read + one write of the tensor) and its buffer disappear.
-    const bool fuse_ok = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && (g_tc_variant == 0 || g_tc_variant == 5 || g_tc_variant == 7);
+    const bool fuse_ok = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && (g_tc_variant == 0 || g_tc_variant == 5 || g_tc_variant >= 7);
     auto shape_ok = g_tc_variant == 5 ? conv_tc5_shape_ok : conv_tc6_fuse_shape_ok;
     const bool fuse0 = fuse_ok && ((e.tc_mask >> 8) & 1) && rs == RS_NONE && l.c0.w_tc && shape_ok(Ho, Wo, x0.C, x1 ? x1->C : 0, l.cout, 0);
     const int nraw1 = l.shortcut ? ((rs == RS_NONE && x1) ? 2 : 1) : 1;
@@ -398,7 +401,7 @@ struct Fwd {
       ConvArgs a;
       a.nseg = 1; a.seg[0].taps = 9;
       if (fuse0) {
-        a.seg[0].src = x0; a.gn_ab = ab0;
+        a.seg[0].src = x0; a.gn_ab = ab0; a.gn_ab16 = (const uint4*)(ab0 + (size_t)N * Ct);
         if (x1) { a.gn_has_cat = true; a.gn_cat = *x1; }
       } else {
         a.seg[0].src = h0;
@@ -417,7 +420,7 @@ struct Fwd {
     {
       ConvArgs a;
       a.nseg = 1; a.seg[0].taps = 9;
-      if (fuse1) { a.seg[0].src = h1; a.gn_ab = ab1; } else { a.seg[0].src = h2; }
+      if (fuse1) { a.seg[0].src = h1; a.gn_ab = ab1; a.gn_ab16 = (const uint4*)(ab1 + (size_t)N * l.cout); } else { a.seg[0].src = h2; }
       if (l.shortcut) {
         if (rs != RS_NONE) { a.seg[a.nseg].src = xr; a.seg[a.nseg++].taps = 1; }
         else {
@@ -465,6 +468,11 @@ struct Fwd {
 
   const float4* outconv(const Layer& l, const TensorDesc& h, const float4* addend) {
     float2* ab = gn(h, nullptr, l.gn0_w, l.gn0_b);
+    if (out_conv_fuses_gn(h)) {                    // GroupNorm-apply + SiLU happen while the conv stages its tile
+      float4* out = act4(h.N, h.H, h.W);
+      if (!dry) { launch_out_conv(st, h, l.small_w, l.out_bias_host, addend, out, ab); count(); }
+      return out;
+    }
     TensorDesc a = act(h.N, h.H, h.W, h.C, false);
     if (!dry) { launch_gn_apply(st, h, nullptr, ab, true, RS_NONE, a, nullptr); count(); }
     float4* out = act4(h.N, h.H, h.W);
@@ -1206,6 +1214,14 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
     clear_graphs(*e);
   }
   else if (k == "attn_variant") { sgmse::g_attn_variant = (int)value; clear_graphs(*e); }
+  else if (k == "fir_variant") { sgmse::g_fir_variant = (int)value; clear_graphs(*e); }
+  else if (k == "inconv_variant") { sgmse::g_inconv_variant = (int)value; clear_graphs(*e); }
+  else if (k == "outconv_variant") {
+    sgmse::g_outconv_variant = (int)value;       // changes the buffers a forward needs (fused GroupNorm or not)
+    if (e->lanes.size() > 1) ensure_lanes(*e, 1);
+    e->arena_need.clear();
+    clear_graphs(*e);
+  }
   else if (k == "lanes") {
     SG_CHECK(value >= 1 && value <= 8, "lanes must be in 1..8");
     e->num_lanes = (int)value;

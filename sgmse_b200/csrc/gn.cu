@@ -16,7 +16,7 @@ namespace sgmse {
 __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int slots0,
                                    const float* __restrict__ st1, int C1, int slots1,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   int cpg, double inv_count, float2* __restrict__ ab) {
+                                   int cpg, double inv_count, float2* __restrict__ ab, uint4* __restrict__ ab16) {
   const int g = blockIdx.x, n = blockIdx.y;
   const int Ct = C0 + C1;
   const int max_slots = slots0 > slots1 ? slots0 : slots1;
@@ -64,20 +64,38 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int sl
     const float a = gamma[ch] * rstd;
     ab[(size_t)n * Ct + ch] = make_float2(a, beta[ch] - (float)mean * a);
   }
+  // half2 form for the in-conv producers (conv_tc6 fused mode 3): per channel PAIR {m_hi, m_lo, a/2, beta/2} with
+  // mean = m_hi + m_lo split in two halfs, so that z/2 = (a/2) * ((x - m_hi) - m_lo) + beta/2 has no cancellation
+  // against a rounded constant.  cpg is even whenever this table is requested.
+  if (ab16)
+    for (int pl = threadIdx.x; pl < cpg / 2; pl += blockDim.x) {
+      const int ch = g * cpg + 2 * pl;
+      const float mf = (float)mean;
+      const __half mh = __float2half_rn(mf);
+      const __half ml = __float2half_rn(mf - __half2float(mh));
+      const __half2 m_hi = __halves2half2(mh, mh), m_lo = __halves2half2(ml, ml);
+      const __half2 ah = __floats2half2_rn(0.5f * gamma[ch] * rstd, 0.5f * gamma[ch + 1] * rstd);
+      const __half2 bh = __floats2half2_rn(0.5f * beta[ch], 0.5f * beta[ch + 1]);
+      uint4 v;
+      v.x = *reinterpret_cast<const uint32_t*>(&m_hi); v.y = *reinterpret_cast<const uint32_t*>(&m_lo);
+      v.z = *reinterpret_cast<const uint32_t*>(&ah); v.w = *reinterpret_cast<const uint32_t*>(&bh);
+      ab16[((size_t)n * Ct + ch) >> 1] = v;
+    }
 }
 
 void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc* s1, const float* gamma,
-                        const float* beta, int groups, float2* ab) {
+                        const float* beta, int groups, float2* ab, uint4* ab16) {
   const int C1 = s1 ? s1->C : 0;
   const int Ct = s0.C + C1;
   SG_CHECK(Ct % groups == 0, "GroupNorm: %d channels not divisible by %d groups", Ct, groups);
   SG_CHECK(s0.stats && s0.slots > 0 && (!s1 || (s1->stats && s1->slots > 0)), "GroupNorm input has no statistics");
   if (s1) SG_CHECK(s1->N == s0.N && s1->H == s0.H && s1->W == s0.W, "concat shape mismatch");
   const int cpg = Ct / groups;
+  SG_CHECK(!ab16 || cpg % 2 == 0, "GroupNorm: the half2 coefficient table needs an even number of channels per group");
   const double inv_count = 1.0 / ((double)s0.H * s0.W * cpg);
   dim3 grid(groups, s0.N);
   gn_finalize_kernel<<<grid, 256, 0, st>>>(s0.stats, s0.C, s0.slots, s1 ? s1->stats : nullptr, C1,
-                                           s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab);
+                                           s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab, ab16);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -239,7 +257,19 @@ gn_apply_fir_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ 
 // Phase 1 stages h = silu(a*x+b) and the raw x of an input tile (+1 pixel halo) in smem as fp32->half pairs;
 // phase 2 applies the separable [1,3,3,1] FIR from smem and writes both outputs with 128-bit stores.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int RS, int TIN, int CV>   // TIN: input tile edge incl. halo; CV: 8-channel vectors per block
+int g_fir_variant = 0;   // 0: one-MUFU silu (tanh form) + half2 FIR-down arithmetic; 1: expf/divide silu, fp32 FIR
+
+// silu(z) = hz*tanh(hz) + hz with hz = z/2: one MUFU instead of two (ex2 + rcp)
+__device__ __forceinline__ float silu_tanh_half_arg(float hz) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hz));
+  return fmaf(hz, t, hz);
+}
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
+template <typename T, int RS, int TIN, int CV, bool FAST>   // TIN: input tile edge incl. halo; CV: 8-channel vectors per block
 __global__ void __launch_bounds__(256)
 gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ ab, int Hi, int Wi,
                           T* __restrict__ out0, T* __restrict__ out1) {
@@ -259,6 +289,10 @@ gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restr
     const float4* p = reinterpret_cast<const float4*>(ab + (size_t)n * C + c);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { float4 v = p[i]; a[2 * i] = v.x; b[2 * i] = v.y; a[2 * i + 1] = v.z; b[2 * i + 1] = v.w; }
+    if (FAST) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] *= 0.5f; b[i] *= 0.5f; }   // the tanh form takes z/2
+    }
   }
   const T* src = x0 + (size_t)n * Hi * Wi * C + c;
   for (int item = threadIdx.x; item < TIN * TIN * CV; item += 256) {
@@ -268,7 +302,7 @@ gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restr
     if ((unsigned)y < (unsigned)Hi && (unsigned)x < (unsigned)Wi) {
       Vec8<T> v; v.load(src + ((size_t)y * Wi + x) * C); v.get(f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) h[i] = silu_f(fmaf(a[i], f[i], b[i]));
+      for (int i = 0; i < 8; ++i) h[i] = FAST ? silu_tanh_half_arg(fmaf(a[i], f[i], b[i])) : silu_f(fmaf(a[i], f[i], b[i]));
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { f[i] = 0.f; h[i] = 0.f; }   // zero padding applies AFTER the activation
@@ -278,6 +312,53 @@ gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restr
     o.set(f); o.store(&xs[px][cv * 8]);
   }
   __syncthreads();
+  if constexpr (FAST && RS == RS_DOWN) {
+    // half2 arithmetic, tree-shaped: row sums k0*(t0+t3) + k1*(t1+t2), then the same across the four rows
+    // (4 rounding levels of 2^-11 instead of 16 sequential ones; x0.125 is exact)
+    const uint32_t K0 = 0x30003000u, K1 = 0x36003600u;   // half2(0.125), half2(0.375)
+    for (int item = threadIdx.x; item < TOUT * TOUT * CV; item += 256) {
+      const int opx = item / CV;
+      const int oy = opx / TOUT, ox = opx % TOUT;
+      uint4 rh[4], rx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int base = (2 * oy + i) * TIN + 2 * ox;
+        uint4 th[4], tx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          th[j] = *reinterpret_cast<const uint4*>(&hs[base + j][cv * 8]);
+          tx[j] = *reinterpret_cast<const uint4*>(&xs[base + j][cv * 8]);
+        }
+        auto rowsum = [&](const uint4 (&tt)[4], uint4& r) {
+          const uint32_t* t0 = reinterpret_cast<const uint32_t*>(&tt[0]);
+          const uint32_t* t1 = reinterpret_cast<const uint32_t*>(&tt[1]);
+          const uint32_t* t2 = reinterpret_cast<const uint32_t*>(&tt[2]);
+          const uint32_t* t3 = reinterpret_cast<const uint32_t*>(&tt[3]);
+          uint32_t* rr = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rr[q] = h2_fma(K1, h2_add(t1[q], t2[q]), h2_mul(K0, h2_add(t0[q], t3[q])));
+        };
+        rowsum(th, rh[i]);
+        rowsum(tx, rx[i]);
+      }
+      uint4 oh, oxr;
+      auto colsum = [&](const uint4 (&r)[4], uint4& o) {
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(&r[0]);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(&r[1]);
+        const uint32_t* r2 = reinterpret_cast<const uint32_t*>(&r[2]);
+        const uint32_t* r3 = reinterpret_cast<const uint32_t*>(&r[3]);
+        uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) oo[q] = h2_fma(K1, h2_add(r1[q], r2[q]), h2_mul(K0, h2_add(r0[q], r3[q])));
+      };
+      colsum(rh, oh);
+      colsum(rx, oxr);
+      const int Y = blockIdx.y * TOUT + oy, X = blockIdx.x * TOUT + ox;
+      const size_t o = (((size_t)n * Ho + Y) * Wo + X) * C + c;
+      *reinterpret_cast<uint4*>(out0 + o) = oh;
+      *reinterpret_cast<uint4*>(out1 + o) = oxr;
+    }
+  } else
   for (int item = threadIdx.x; item < TOUT * TOUT * CV; item += 256) {
     const int opx = item / CV;
     const int oy = opx / TOUT, ox = opx % TOUT;
@@ -336,10 +417,12 @@ static void gn_apply_dispatch(cudaStream_t st, const TensorDesc& x0, const Tenso
     T* o1 = (T*)out1->p;
     if (std::is_same<T, __half>::value && rs == RS_UP && x0.H % 8 == 0 && x0.W % 8 == 0 && x0.C % 64 == 0) {
       dim3 g(x0.W / 8, x0.H / 8, x0.N * (x0.C / 64));
-      gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      if (g_fir_variant == 0) gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, true><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      else gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, false><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
     } else if (std::is_same<T, __half>::value && rs == RS_DOWN && out0.H % 8 == 0 && out0.W % 8 == 0 && x0.C % 32 == 0) {
       dim3 g(out0.W / 8, out0.H / 8, x0.N * (x0.C / 32));
-      gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      if (g_fir_variant == 0) gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, true><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      else gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, false><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
     } else
     if (rs == RS_DOWN) gn_apply_fir_kernel<T, RS_DOWN><<<grid, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
     else gn_apply_fir_kernel<T, RS_UP><<<grid, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);

@@ -24,14 +24,17 @@ struct TensorDesc {
 
 // ---- GroupNorm ----
 // ab[n][c] = (a, b) with y = a*x + b  (a = gamma*rstd, b = beta - mean*rstd*gamma), eps = 1e-6
+// ab16 (optional): [n][Ct/2] per channel pair {half2 m_hi, half2 m_lo, half2 a/2, half2 beta/2}, mean = m_hi + m_lo
 void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc* s1, const float* gamma,
-                        const float* beta, int groups, float2* ab);
+                        const float* beta, int groups, float2* ab, uint4* ab16 = nullptr);
 // stand-alone per-(sample, channel) statistics (slots = 1) for levels too small for per-tile partials
 void launch_channel_stats(cudaStream_t st, TensorDesc& t);
 enum Resample { RS_NONE = 0, RS_DOWN = 1, RS_UP = 2 };
 // out0 = [silu](a*x+b) (concat of x0,x1), optionally FIR-resampled; out1 (optional) = FIR-resampled raw x0
 void launch_gn_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float2* ab, bool silu,
                      Resample rs, TensorDesc& out0, TensorDesc* out1);
+
+extern int g_fir_variant;   // 0: one-MUFU (tanh-form) silu + half2 FIR-down arithmetic in the tiled fp16 kernels; 1: expf silu, fp32 FIR
 
 // ---- convolutions ----
 struct ConvSeg {
@@ -53,6 +56,7 @@ struct ConvArgs {
   // Fused GroupNorm-apply + SiLU (conv_tc5 only): seg[0] (3x3) reads RAW tensors -- seg[0].src, concatenated with
   // gn_cat when gn_has_cat -- and applies silu(a*x+b) with (a, b) = gn_ab[n][channel] on the way into shared memory.
   const float2* gn_ab = nullptr;
+  const uint4* gn_ab16 = nullptr;  // the same coefficients in the half2 form of launch_gn_finalize (conv_tc6 mode 3)
   bool gn_has_cat = false;
   TensorDesc gn_cat;
   int ktot() const {
@@ -85,7 +89,9 @@ bool conv_tc6_fuse_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
 extern int g_tc_variant;   // 0 (= 7): newest applicable kernels (v6 with fused GN where possible, else v4/v1), 1: v1 only,
                            // 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1), 4: v4 (+v1) without GroupNorm fusion,
-                           // 5: v5 fused GN (+v4), 6: v6 without fusion (+v4)
+                           // 5: v5 fused GN (+v4), 6: v6 without fusion (+v4), 8: v6 with the first-version fused
+                           // producers (LDG-fed, mode 1), 9: in-place producers with fp32 math (mode 2); the default (0)
+                           // is in place with half2 math (mode 3)
 
 // input layer: state float4 (x.re,x.im,y.re,y.im) -> conv3x3(4->C); w [36][C] (k = tap*4+cin), bias [C]
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
@@ -96,8 +102,12 @@ void launch_combine(cudaStream_t st, const float4* pyr, const float* w, const fl
 // 4-channel FIR resample of the input/output pyramids
 void launch_fir4(cudaStream_t st, const float4* in, int N, int H, int W, Resample rs, float4* out);
 // out4 = conv3x3_{C->4}(act) + bias (+ addend);  w [9*C][4] (device), bias: HOST pointer to 4 floats
+// gn_ab != nullptr: `act` is the RAW tensor and silu(a*x+b) is applied while staging (only when out_conv_fuses_gn(act))
+bool out_conv_fuses_gn(const TensorDesc& act);
 void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, const float* bias,
-                     const float4* addend, float4* out);
+                     const float4* addend, float4* out, const float2* gn_ab = nullptr);
+extern int g_outconv_variant;   // 0: mma.sync kernel for fp16 C in {128, 256} (fuses GroupNorm+SiLU); 1: CUDA-core kernels
+extern int g_inconv_variant;    // 0: mma.sync input conv for fp16 C in {32, 64, 128}; 1: CUDA-core kernel
 
 // ---- attention: qkv [N,H,W,3C] (q|k|v), out [N,H,W,C] = softmax(q k^T / sqrt(C)) v over H*W tokens
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out);

@@ -8,6 +8,16 @@
 
 namespace sgmse {
 
+// mma.sync helpers shared by the 4-channel ends
+__device__ __forceinline__ void oc_ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void oc_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 // ------------------------------------------------------------------------------------------------
 // input conv: state float4 [N,H,W] -> T [N,H,W,C];   w[k][c], k = tap*4 + cin
 // ------------------------------------------------------------------------------------------------
@@ -55,10 +65,152 @@ __global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restric
   }
 }
 
+// fp16 tensor-core variant (mma.sync m16n8k16): the 36-deep contraction (9 taps x 4 state components) is padded to
+// K = 48 = 3 k-steps; a warp owns 32 pixels x all C output channels (2 m-tiles x NT n-tiles).  The CUDA-core kernel
+// above needs 36 FMA per output element (FMA-bound: ~150 us for [16,256,512] -> 128 channels at full FP32 rate);
+// here the arithmetic is 3 HMMA per 16x8 outputs and the kernel is bound by the 256 B/pixel it writes.
+//   A fragment (pixels x k): k = tap*4 + component, so the k pair (2t, 2t+1) of k-step s is the (.xy | .zw) half of the
+//   state float4 of neighbour tap 4s + (t >> 1) [a0/a1] and 4s + 2 + (t >> 1) [a2/a3]: straight from global/L1.
+//   B fragments (k x channels) are built once per block in shared memory; the block then walks tiles of 128 pixels.
+//   Output goes through a per-warp padded smem tile so that global stores are 128-bit and row-contiguous.
+int g_inconv_variant = 0;   // 0: tensor-core kernel for fp16 output where it applies, 1: CUDA-core kernel
+
+template <int NT>   // NT = C / 8
+__global__ void __launch_bounds__(128) input_conv_mma_kernel(const float4* __restrict__ state, int H, int W,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             __half* __restrict__ out, float* __restrict__ stats, int slots,
+                                                             int num_tiles) {
+  constexpr int C = NT * 8;
+  constexpr int PITCH = C + 8;                       // halfs per staged row: conflict-free 32-bit writes, 16-B aligned rows
+  extern __shared__ __align__(16) uint8_t ic_smem[];
+  uint2* wfrag = reinterpret_cast<uint2*>(ic_smem);                                   // [3][NT][32]
+  __half* stage = reinterpret_cast<__half*>(ic_smem + (size_t)3 * NT * 32 * sizeof(uint2));   // [4 warps][32][PITCH]
+  float* red = reinterpret_cast<float*>(stage + (size_t)4 * 32 * PITCH);              // [4 warps][C][2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 3 * NT * 32; i += 128) {
+    const int l = i & 31, j = (i >> 5) % NT, s = i / (32 * NT);
+    const int gg = l >> 2, tt = l & 3;
+    const int c = j * 8 + gg;
+    const int k0 = 16 * s + 2 * tt;
+    auto wk = [&](int k) { return k < 36 ? w[k * C + c] : 0.f; };
+    const __half2 b0 = __floats2half2_rn(wk(k0), wk(k0 + 1));
+    const __half2 b1 = __floats2half2_rn(wk(k0 + 8), wk(k0 + 9));
+    wfrag[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
+  }
+  float bia[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { bia[j][0] = bias[j * 8 + 2 * t]; bia[j][1] = bias[j * 8 + 2 * t + 1]; }
+  __syncthreads();
+  const int HW = H * W;
+  __half* wstage = stage + (size_t)warp * 32 * PITCH;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int m0 = tile * 128;
+    const int n = m0 / HW, r0 = m0 - n * HW;
+    const float4* sp = state + (size_t)n * HW;
+    float ssum[NT][2], ssq[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { ssum[j][0] = ssum[j][1] = ssq[j][0] = ssq[j][1] = 0.f; }
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      // A fragments of this m-tile: rows g and g + 8
+      uint32_t af[3][4];
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        const int r = r0 + warp * 32 + mt * 16 + g + hr * 8;
+        const int py = r / W, px = r - py * W;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {                 // q-th k-octet: tap 2q + (t >> 1)
+          const int tap = 2 * q + (t >> 1);
+          float2 v = make_float2(0.f, 0.f);
+          if (tap < 9) {
+            const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;
+            if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W)
+              v = reinterpret_cast<const float2*>(sp + (size_t)y * W + x)[t & 1];
+          }
+          const __half2 hv = __floats2half2_rn(v.x, v.y);
+          af[q >> 1][(q & 1) * 2 + hr] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const uint2 b = wfrag[(s * NT + j) * 32 + lane];
+          oc_mma(acc, af[s], b.x, b.y);
+        }
+        // rows g (acc[0..1]) and g + 8 (acc[2..3]), channels 8j + 2t, +1
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const __half2 hv = __floats2half2_rn(acc[2 * hr] + bia[j][0], acc[2 * hr + 1] + bia[j][1]);
+          const float2 f = __half22float2(hv);
+          ssum[j][0] += f.x; ssq[j][0] = fmaf(f.x, f.x, ssq[j][0]);
+          ssum[j][1] += f.y; ssq[j][1] = fmaf(f.y, f.y, ssq[j][1]);
+          *reinterpret_cast<__half2*>(wstage + (size_t)(mt * 16 + g + hr * 8) * PITCH + j * 8 + 2 * t) = hv;
+        }
+      }
+    }
+    __syncwarp();
+    // 32 rows x C halfs -> global, 128-bit, row-contiguous
+    {
+      __half* op = out + (size_t)(m0 + warp * 32) * C;
+      constexpr int VPR = C / 8;                       // 16-B vectors per row
+      for (int i = lane; i < 32 * VPR; i += 32) {
+        const int row = i / VPR, cvv = i - row * VPR;
+        *reinterpret_cast<uint4*>(op + (size_t)row * C + cvv * 8) =
+            *reinterpret_cast<const uint4*>(wstage + (size_t)row * PITCH + cvv * 8);
+      }
+    }
+    if (stats) {
+      // per-channel partials of the 128-pixel tile: rows across lanes (fixed xor tree), then the 4 warps in order
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float s1 = ssum[j][e], s2 = ssq[j][e];
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+          if (g == 0) { red[(warp * C + j * 8 + 2 * t + e) * 2] = s1; red[(warp * C + j * 8 + 2 * t + e) * 2 + 1] = s2; }
+        }
+      __syncthreads();
+      for (int c = tid; c < C; c += 128) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 4; ++wv) { s1 += red[(wv * C + c) * 2]; s2 += red[(wv * C + c) * 2 + 1]; }
+        float* d = stats + (((size_t)n * slots + r0 / 128) * C + c) * 2;
+        d[0] = s1; d[1] = s2;
+      }
+      __syncthreads();
+    }
+    __syncwarp();
+  }
+}
+
+template <int NT>
+static void input_conv_mma_launch(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
+                                  const float* bias, TensorDesc& out) {
+  constexpr int C = NT * 8;
+  const int num_tiles = N * H * W / 128;
+  const size_t smem = (size_t)3 * NT * 32 * sizeof(uint2) + (size_t)4 * 32 * (C + 8) * 2 + (size_t)4 * C * 2 * 4;
+  auto k = input_conv_mma_kernel<NT>;
+  CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(num_tiles, 148 * 4);
+  k<<<grid, 128, smem, st>>>(state, H, W, w, bias, (__half*)out.p, out.stats, out.slots, num_tiles);
+  CUDA_OK(cudaGetLastError());
+}
+
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
                        const float* bias, TensorDesc& out) {
   const int HW = H * W;
   SG_CHECK(HW % 32 == 0, "input conv: H*W must be a multiple of 32");
+  if (out.dt == DT_F16 && g_inconv_variant == 0 && HW % 128 == 0 && (out.C == 128 || out.C == 64 || out.C == 32)) {
+    out.slots = HW / 128;
+    if (out.C == 128) input_conv_mma_launch<16>(st, state, N, H, W, w, bias, out);
+    else if (out.C == 64) input_conv_mma_launch<8>(st, state, N, H, W, w, bias, out);
+    else input_conv_mma_launch<4>(st, state, N, H, W, w, bias, out);
+    return;
+  }
   const int TP = (HW % 128 == 0) ? 128 : 32;
   out.slots = HW / TP;
   const int grid = N * HW / TP;
@@ -257,19 +409,11 @@ __global__ void __launch_bounds__(256) out_conv_coop_kernel(const T* __restrict_
 // fp16 tensor-core variant (mma.sync m16n8k16, N = 8 with the 4 real outputs in columns 0..3): a block stages a
 // 16x16 pixel tile (+1 halo) of the activation in shared memory once, every warp computes two 16-pixel rows with
 // 9 taps x C/16 MMAs each.  ~15x fewer instructions than the CUDA-core kernels above; HBM/L2-bound.
-__device__ __forceinline__ void oc_ldsm_x4(uint32_t (&r)[4], const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void oc_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 template <int C>
 __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restrict__ act, int H, int W,
                                                            const float* __restrict__ w, float4 bias,
-                                                           const float4* __restrict__ addend, float4* __restrict__ out) {
+                                                           const float4* __restrict__ addend, float4* __restrict__ out,
+                                                           const float2* __restrict__ gn_ab) {
   constexpr int LD = C + 8;            // halfs per staged pixel (16-byte aligned, conflict-free ldmatrix rows)
   constexpr int KS = C / 16;
   extern __shared__ __align__(16) uint8_t oc_smem[];
@@ -292,12 +436,30 @@ __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restr
     }
     wfrag[i] = v;
   }
+  // optional fused GroupNorm-apply + SiLU of the RAW tensor while staging (256 % (C/8) == 0: a thread keeps one
+  // 8-channel vector, so its (a, b) live in registers); out-of-image pixels stay zero (padding follows the activation)
+  float ga[8], gb[8];
+  if (gn_ab) {
+    const float4* q = reinterpret_cast<const float4*>(gn_ab + (size_t)n * C + (tid % (C / 8)) * 8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float4 v = q[k]; ga[2 * k] = v.x; gb[2 * k] = v.y; ga[2 * k + 1] = v.z; gb[2 * k + 1] = v.w; }
+  }
   for (int i = tid; i < 18 * 18 * (C / 8); i += 256) {
     const int px = i / (C / 8), cv = i % (C / 8);
     const int y = y0 - 1 + px / 18, x = x0 - 1 + px % 18;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W)
+    if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
       v = *reinterpret_cast<const uint4*>(act + (((size_t)n * H + y) * W + x) * C + cv * 8);
+      if (gn_ab) {
+        Vec8<__half> vv; vv.raw = v;
+        float f[8];
+        vv.get(f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = silu_f(fmaf(ga[k], f[k], gb[k]));
+        vv.set(f);
+        v = vv.raw;
+      }
+    }
     *reinterpret_cast<uint4*>(tile + (size_t)px * LD + cv * 8) = v;
   }
   __syncthreads();
@@ -337,12 +499,12 @@ __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restr
 
 template <int C>
 static void out_conv_mma_launch(cudaStream_t st, const TensorDesc& act, const float* w, float4 b, const float4* addend,
-                                float4* out) {
+                                float4* out, const float2* gn_ab) {
   const size_t smem = (size_t)18 * 18 * (C + 8) * 2 + (size_t)9 * (C / 16) * 32 * sizeof(uint2);
   auto k = out_conv_mma_kernel<C>;
   CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(act.W, 16), cdiv(act.H, 16), act.N);
-  k<<<grid, 256, smem, st>>>((const __half*)act.p, act.H, act.W, w, b, addend, out);
+  k<<<grid, 256, smem, st>>>((const __half*)act.p, act.H, act.W, w, b, addend, out, gn_ab);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -374,15 +536,20 @@ static void out_conv_dispatch(cudaStream_t st, const TensorDesc& act, const floa
   CUDA_OK(cudaGetLastError());
 }
 
+bool out_conv_fuses_gn(const TensorDesc& act) {
+  return act.dt == DT_F16 && g_outconv_variant == 0 && (act.C == 128 || act.C == 256);
+}
+
 void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, const float* bias,
-                     const float4* addend, float4* out) {
+                     const float4* addend, float4* out, const float2* gn_ab) {
+  SG_CHECK(!gn_ab || out_conv_fuses_gn(act), "out conv: fused GroupNorm is only available in the tensor-core kernel");
   SG_CHECK(act.C % 8 == 0, "out conv: C must be a multiple of 8");
   SG_CHECK((size_t)9 * act.C * sizeof(float4) <= 96 * 1024, "out conv: %d channels exceed the shared-memory weight buffer", act.C);
   // `bias` is a HOST pointer to 4 floats (kept with the layer description)
   const float4 b = make_float4(bias[0], bias[1], bias[2], bias[3]);
   if (act.dt == DT_F16 && g_outconv_variant == 0 && (act.C == 128 || act.C == 256)) {
-    if (act.C == 128) out_conv_mma_launch<128>(st, act, w, b, addend, out);
-    else out_conv_mma_launch<256>(st, act, w, b, addend, out);
+    if (act.C == 128) out_conv_mma_launch<128>(st, act, w, b, addend, out, gn_ab);
+    else out_conv_mma_launch<256>(st, act, w, b, addend, out, gn_ab);
     return;
   }
   if (act.dt == DT_F16) out_conv_dispatch<__half>(st, act, (const float4*)w, b, addend, out);

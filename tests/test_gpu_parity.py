@@ -250,15 +250,46 @@ def test_tc_kernel_variants_agree(full_sd):
     outs = {}
     # v1 only; v2 (+v1); v3 CTA pairs; v4 swapped operands; 5: v4 + GroupNorm/SiLU fused into the conv (conv_tc5);
     # 6: halo-tile kernel (conv_tc6) without fusion; 0 = default = conv_tc6 with the fusion
-    for variant in (1, 2, 3, 4, 5, 6, 0):
+    # 8: conv_tc6 with the first-version fused producers (LDG-fed, fp32 math); 9: TMA-fed raw tile transformed in place,
+    # fp32 math; 0 = default: in place with half2 math on the split-mean coefficient table
+    for variant in (1, 2, 3, 4, 5, 6, 8, 9, 0):
         eng.set_option("tc_variant", variant)
         outs[variant] = eng.dnn_forward(x, t)
         assert eng.counter("direct_convs_last_forward") == 0
         assert torch.isfinite(torch.view_as_real(outs[variant])).all()
-    errs = {v: rel_l2(outs[v], outs[1]) for v in (2, 3, 4, 5, 6, 0)}
+    errs = {v: rel_l2(outs[v], outs[1]) for v in (2, 3, 4, 5, 6, 8, 9, 0)}
     print("tc variants vs v1: " + ", ".join(f"v{v if v else '6-fused'} rel-L2 {e:.3e}" for v, e in errs.items()))
     assert all(e < 5e-3 for e in errs.values())
+    # the two fp32-math producers evaluate the same expression on the same values: bit-identical
+    assert torch.equal(outs[8], outs[9])
     eng.set_option("tc_variant", 0)
+    eng.close()
+
+
+def test_small_end_kernel_variants_agree(full_sd):
+    """The mma.sync input conv (state rounded to fp16, K padded 36 -> 48) against the fp32-FMA CUDA-core kernel, and
+    the progressive-output conv with GroupNorm+SiLU fused into its mma.sync staging against gn_apply + the CUDA-core
+    conv with fp32 weights."""
+    eng = Engine(EngineConfig(mode="fp16_tc", max_batch=2))
+    eng.load_state_dict(full_sd)
+    g = torch.Generator().manual_seed(13)
+    x = (torch.complex(torch.randn(2, 2, 256, 128, generator=g), torch.randn(2, 2, 256, 128, generator=g)) * 0.3).cuda()
+    t = torch.tensor([0.6, 0.05]).cuda()
+    eng.set_option("record_taps", 1)
+    base = eng.dnn_forward(x, t)
+    tap0 = eng.tap("in_conv")
+    eng.set_option("outconv_variant", 1)
+    unfused = eng.dnn_forward(x, t)
+    eng.set_option("outconv_variant", 0)
+    assert rel_l2(unfused, base) < 2e-3              # CUDA-core fp32-weight conv vs fp16 mma.sync conv
+    eng.set_option("inconv_variant", 1)
+    cc = eng.dnn_forward(x, t)
+    tap1 = eng.tap("in_conv")
+    eng.set_option("inconv_variant", 0)
+    e_in = (torch.linalg.vector_norm(tap0 - tap1) / torch.linalg.vector_norm(tap1)).item()
+    print(f"input conv mma vs CUDA-core: rel-L2 {e_in:.3e}; network output {rel_l2(cc, base):.3e}; "
+          f"out conv fused vs CUDA-core unfused {rel_l2(unfused, base):.3e}")
+    assert e_in < 2e-3 and rel_l2(cc, base) < 5e-3
     eng.close()
 
 

@@ -1,0 +1,61 @@
+"""A/B timing of one eager (un-graphed) score-network evaluation at the benchmark shape under option settings.
+
+    python tools/ab_forward.py [--batch 16] [--reps 4] tc_variant=8 tc_variant=0 inconv_variant=1 ...
+
+Each positional `key=value` is applied on top of the defaults (all variants 0) for one measurement, then reset.
+Prints ms per forward (CUDA events around `reps` forwards) and the summed tcgen05 conv time of one forward.
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from sgmse_b200 import Engine, EngineConfig
+from sgmse_b200.synth import synthetic_blob
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--T", type=int, default=512)
+ap.add_argument("settings", nargs="*")
+a = ap.parse_args()
+
+cfg = EngineConfig(mode="fp16_tc", max_batch=a.batch, use_graphs=False)
+eng = Engine(cfg)
+eng.load_blob(synthetic_blob(eng, 0))
+F = cfg.n_fft // 2 + 1
+g = torch.Generator().manual_seed(0)
+x = (torch.complex(torch.randn(a.batch, 2, F, a.T, generator=g), torch.randn(a.batch, 2, F, a.T, generator=g)) * 0.3).cuda()
+t = torch.full((a.batch,), 0.5).cuda()
+DEFAULTS = {"tc_variant": 0, "inconv_variant": 0, "outconv_variant": 0, "fir_variant": 0}
+ref = None
+for setting in ["default"] + a.settings:
+    opts = dict(DEFAULTS)
+    if setting != "default":
+        for kv in setting.split(","):
+            k, v = kv.split("=")
+            opts[k] = int(v)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    out = eng.dnn_forward(x, t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        out = eng.dnn_forward(x, t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.reps
+    eng.set_option("time_convs", 1)
+    eng.dnn_forward(x, t)
+    torch.cuda.synchronize()
+    us, mf, cnt = eng.counter("timed_conv_tc_us"), eng.counter("timed_conv_tc_mflop"), eng.counter("timed_conv_tc_count")
+    eng.set_option("time_convs", 0)
+    if ref is None:
+        ref = out.clone()
+    err = (torch.linalg.vector_norm(torch.view_as_real(out - ref)) / torch.linalg.vector_norm(torch.view_as_real(ref))).item()
+    print(f"{setting:40s} {ms:8.3f} ms/forward  launches {eng.counter('launches_last_forward'):4d}  tc convs {cnt:4d}: "
+          f"{us / 1e3:7.3f} ms = {mf / max(us, 1):7.1f} TFLOP/s   rel-L2 vs default {err:.2e}", flush=True)
+eng.close()
