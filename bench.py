@@ -271,7 +271,7 @@ def run_b200(args):
 
     roof = None
     if not args.no_roofline and args.mode == "fp16_tc":
-        # dominant kernel = conv_tc_kernel (tcgen05 implicit GEMM): CUDA events around every launch of one more
+        # dominant kernels = the tcgen05 implicit-GEMM convolutions: CUDA events around every launch of one more
         # (eager, un-graphed) step on the launching stream
         eng.set_option("time_convs", 1)
         step_dev(0)
@@ -289,7 +289,7 @@ def run_b200(args):
             tj = json.load(open(tpath))
             traffic = tj["traffic_bytes_per_launch"]
             traffic_note = {k: tj[k] for k in ("kernel", "shape", "algorithmic_bytes_per_launch", "source")}
-        roof = {"kernel": "tcgen05 implicit-GEMM convolutions (conv_tc4/conv_tc5 + conv_tc on the coarsest levels)",
+        roof = {"kernel": "tcgen05 implicit-GEMM convolutions (conv_tc6 with fused GroupNorm+SiLU producers; conv_tc4 / conv_tc on the levels below 32 rows)",
                 "bound": "tensor", "achieved": round(ach, 1),
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 4),
                 "traffic": traffic, "traffic_of": traffic_note,

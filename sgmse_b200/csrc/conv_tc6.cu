@@ -13,7 +13,7 @@
 //     2304 tensor clocks of MMA work, 11 per producer thread, loaded one stage ahead of the slot they go into.
 // Everything else (swapped operands, N = 256 pixel UMMAs, channel-per-lane epilogue, identity residual segment) is
 // conv_tc4's.
-// Fused mode 2 (default): the RAW halo tile of a fused chunk is brought in by TMA (a_raw barrier) as soon as its slot
+// Fused mode 2 (tc_variant 9; mode 3 = the same with half2 math, tc_variant 10): the RAW halo tile of a fused chunk is brought in by TMA (a_raw barrier) as soon as its slot
 // is released, and the producer warps transform it IN PLACE (LDS -> silu(a*x+b) -> STS to the same swizzled address,
 // out-of-image rows keep TMA's zero fill = the conv's zero padding) before arriving on a_full.  Global-load latency
 // is off the producers' critical path (mode 1 issues its LDGs only one stage ahead, so once the producers are the
@@ -78,6 +78,8 @@ struct Tc6Params {
   float* stats;
   int slots;
   int desc_mode;                 // 0: base_offset field 0; 1: base_offset = (start >> 7) & 7
+  int mma_style;                 // 0: one elect + 4 UMMAs + commit per tap (mma_tap_elect); 1: one elect per UMMA
+  int tma_poll;                  // 0: ordered issue loop; 1: two cursors (activations, weights) polled without blocking
   int* dbg;
 };
 
@@ -112,6 +114,43 @@ __device__ __forceinline__ void mma_elect(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One tap of one 64-channel chunk: four K=16 UMMAs (descriptor start addresses advance by 32 B = 2 units) and the
+// commit that releases the weight stage, issued by ONE elected lane under a single elect.sync.  Descriptors travel as
+// (lo, hi) 32-bit halves: the k-step only touches the 14-bit start-address field of the low word (no carry: shared
+// memory addresses >> 4 stay below 2^14).  `acc` = 0 only for the very first UMMA of a tile.
+__device__ __forceinline__ void mma_tap_elect(uint32_t tmem_d, uint32_t wlo, uint32_t whi, uint32_t plo, uint32_t phi,
+                                              uint32_t idesc, uint32_t acc, uint32_t w_empty_bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q, p, t;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 la, lb;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u32 la, %1, 2;\n\t"
+      "add.u32 lb, %3, 2;\n\t"
+      "mov.b64 da, {la, %2};\n\t"
+      "mov.b64 db, {lb, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+      "add.u32 la, %1, 4;\n\t"
+      "add.u32 lb, %3, 4;\n\t"
+      "mov.b64 da, {la, %2};\n\t"
+      "mov.b64 db, {lb, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+      "add.u32 la, %1, 6;\n\t"
+      "add.u32 lb, %3, 6;\n\t"
+      "mov.b64 da, {la, %2};\n\t"
+      "mov.b64 db, {lb, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(wlo), "r"(whi), "r"(plo), "r"(phi), "r"(idesc), "r"(acc), "r"(w_empty_bar)
       : "memory");
 }
 __device__ __forceinline__ void commit_elect(uint64_t* bar) {
@@ -158,6 +197,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -217,7 +259,78 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 
   if (warp == 0) {
     // =========================== TMA producer: weights, TMA-fed halo tiles, L2 prefetch of the fused ones ====
-    if (lane == 0) {
+    if (lane == 0 && P.tma_poll && P.fused != 1) {
+      // Two independent cursors over the same (tile, segment, chunk [, tap]) sequence -- activation tiles and weight
+      // tiles -- polled without blocking, activations first.  In program order the activation tile of chunk c+2 comes
+      // after the last weight tile of chunk c+1, which the 6-stage weight ring only admits once the MMA warp is three
+      // taps into chunk c+1; a single ordered loop therefore issues every activation load ~1500 tensor clocks after
+      // its slot was released, which the 2-stage activation ring (load -> [transform] -> MMA) cannot hide.
+      const int nfused = P.fused ? P.seg_chunks[0] : 0;
+      int a_tile = blockIdx.x, a_s = 0, a_ch = 0, sa = 0; uint32_t pa = 0;
+      int w_tile = blockIdx.x, w_s = 0, w_ch = 0, w_tap = 0, sb = 0; uint32_t pb = 0;
+      bool a_done = a_tile >= P.num_tiles, w_done = a_done;
+      auto prefetch_fused = [&](int tile, int i) {   // L2 prefetch of fused chunk i of `tile` (rolling into the CTA's next tile)
+        if (i >= nfused) { i -= nfused; tile += gridDim.x; }
+        if (i >= nfused || tile >= P.num_tiles) return;
+        const int mt = tile / P.n_cblk;
+        const int pn = mt / tiles_per_utt, prem = mt % tiles_per_utt;
+        const int px0 = (prem % P.tiles_w) * TILE_W, py0 = (prem / P.tiles_w) * TILE_H;
+        const int cg = i * 64;
+        if (cg < P.C0) tma_prefetch_4d(&map_a0, cg, px0 - 1, py0 - 1, pn);
+        else tma_prefetch_4d(&map_cat, cg - P.C0, px0 - 1, py0 - 1, pn);
+      };
+      if (!a_done && nfused) prefetch_fused(a_tile, 0);
+      long long t_last = clock64();
+      while (!(a_done && w_done)) {
+        bool progress = false;
+        if (!a_done && mbar_test_wait(&a_empty[sa], pa ^ 1)) {
+          const int m_tile = a_tile / P.n_cblk;
+          const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
+          const int x0 = (rem % P.tiles_w) * TILE_W, y0 = (rem / P.tiles_w) * TILE_H;
+          const CUtensorMap* ma = a_s == 0 ? &map_a0 : (a_s == 1 ? &map_a1 : (a_s == 2 ? &map_a2 : &map_a3));
+          if (P.fused && a_s == 0) {                 // raw tile by TMA, transformed in place by the producer warps
+            const int cg = a_ch * BLOCK_K;
+            mbar_arrive_expect_tx(&a_raw[sa], A_BYTES);
+            if (cg < P.C0) tma_load_4d(smem + sa * A_STRIDE, &map_a0, &a_raw[sa], cg, x0 - 1, y0 - 1, n);
+            else tma_load_4d(smem + sa * A_STRIDE, &map_cat, &a_raw[sa], cg - P.C0, x0 - 1, y0 - 1, n);
+            prefetch_fused(a_tile, a_ch + 1);
+          } else if (P.seg_taps[a_s] == 1) {         // 1x1 segment: only the [32][8]-pixel centre, dense (SBO = 1024)
+            mbar_arrive_expect_tx(&a_full[sa], TILE_PX * 128);
+            tma_load_4d(smem + sa * A_STRIDE, ma, &a_full[sa], a_ch * BLOCK_K, x0, y0, n);
+          } else {
+            mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
+            tma_load_4d(smem + sa * A_STRIDE, ma, &a_full[sa], a_ch * BLOCK_K, x0 - 1, y0 - 1, n);
+          }
+          if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+          if (++a_ch == P.seg_chunks[a_s]) {
+            a_ch = 0;
+            if (++a_s == P.nseg) { a_s = 0; a_tile += gridDim.x; a_done = a_tile >= P.num_tiles; }
+          }
+          progress = true;
+        }
+        if (!w_done && mbar_test_wait(&w_empty[sb], pb ^ 1)) {
+          const int c_blk = w_tile % P.n_cblk;
+          const int kb = P.seg_kb0[w_s] + w_tap * P.seg_chunks[w_s] + w_ch;
+          mbar_arrive_expect_tx(&w_full[sb], W_BYTES);
+          tma_load_2d(smem + L::OFF_W + sb * W_BYTES, &map_w, &w_full[sb], kb * BLOCK_K, c_blk * BLOCK_C);
+          if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+          if (++w_tap == P.seg_taps[w_s]) {
+            w_tap = 0;
+            if (++w_ch == P.seg_chunks[w_s]) {
+              w_ch = 0;
+              if (++w_s == P.nseg) { w_s = 0; w_tile += gridDim.x; w_done = w_tile >= P.num_tiles; }
+            }
+          }
+          progress = true;
+        }
+        if (progress) t_last = clock64();
+        else if (clock64() - t_last > 4000000000LL) {
+          if (P.dbg) atomicExch(P.dbg, a_done ? 150 + sb : 100 + sa);
+          __threadfence_system();
+          asm volatile("trap;");
+        }
+      }
+    } else if (lane == 0) {                          // ordered loop (in fused mode 1 with bystander arrivals)
       int sa = 0; uint32_t pa = 0;
       int sb = 0; uint32_t pb = 0;
       const int nfused = P.fused ? P.seg_chunks[0] : 0;
@@ -254,6 +367,9 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
               if (cg < P.C0) tma_load_4d(smem + sa * A_STRIDE, &map_a0, &a_raw[sa], cg, x0 - 1, y0 - 1, n);
               else tma_load_4d(smem + sa * A_STRIDE, &map_cat, &a_raw[sa], cg - P.C0, x0 - 1, y0 - 1, n);
               prefetch_chunk(ch + 1);
+            } else if (ntap == 1) {                // 1x1 segment: only the [32][8]-pixel centre, dense (SBO = 1024)
+              mbar_arrive_expect_tx(&a_full[sa], TILE_PX * 128);
+              tma_load_4d(smem + sa * A_STRIDE, ma, &a_full[sa], ch * BLOCK_K, x0, y0, n);
             } else {
               mbar_arrive_expect_tx(&a_full[sa], A_BYTES);
               tma_load_4d(smem + sa * A_STRIDE, ma, &a_full[sa], ch * BLOCK_K, x0 - 1, y0 - 1, n);
@@ -285,23 +401,41 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         const int chunks = P.seg_chunks[s];
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(&a_full[sa], pa, P.dbg, 300 + sa);
-          const uint32_t a_base = smem_u32(smem + sa * A_STRIDE);
-          for (int tap = 0; tap < ntap; ++tap) {
+          // descriptor halves (see desc_sw128): lo = start >> 4 | LBO field 1; hi = SBO >> 4 | fixed bit 46 | SWIZZLE_128B
+          const uint32_t plo0 = ((smem_u32(smem + sa * A_STRIDE) >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t phi = (uint32_t)((ntap == 9 ? SBO_BYTES : 1024) >> 4) | (1u << 14) | (2u << 29);
+          constexpr uint32_t whi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+          auto tap_issue = [&](uint32_t off_rows) {    // off_rows: halo pixel (row of 128 B = 8 units) of output pixel (0,0)
             mbar_wait(&w_full[sb], pb, P.dbg, 350 + sb);
             tc_fence_after();
-            // halo pixel of output pixel (0,0) under this tap: (dy, dx) for 3x3, the centre (1, 1) for 1x1
-            const int off = ntap == 9 ? (tap / 3) * HALO_W + tap % 3 : HALO_W + 1;
-            const uint64_t wdesc = desc_sw128(smem_u32(smem + L::OFF_W + sb * W_BYTES), 1024, 0);          // A operand: weights
-            const uint64_t pdesc = desc_sw128(a_base + (uint32_t)(off * 128), SBO_BYTES, P.desc_mode);     // B operand: pixels
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              mma_elect(d_tmem, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), IDESC6, acc);
-              acc = 1;
-            }
-            commit_elect(&w_empty[sb]);
-            if (tap == ntap - 1) commit_elect(&a_empty[sa]);
+            const uint32_t wlo = ((smem_u32(smem + L::OFF_W + sb * W_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
+            mma_tap_elect(d_tmem, wlo, whi, plo0 + off_rows * 8u, phi, IDESC6, acc, smem_u32(&w_empty[sb]));
+            acc = 1;
             if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+          };
+          if (P.mma_style == 1) {                    // first version: one elect.sync per UMMA, descriptors rebuilt per tap
+            const uint32_t a_base = smem_u32(smem + sa * A_STRIDE);
+            for (int tap = 0; tap < ntap; ++tap) {
+              mbar_wait(&w_full[sb], pb, P.dbg, 350 + sb);
+              tc_fence_after();
+              const int off = ntap == 9 ? (tap / 3) * HALO_W + tap % 3 : 0;
+              const uint64_t wdesc = desc_sw128(smem_u32(smem + L::OFF_W + sb * W_BYTES), 1024, 0);
+              const uint64_t pdesc = desc_sw128(a_base + (uint32_t)(off * 128), ntap == 9 ? SBO_BYTES : 1024, P.desc_mode);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                mma_elect(d_tmem, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), IDESC6, acc);
+                acc = 1;
+              }
+              commit_elect(&w_empty[sb]);
+              if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+            }
+          } else if (ntap == 9) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) tap_issue((uint32_t)((tap / 3) * HALO_W + tap % 3));
+          } else {
+            tap_issue(0u);                           // a 1x1 segment's stage holds the dense centre box
           }
+          commit_elect(&a_empty[sa]);
           if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
         }
       }
@@ -315,6 +449,9 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const int ch = lg * 32 + lane;
     const int ch_chunk_off = (ch >> 6) * (GROUP_PX * 128) + (ch & 7) * 2;
     const int ch_c16 = (ch & 63) >> 3;
+    uint32_t offk[8];                              // swizzled 16-B chunk of this channel in staged row p: (ch_c16 ^ (p & 7)) << 4
+#pragma unroll
+    for (int k = 0; k < 8; ++k) offk[k] = (uint32_t)((ch_c16 ^ k) << 4);
     int as = 0; uint32_t as_phase = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const int c_blk = tile % P.n_cblk, m_tile = tile / P.n_cblk;
@@ -340,13 +477,18 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
-        uint8_t* base = buf + ch_chunk_off;
+        // two pixels per conversion; shared-space 16-bit stores with immediate row offsets (no 64-bit address math)
+        const uint32_t sbase = smem_u32(buf) + (uint32_t)ch_chunk_off;
+        const float sc = P.scale, bs = bt * P.scale;
 #pragma unroll
-        for (int p = 0; p < GROUP_PX; ++p) {
-          const __half h = __float2half_rn((__uint_as_float(r[p]) + bt) * P.scale);
-          const float f = __half2float(h);
-          ssum += f; ssq = fmaf(f, f, ssq);
-          *reinterpret_cast<__half*>(base + p * 128 + ((ch_c16 ^ (p & 7)) << 4)) = h;
+        for (int p = 0; p < GROUP_PX; p += 2) {
+          const __half2 h2 = __floats2half2_rn(fmaf(__uint_as_float(r[p]), sc, bs), fmaf(__uint_as_float(r[p + 1]), sc, bs));
+          const float2 f = __half22float2(h2);
+          ssum += f.x; ssq = fmaf(f.x, f.x, ssq);
+          ssum += f.y; ssq = fmaf(f.y, f.y, ssq);
+          const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+          sts16(sbase + p * 128 + offk[p & 7], (uint16_t)(hb & 0xffffu));
+          sts16(sbase + (p + 1) * 128 + offk[(p + 1) & 7], (uint16_t)(hb >> 16));
         }
         fence_proxy_async_smem();
         named_bar_sync(1, NUM_EPI_THREADS);
@@ -560,15 +702,17 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   for (int i = 0; i < a.nseg; ++i) { srcs[nseg] = &a.seg[i].src; taps[nseg++] = a.seg[i].taps; }
   if (a.residual) { srcs[nseg] = a.residual; taps[nseg++] = 1; }
   P.nseg = nseg;
-  // fused producers: 3 = in place, half2 math (default); 2 = in place, fp32 math (variant 9, or no half2 table);
-  // 1 = LDG-fed, fp32 math (variant 8, the first fused version)
-  P.fused = a.gn_ab ? (g_tc_variant == 8 ? 1 : ((g_tc_variant == 9 || !a.gn_ab16) ? 2 : 3)) : 0;
+  // fused producers: 1 = LDG-fed, fp32 math (default: fastest in the interleaved A/B of round 1, profiles/r01_ab_forward.txt);
+  // 2 = TMA-fed raw tile transformed in place, fp32 math (variant 9); 3 = in place, half2 math on the split-mean table
+  // (variant 10)
+  P.fused = a.gn_ab ? ((g_tc_variant == 10 && a.gn_ab16) ? 3 : (g_tc_variant == 9 || g_tc_variant == 10) ? 2 : 1) : 0;
   const TensorDesc* cat = (a.gn_ab && a.gn_has_cat) ? &a.gn_cat : nullptr;
   CUtensorMap ma[MAX_SEG];
   int kb = 0;
   for (int i = 0; i < MAX_SEG; ++i) {
     const TensorDesc& s = *srcs[i < nseg ? i : 0];
-    ma[i] = make_act_map(s.p, s.N, s.H, s.W, s.C, HALO_W, HALO_H, 1);
+    const bool centre = i < nseg && taps[i] == 1;
+    ma[i] = make_act_map(s.p, s.N, s.H, s.W, s.C, centre ? TILE_W : HALO_W, centre ? TILE_H : HALO_H, 1);
     if (i < nseg) {
       const int C = s.C + ((i == 0 && cat) ? cat->C : 0);
       P.seg_chunks[i] = C / 64; P.seg_taps[i] = taps[i]; P.seg_kb0[i] = kb;
@@ -591,6 +735,7 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   P.stats = out.stats; P.slots = out.slots;
   static const int desc_mode = [] { const char* v = getenv("SGMSE_B200_TC6_DESC"); return v ? atoi(v) : 0; }();
   P.desc_mode = desc_mode;
+  P.mma_style = g_tc6_mma_style; P.tma_poll = g_tc6_tma_poll;
   P.dbg = dbg;
   auto kern = conv_tc6_kernel<A_STAGES, B_STAGES>;
   static bool attr_set = false;
@@ -616,6 +761,11 @@ bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out) {
   return a.nseg + (a.residual ? 1 : 0) <= MAX_SEG;
 }
 
+// A/B switches (engine options "tc6_rings", "tc6_mma", "tc6_tma_poll")
+int g_tc6_rings = [] { const char* v = getenv("SGMSE_B200_TC6_RINGS"); return v ? atoi(v) : 0; }();   // 0: 2 activation + 6 weight stages; 1: 3 + 4
+int g_tc6_mma_style = 0;
+int g_tc6_tma_poll = 0;
+
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   if (a.gn_ab) {
     const int nraw = (a.nseg - 1) + (a.residual ? 1 : 0);
@@ -626,8 +776,7 @@ void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* d
   } else {
     SG_CHECK(conv_tc6_supported(a, out), "conv_tc6: unsupported shape");
   }
-  static const int ring_cfg = [] { const char* v = getenv("SGMSE_B200_TC6_RINGS"); return v ? atoi(v) : 0; }();
-  if (ring_cfg == 1) launch6<3, 4>(st, a, out, dbg);
+  if (g_tc6_rings == 1) launch6<3, 4>(st, a, out, dbg);
   else launch6<2, 6>(st, a, out, dbg);
 }
 

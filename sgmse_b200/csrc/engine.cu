@@ -4,6 +4,8 @@
 //
 // Reference call stack replaced: ScoreModel.enhance (model.py:426-465) -> get_pc_sampler
 // (sampling/__init__.py:26-70) -> NCSNpp.forward (backbones/ncsnpp.py:256-419).
+#include <cstring>
+
 #include "engine.h"
 
 #include <math.h>
@@ -289,6 +291,25 @@ void load_weights(Engine& e, const float* blob) {
           for (int tap = 0; tap < 9; ++tap) p[((size_t)tap * C + ci) * 4 + o] = blob[l.conv0_w + ((size_t)o * C + ci) * 9 + tap];
       l.small_w = (float*)upload(e, p.data(), p.size() * 4);
       for (int o = 0; o < 4; ++o) l.out_bias_host[o] = blob[l.conv0_b + o];
+      if (C % 16 == 0) {
+        // B fragments of mma.sync m16n8k16 (k x n = 16 x 8, the 4 outputs in columns 0..3): lane (g, t) holds
+        // b0 = (k = 2t, 2t+1 ; n = g), b1 = (k = 2t+8, 2t+9 ; n = g)
+        const int KS = C / 16;
+        std::vector<uint2> fr((size_t)9 * KS * 32, make_uint2(0u, 0u));
+        auto h2 = [](float lo, float hi) {
+          const __half2 v = __floats2half2_rn(lo, hi);
+          uint32_t u; memcpy(&u, &v, 4); return u;
+        };
+        for (int tap = 0; tap < 9; ++tap)
+          for (int kk = 0; kk < KS; ++kk)
+            for (int ln = 0; ln < 32; ++ln) {
+              const int gg = ln >> 2, tt = ln & 3;
+              if (gg >= 4) continue;
+              const float* wp = &p[((size_t)tap * C + kk * 16 + 2 * tt) * 4 + gg];
+              fr[((size_t)tap * KS + kk) * 32 + ln] = make_uint2(h2(wp[0], wp[4]), h2(wp[32], wp[36]));
+            }
+        l.small_wfrag = (uint2*)upload(e, fr.data(), fr.size() * sizeof(uint2));
+      }
     }
   }
   e.dense_w_stacked = (float*)upload(e, dw.data(), dw.size() * 4);
@@ -401,7 +422,8 @@ struct Fwd {
       ConvArgs a;
       a.nseg = 1; a.seg[0].taps = 9;
       if (fuse0) {
-        a.seg[0].src = x0; a.gn_ab = ab0; a.gn_ab16 = (const uint4*)(ab0 + (size_t)N * Ct);
+        a.seg[0].src = x0; a.gn_ab = ab0;
+        if ((Ct / gn_groups(Ct)) % 2 == 0) a.gn_ab16 = (const uint4*)(ab0 + (size_t)N * Ct);
         if (x1) { a.gn_has_cat = true; a.gn_cat = *x1; }
       } else {
         a.seg[0].src = h0;
@@ -420,7 +442,10 @@ struct Fwd {
     {
       ConvArgs a;
       a.nseg = 1; a.seg[0].taps = 9;
-      if (fuse1) { a.seg[0].src = h1; a.gn_ab = ab1; a.gn_ab16 = (const uint4*)(ab1 + (size_t)N * l.cout); } else { a.seg[0].src = h2; }
+      if (fuse1) {
+        a.seg[0].src = h1; a.gn_ab = ab1;
+        if ((l.cout / gn_groups(l.cout)) % 2 == 0) a.gn_ab16 = (const uint4*)(ab1 + (size_t)N * l.cout);
+      } else { a.seg[0].src = h2; }
       if (l.shortcut) {
         if (rs != RS_NONE) { a.seg[a.nseg].src = xr; a.seg[a.nseg++].taps = 1; }
         else {
@@ -470,13 +495,13 @@ struct Fwd {
     float2* ab = gn(h, nullptr, l.gn0_w, l.gn0_b);
     if (out_conv_fuses_gn(h)) {                    // GroupNorm-apply + SiLU happen while the conv stages its tile
       float4* out = act4(h.N, h.H, h.W);
-      if (!dry) { launch_out_conv(st, h, l.small_w, l.out_bias_host, addend, out, ab); count(); }
+      if (!dry) { launch_out_conv(st, h, l.small_w, l.out_bias_host, addend, out, ab, l.small_wfrag); count(); }
       return out;
     }
     TensorDesc a = act(h.N, h.H, h.W, h.C, false);
     if (!dry) { launch_gn_apply(st, h, nullptr, ab, true, RS_NONE, a, nullptr); count(); }
     float4* out = act4(h.N, h.H, h.W);
-    if (!dry) { launch_out_conv(st, a, l.small_w, l.out_bias_host, addend, out); count(); }
+    if (!dry) { launch_out_conv(st, a, l.small_w, l.out_bias_host, addend, out, nullptr, l.small_wfrag); count(); }
     return out;
   }
 
@@ -1214,6 +1239,9 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
     clear_graphs(*e);
   }
   else if (k == "attn_variant") { sgmse::g_attn_variant = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_rings") { sgmse::g_tc6_rings = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_mma") { sgmse::g_tc6_mma_style = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_tma_poll") { sgmse::g_tc6_tma_poll = (int)value; clear_graphs(*e); }
   else if (k == "fir_variant") { sgmse::g_fir_variant = (int)value; clear_graphs(*e); }
   else if (k == "inconv_variant") { sgmse::g_inconv_variant = (int)value; clear_graphs(*e); }
   else if (k == "outconv_variant") {

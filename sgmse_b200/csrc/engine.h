@@ -46,6 +46,7 @@ struct Layer {
   float* small_w = nullptr;   // LK_COMBINE: [4][C]; LK_OUTCONV: [9C][4]
   float* small_b = nullptr;   // LK_COMBINE: [C] (device)
   float out_bias_host[4] = {0, 0, 0, 0};
+  uint2* small_wfrag = nullptr;   // LK_OUTCONV: mma.sync B fragments [9][C/16][32] of small_w in fp16 (see out_conv_mma_kernel)
 };
 
 struct Arena {

@@ -87,11 +87,12 @@ void launch_conv_tc5(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* d
 bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out);
 bool conv_tc6_fuse_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
-extern int g_tc_variant;   // 0 (= 7): newest applicable kernels (v6 with fused GN where possible, else v4/v1), 1: v1 only,
-                           // 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1), 4: v4 (+v1) without GroupNorm fusion,
-                           // 5: v5 fused GN (+v4), 6: v6 without fusion (+v4), 8: v6 with the first-version fused
-                           // producers (LDG-fed, mode 1), 9: in-place producers with fp32 math (mode 2); the default (0)
-                           // is in place with half2 math (mode 3)
+extern int g_tc6_rings, g_tc6_mma_style, g_tc6_tma_poll;   // conv_tc6 A/B switches, see conv_tc6.cu
+extern int g_tc_variant;   // 0 (= 7, 8): newest applicable kernels (v6 with fused GroupNorm+SiLU where possible: LDG-fed producers,
+                           // fp32 math = fused mode 1; else v4/v1), 1: v1 only, 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1),
+                           // 4: v4 (+v1) without GroupNorm fusion, 5: v5 fused GN (+v4), 6: v6 without fusion (+v4),
+                           // 9: v6 fused, TMA-fed raw tile transformed in place, fp32 math (mode 2),
+                           // 10: the same with half2 math on the split-mean coefficient table (mode 3)
 
 // input layer: state float4 (x.re,x.im,y.re,y.im) -> conv3x3(4->C); w [36][C] (k = tap*4+cin), bias [C]
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
@@ -104,9 +105,11 @@ void launch_fir4(cudaStream_t st, const float4* in, int N, int H, int W, Resampl
 // out4 = conv3x3_{C->4}(act) + bias (+ addend);  w [9*C][4] (device), bias: HOST pointer to 4 floats
 // gn_ab != nullptr: `act` is the RAW tensor and silu(a*x+b) is applied while staging (only when out_conv_fuses_gn(act))
 bool out_conv_fuses_gn(const TensorDesc& act);
+// wfrag (optional): the fp16 mma.sync B fragments of w packed at load time ([9][C/16][32] uint2), else built per block
 void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, const float* bias,
-                     const float4* addend, float4* out, const float2* gn_ab = nullptr);
-extern int g_outconv_variant;   // 0: mma.sync kernel for fp16 C in {128, 256} (fuses GroupNorm+SiLU); 1: CUDA-core kernels
+                     const float4* addend, float4* out, const float2* gn_ab = nullptr, const uint2* wfrag = nullptr);
+extern int g_outconv_variant;   // 0: mma.sync kernel for fp16 C in {128, 256}; 1: CUDA-core kernels; 2: mma.sync kernel with
+                                // GroupNorm+SiLU fused into its staging (measured slower than gn_apply + conv: profiles/)
 extern int g_inconv_variant;    // 0: mma.sync input conv for fp16 C in {32, 64, 128}; 1: CUDA-core kernel
 
 // ---- attention: qkv [N,H,W,3C] (q|k|v), out [N,H,W,C] = softmax(q k^T / sqrt(C)) v over H*W tokens

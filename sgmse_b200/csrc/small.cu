@@ -413,7 +413,7 @@ template <int C>
 __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restrict__ act, int H, int W,
                                                            const float* __restrict__ w, float4 bias,
                                                            const float4* __restrict__ addend, float4* __restrict__ out,
-                                                           const float2* __restrict__ gn_ab) {
+                                                           const float2* __restrict__ gn_ab, const uint2* __restrict__ wfrag_g) {
   constexpr int LD = C + 8;            // halfs per staged pixel (16-byte aligned, conflict-free ldmatrix rows)
   constexpr int KS = C / 16;
   extern __shared__ __align__(16) uint8_t oc_smem[];
@@ -423,6 +423,10 @@ __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restr
   const int g = lane >> 2, t = lane & 3;
   const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16, n = blockIdx.z;
   // B fragments: b0 = (k = 2t, 2t+1 ; n = g), b1 = (k = 2t+8, 2t+9 ; n = g); output columns >= 4 are zero padding
+  if (wfrag_g) {                                   // packed at load time: a plain 128-bit copy
+    const uint4* src = reinterpret_cast<const uint4*>(wfrag_g);
+    for (int i = tid; i < 9 * KS * 16; i += 256) reinterpret_cast<uint4*>(wfrag)[i] = __ldg(src + i);
+  } else
   for (int i = tid; i < 9 * KS * 32; i += 256) {
     const int l = i & 31, blk = i >> 5;
     const int tap = blk / KS, kk = blk % KS, gg = l >> 2, tt = l & 3;
@@ -499,16 +503,16 @@ __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restr
 
 template <int C>
 static void out_conv_mma_launch(cudaStream_t st, const TensorDesc& act, const float* w, float4 b, const float4* addend,
-                                float4* out, const float2* gn_ab) {
+                                float4* out, const float2* gn_ab, const uint2* wfrag) {
   const size_t smem = (size_t)18 * 18 * (C + 8) * 2 + (size_t)9 * (C / 16) * 32 * sizeof(uint2);
   auto k = out_conv_mma_kernel<C>;
   CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(act.W, 16), cdiv(act.H, 16), act.N);
-  k<<<grid, 256, smem, st>>>((const __half*)act.p, act.H, act.W, w, b, addend, out, gn_ab);
+  k<<<grid, 256, smem, st>>>((const __half*)act.p, act.H, act.W, w, b, addend, out, gn_ab, wfrag);
   CUDA_OK(cudaGetLastError());
 }
 
-int g_outconv_variant = 0;   // 0: mma.sync kernel for fp16 C in {128, 256}; 1: CUDA-core kernels
+int g_outconv_variant = 0;   // see kernels.h
 
 template <typename T>
 static void out_conv_dispatch(cudaStream_t st, const TensorDesc& act, const float4* w, float4 b, const float4* addend,
@@ -537,19 +541,19 @@ static void out_conv_dispatch(cudaStream_t st, const TensorDesc& act, const floa
 }
 
 bool out_conv_fuses_gn(const TensorDesc& act) {
-  return act.dt == DT_F16 && g_outconv_variant == 0 && (act.C == 128 || act.C == 256);
+  return act.dt == DT_F16 && g_outconv_variant == 2 && (act.C == 128 || act.C == 256);
 }
 
 void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, const float* bias,
-                     const float4* addend, float4* out, const float2* gn_ab) {
+                     const float4* addend, float4* out, const float2* gn_ab, const uint2* wfrag) {
   SG_CHECK(!gn_ab || out_conv_fuses_gn(act), "out conv: fused GroupNorm is only available in the tensor-core kernel");
   SG_CHECK(act.C % 8 == 0, "out conv: C must be a multiple of 8");
   SG_CHECK((size_t)9 * act.C * sizeof(float4) <= 96 * 1024, "out conv: %d channels exceed the shared-memory weight buffer", act.C);
   // `bias` is a HOST pointer to 4 floats (kept with the layer description)
   const float4 b = make_float4(bias[0], bias[1], bias[2], bias[3]);
-  if (act.dt == DT_F16 && g_outconv_variant == 0 && (act.C == 128 || act.C == 256)) {
-    if (act.C == 128) out_conv_mma_launch<128>(st, act, w, b, addend, out, gn_ab);
-    else out_conv_mma_launch<256>(st, act, w, b, addend, out, gn_ab);
+  if (act.dt == DT_F16 && g_outconv_variant != 1 && (act.C == 128 || act.C == 256)) {
+    if (act.C == 128) out_conv_mma_launch<128>(st, act, w, b, addend, out, gn_ab, wfrag);
+    else out_conv_mma_launch<256>(st, act, w, b, addend, out, gn_ab, wfrag);
     return;
   }
   if (act.dt == DT_F16) out_conv_dispatch<__half>(st, act, (const float4*)w, b, addend, out);

@@ -249,27 +249,33 @@ def test_tc_kernel_variants_agree(full_sd):
     t = torch.tensor([0.7, 0.1]).cuda()
     outs = {}
     # v1 only; v2 (+v1); v3 CTA pairs; v4 swapped operands; 5: v4 + GroupNorm/SiLU fused into the conv (conv_tc5);
-    # 6: halo-tile kernel (conv_tc6) without fusion; 0 = default = conv_tc6 with the fusion
-    # 8: conv_tc6 with the first-version fused producers (LDG-fed, fp32 math); 9: TMA-fed raw tile transformed in place,
-    # fp32 math; 0 = default: in place with half2 math on the split-mean coefficient table
-    for variant in (1, 2, 3, 4, 5, 6, 8, 9, 0):
+    # 6: halo-tile kernel (conv_tc6) without fusion
+    # 9: conv_tc6 fused with the TMA-fed raw tile transformed in place (fp32 math); 10: the same with half2 math on the
+    # split-mean coefficient table; 0 = default = conv_tc6 fused with LDG-fed producers (fp32 math)
+    for variant in (1, 2, 3, 4, 5, 6, 9, 10, 0):
         eng.set_option("tc_variant", variant)
         outs[variant] = eng.dnn_forward(x, t)
         assert eng.counter("direct_convs_last_forward") == 0
         assert torch.isfinite(torch.view_as_real(outs[variant])).all()
-    errs = {v: rel_l2(outs[v], outs[1]) for v in (2, 3, 4, 5, 6, 8, 9, 0)}
+    errs = {v: rel_l2(outs[v], outs[1]) for v in (2, 3, 4, 5, 6, 9, 10, 0)}
     print("tc variants vs v1: " + ", ".join(f"v{v if v else '6-fused'} rel-L2 {e:.3e}" for v, e in errs.items()))
     assert all(e < 5e-3 for e in errs.values())
     # the two fp32-math producers evaluate the same expression on the same values: bit-identical
-    assert torch.equal(outs[8], outs[9])
+    assert torch.equal(outs[0], outs[9])
+    # A/B switches of conv_tc6: ring depths, UMMA issue style, TMA issue loop -- all bit-identical to the default
+    for key, val in (("tc6_rings", 1), ("tc6_mma", 1), ("tc6_tma_poll", 1)):
+        eng.set_option(key, val)
+        assert torch.equal(eng.dnn_forward(x, t), outs[0]), key
+        eng.set_option(key, 0)
     eng.set_option("tc_variant", 0)
     eng.close()
 
 
 def test_small_end_kernel_variants_agree(full_sd):
-    """The mma.sync input conv (state rounded to fp16, K padded 36 -> 48) against the fp32-FMA CUDA-core kernel, and
-    the progressive-output conv with GroupNorm+SiLU fused into its mma.sync staging against gn_apply + the CUDA-core
-    conv with fp32 weights."""
+    """The mma.sync input conv (state rounded to fp16, K padded 36 -> 48) against the fp32-FMA CUDA-core kernel; the
+    progressive-output conv on mma.sync against the CUDA-core kernel with fp32 weights, and with GroupNorm+SiLU fused
+    into its staging (opt-in variant 2: same expression, same rounding point -> bit-identical); the one-MUFU / half2
+    FIR resamplers against the expf / fp32 ones."""
     eng = Engine(EngineConfig(mode="fp16_tc", max_batch=2))
     eng.load_state_dict(full_sd)
     g = torch.Generator().manual_seed(13)
@@ -279,17 +285,23 @@ def test_small_end_kernel_variants_agree(full_sd):
     base = eng.dnn_forward(x, t)
     tap0 = eng.tap("in_conv")
     eng.set_option("outconv_variant", 1)
-    unfused = eng.dnn_forward(x, t)
+    cuda_core = eng.dnn_forward(x, t)
+    eng.set_option("outconv_variant", 2)
+    fused = eng.dnn_forward(x, t)
     eng.set_option("outconv_variant", 0)
-    assert rel_l2(unfused, base) < 2e-3              # CUDA-core fp32-weight conv vs fp16 mma.sync conv
+    assert rel_l2(cuda_core, base) < 2e-3
+    assert torch.equal(fused, base)
     eng.set_option("inconv_variant", 1)
     cc = eng.dnn_forward(x, t)
     tap1 = eng.tap("in_conv")
     eng.set_option("inconv_variant", 0)
     e_in = (torch.linalg.vector_norm(tap0 - tap1) / torch.linalg.vector_norm(tap1)).item()
+    eng.set_option("fir_variant", 1)
+    slow_fir = eng.dnn_forward(x, t)
+    eng.set_option("fir_variant", 0)
     print(f"input conv mma vs CUDA-core: rel-L2 {e_in:.3e}; network output {rel_l2(cc, base):.3e}; "
-          f"out conv fused vs CUDA-core unfused {rel_l2(unfused, base):.3e}")
-    assert e_in < 2e-3 and rel_l2(cc, base) < 5e-3
+          f"out conv mma vs CUDA-core {rel_l2(cuda_core, base):.3e}; FIR fast vs fp32 {rel_l2(slow_fir, base):.3e}")
+    assert e_in < 2e-3 and rel_l2(cc, base) < 5e-3 and rel_l2(slow_fir, base) < 5e-3
     eng.close()
 
 
