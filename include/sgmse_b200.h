@@ -115,6 +115,15 @@ int sgmse_b200_score(sgmse_b200_engine* e, const void* x_t, const void* y, const
 int sgmse_b200_pc_sample(sgmse_b200_engine* e, const void* y, int B, int F, int T, const sgmse_b200_sampler* s,
                          const void* noise, void* out, int* nfe, void* stream);
 int sgmse_b200_noise_draws(const sgmse_b200_sampler* s);
+/* The sampler's host-computed schedule, exactly as the captured launch sequence uses it (host-only; works without a
+ * GPU): ts[N] = torch.linspace(1, t_eps, N) in fp32 (sampling/__init__.py:56), prior_std = OUVESDE._std(1)
+ * (sdes.py:206-229), and one (cy, cs, cz) row per state update in execution order -- per step the corrector steps, then
+ * the predictor: x_mean = x + cy (y - x) + cs * score ; x = x_mean + cz * z  (correctors.py:69-81: cy = 0,
+ * cs = eps = 2 (snr std(t))^2, cz = sqrt(2 eps); predictors.py:60-65 + sdes.py:72-137: cy = -theta dt, cs = G^2,
+ * cz = G = g(t) sqrt(dt)).  The Langevin corrector's data-dependent rows are returned as zeros (filled on the device).
+ * coef: [cap_updates][3] floats; *n_updates receives the number of rows (also when coef is NULL). */
+int sgmse_b200_sampler_schedule(const sgmse_b200_engine* e, const sgmse_b200_sampler* s, float* ts, float* prior_std,
+                                float* coef, int cap_updates, int* n_updates);
 
 /* padded frame count for a waveform of L samples */
 int sgmse_b200_padded_frames(const sgmse_b200_engine* e, int L);

@@ -50,6 +50,7 @@ SYMBOLS = {
     "sgmse_b200_pc_sample": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Sampler), _P, _P,
                                        C.POINTER(C.c_int), _P]),
     "sgmse_b200_noise_draws": (C.c_int, [C.POINTER(Sampler)]),
+    "sgmse_b200_sampler_schedule": (C.c_int, [_P, C.POINTER(Sampler), _P, _P, _P, C.c_int, C.POINTER(C.c_int)]),
     "sgmse_b200_padded_frames": (C.c_int, [_P, C.c_int]),
     "sgmse_b200_analysis": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "sgmse_b200_synthesis": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -1136,6 +1136,32 @@ int sgmse_b200_score(sgmse_b200_engine* e, const void* x_t, const void* y, const
 
 int sgmse_b200_noise_draws(const sgmse_b200_sampler* s) { return s ? noise_draws(*s) : -1; }
 
+int sgmse_b200_sampler_schedule(const sgmse_b200_engine* e, const sgmse_b200_sampler* s, float* ts, float* prior_std,
+                                float* coef, int cap_updates, int* n_updates) {
+  API_BEGIN
+  SG_CHECK(e && s && s->N >= 1, "bad argument");
+  const SamplerTables tb = make_tables(*e, *s);
+  if (ts) for (int i = 0; i < s->N; ++i) ts[i] = tb.ts[i];
+  if (prior_std) {
+    const sgmse_b200_config& c = e->cfg;
+    const double th = c.theta, smin = c.sigma_min, smax = c.sigma_max, ls = log(smax / smin);
+    *prior_std = (float)sqrt(smin * smin * exp(-2 * th) * (exp(2 * (th + ls)) - 1) * ls / (th + ls));
+  }
+  if (n_updates) *n_updates = (int)tb.coef.size();
+  if (coef) {
+    SG_CHECK(cap_updates >= (int)tb.coef.size(), "coef buffer holds %d rows, the schedule has %zu", cap_updates, tb.coef.size());
+    const int ncorr = s->corrector != SGMSE_B200_CORR_NONE ? s->corrector_steps : 0;
+    const int per_step = ncorr + (s->predictor != SGMSE_B200_PRED_NONE ? 1 : 0);
+    for (size_t i = 0; i < tb.coef.size(); ++i) {
+      const bool on_device = s->corrector == SGMSE_B200_CORR_LANGEVIN && per_step > 0 && (int)(i % per_step) < ncorr;
+      coef[3 * i] = on_device ? 0.f : tb.coef[i].cy;
+      coef[3 * i + 1] = on_device ? 0.f : tb.coef[i].cs;
+      coef[3 * i + 2] = on_device ? 0.f : tb.coef[i].cz;
+    }
+  }
+  API_END
+}
+
 int sgmse_b200_pc_sample(sgmse_b200_engine* e, const void* y, int B, int F, int T, const sgmse_b200_sampler* s,
                          const void* noise, void* out, int* nfe, void* stream) {
   API_BEGIN

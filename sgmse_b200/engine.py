@@ -221,6 +221,19 @@ class Engine:
         s = self.sampler_struct(**kw)
         return int(self.lib.sgmse_b200_noise_draws(C.byref(s)))
 
+    def sampler_schedule(self, **kw):
+        """Host-computed schedule of the PC sampler (no GPU needed): ``(ts f32 [N], prior_std, coef f32 [updates, 3])``
+        with rows ``(cy, cs, cz)`` of ``x_mean = x + cy (y - x) + cs score; x = x_mean + cz z`` in execution order."""
+        s = self.sampler_struct(**kw)
+        n = C.c_int(0)
+        _lib.check(self.lib.sgmse_b200_sampler_schedule(self._h, C.byref(s), None, None, None, 0, C.byref(n)))
+        ts = torch.empty(s.N, dtype=torch.float32)
+        coef = torch.empty(n.value, 3, dtype=torch.float32)
+        std = C.c_float(0.0)
+        _lib.check(self.lib.sgmse_b200_sampler_schedule(self._h, C.byref(s), C.c_void_p(ts.data_ptr()), C.byref(std),
+                                                        C.c_void_p(coef.data_ptr()), n.value, C.byref(n)))
+        return ts, float(std.value), coef
+
     def pc_sample(self, y: torch.Tensor, noise: Optional[torch.Tensor] = None, **kw):
         """y c64 [B,1,F,T] -> (sample c64 [B,1,F,T], nfe).  ``noise``: optional c64 [draws,B,1,F,T]."""
         self._use_device()

@@ -78,3 +78,43 @@ def test_enhance_chain_matches_reference_sequence(model16k):
     got = o_pipe.enhance(model16k.dnn.state_dict(), NetConfig.ncsnpp(), o_spec.SpecConfig(), o_sde.OUVE(), wav, draws, N=1)
     assert nfe == 2
     assert ((ref - got[0]).abs().max() / ref.abs().max()).item() < 1e-3
+
+
+@pytest.mark.parametrize("sde_kw,N,snr", [
+    (dict(theta=1.5, sigma_min=0.05, sigma_max=0.5), 30, 0.5),      # config 2 (VoiceBank-DEMAND), model.py:426 defaults
+    (dict(theta=1.5, sigma_min=0.05, sigma_max=0.5), 50, 0.33),     # config 4 (WSJ0-REVERB, README.md:43)
+    (dict(theta=2.0, sigma_min=0.1, sigma_max=1.0), 30, 0.5),       # config 3 (EARS-WHAM 48 kHz, README.md:89)
+])
+def test_sampler_schedule_matches_reference_scalars(sde_kw, N, snr):
+    """Every per-step scalar the captured launch sequence bakes in (engine.cu: make_tables, exported through
+    sgmse_b200_sampler_schedule) against the reference's own objects: OUVESDE._std / .sde / .discretize
+    (sdes.py:188-219,72-89), the step sizes of sampling/__init__.py:56-62, AnnealedLangevinDynamics' step size
+    (correctors.py:69-81) and ReverseDiffusionPredictor (predictors.py:60-65).  Host-only: runs without a GPU."""
+    refshim.import_reference()
+    from sgmse.sdes import OUVESDE
+    from sgmse_b200 import Engine, EngineConfig
+    sde = OUVESDE(N=N, **sde_kw)
+    eng = Engine(EngineConfig(**sde_kw, t_eps=0.03))
+    ts, std1, coef = eng.sampler_schedule(N=N, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=snr)
+    eng.close()
+    ref_ts = torch.linspace(sde.T, 0.03, N)
+    # the engine follows the CUDA linspace kernel the reference runs on a GPU (one rounding per element); the vectorised
+    # CPU kernel rounds twice (base + step * lane) and may differ in the last bit
+    assert torch.allclose(ts, ref_ts, rtol=2.5e-7, atol=0.0)
+    assert abs(std1 - float(sde._std(torch.ones(1)))) < 1e-6 * std1 + 1e-7
+    assert coef.shape == (2 * N, 3)
+    x = torch.zeros(1, 1, 1, 1, dtype=torch.complex64)
+    y = torch.ones(1, 1, 1, 1, dtype=torch.complex64)
+    for i in range(N):
+        # step sizes are differences of neighbouring fp32 time steps (sampling/__init__.py:59-62): a last-bit difference
+        # in the linspace is 3e-6 of dt, so the formulas are checked on the engine's own time steps
+        t = ts[i:i + 1]
+        stepsize = ts[i] - ts[i + 1] if i != N - 1 else ts[-1]
+        std = float(sde._std(t))
+        eps = 2 * (snr * std) ** 2
+        cy, cs, cz = coef[2 * i].tolist()                      # corrector row
+        assert cy == 0.0 and abs(cs - eps) <= 2e-6 * eps and abs(cz - (2 * eps) ** 0.5) <= 2e-6 * (2 * eps) ** 0.5
+        f, G = sde.discretize(x, y, t, stepsize)               # f = theta (y - x) dt with y - x = 1, G = g sqrt(dt)
+        cy, cs, cz = coef[2 * i + 1].tolist()                  # predictor row: x_mean = x - (f - G^2 score)
+        assert abs(cy + float(f.real)) <= 2e-6 * abs(float(f.real))
+        assert abs(cz - float(G)) <= 2e-6 * float(G) and abs(cs - float(G) ** 2) <= 4e-6 * float(G) ** 2
