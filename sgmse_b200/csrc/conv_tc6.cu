@@ -625,22 +625,29 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           v[j] = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y * P.W + x) * Cs));
       }
     };
-    if ((int)blockIdx.x < P.num_tiles) issue_loads(blockIdx.x, 0);
+    // (a, b) of the next chunk are fetched one chunk ahead as well: the producers are this kernel's critical path (the
+    // MMA warp waits on a_full for a quarter of its samples), and an L2 round trip per chunk in front of the
+    // evaluation was 11 % of their time (profiles/r01_conv_tc6_ncu.txt)
+    float4 abn[4];
+    auto load_ab = [&](int tile, int ch) {
+      const int n = (tile / P.n_cblk) / tiles_per_utt;
+      const float4* q = reinterpret_cast<const float4*>(P.ab + (size_t)n * Ct + ch * 64 + cv * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) abn[k] = __ldg(q + k);
+    };
+    if ((int)blockIdx.x < P.num_tiles) { load_ab(blockIdx.x, 0); issue_loads(blockIdx.x, 0); }
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / P.n_cblk;
-      const int n = m_tile / tiles_per_utt, rem = m_tile % tiles_per_utt;
+      const int rem = m_tile % tiles_per_utt;
       const int x0 = (rem % P.tiles_w) * TILE_W, y0 = (rem / P.tiles_w) * TILE_H;
       for (int ch = 0; ch < nfused; ++ch) {
-        const int cg = ch * 64 + cv * 8;
         float a[8], b[8];                          // (a, b)/2: the half argument of the tanh form of silu
-        {
-          const float4* q = reinterpret_cast<const float4*>(P.ab + (size_t)n * Ct + cg);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 w = __ldg(q + k);
-            a[2 * k] = 0.5f * w.x; b[2 * k] = 0.5f * w.y; a[2 * k + 1] = 0.5f * w.z; b[2 * k + 1] = 0.5f * w.w;
-          }
+        for (int k = 0; k < 4; ++k) {
+          a[2 * k] = 0.5f * abn[k].x; b[2 * k] = 0.5f * abn[k].y; a[2 * k + 1] = 0.5f * abn[k].z; b[2 * k + 1] = 0.5f * abn[k].w;
         }
+        if (ch + 1 < nfused) load_ab(tile, ch + 1);
+        else if (tile + (int)gridDim.x < P.num_tiles) load_ab(tile + gridDim.x, 0);
         mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 600 + sa);
         uint8_t* stage = smem + sa * A_STRIDE;
 #pragma unroll
