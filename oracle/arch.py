@@ -17,7 +17,7 @@ from typing import List, Tuple
 
 @dataclass
 class NetConfig:
-    backbone: str = "ncsnpp"            # 'ncsnpp' | 'ncsnpp_48k'
+    backbone: str = "ncsnpp"            # 'ncsnpp' | 'ncsnpp_48k' | 'ncsnpp_v2'
     nf: int = 128
     ch_mult: Tuple[int, ...] = (1, 1, 2, 2, 2, 2, 2)
     num_res_blocks: int = 2
@@ -37,6 +37,14 @@ class NetConfig:
     def ncsnpp_48k(**kw) -> "NetConfig":
         base = dict(backbone="ncsnpp_48k", attn_resolutions=(), progressive="none",
                     progressive_input="none")
+        base.update(kw)
+        return NetConfig(**base)
+
+    @staticmethod
+    def ncsnpp_v2(**kw) -> "NetConfig":
+        """ncsnpp_v2.py:36-395: the same module list as 'ncsnpp' (identical state_dict layout), called as
+        ``dnn(x, y, t)`` and without the in-network ``/t`` (scaling lives in ScoreModel.forward, model.py:283-304)."""
+        base = dict(backbone="ncsnpp_v2", scale_by_sigma=False)
         base.update(kw)
         return NetConfig(**base)
 

@@ -79,6 +79,54 @@ def golden_network(name, backbone, cfg: NetConfig, seed):
     print(name, "params", sum(v.numel() for v in sd.values()))
 
 
+PRECOND = {
+    "plain": dict(loss_type="data_prediction", network_scaling=None, c_in="1", c_out="1", c_skip="0", sigma_data=0.1),
+    "edm": dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1),
+}
+
+
+def golden_v2(name, cfg: NetConfig, seed):
+    """backbone 'ncsnpp_v2' behind ScoreModel.forward's preconditioning (model.py:283-304) with the
+    Schroedinger-bridge SDE and both SB samplers (sampling/__init__.py:145-249), plus the OUVE predictor-corrector
+    sampler driven by a score-matching v2 model.  One set of weights, several ScoreModel wrappers."""
+    kw = dict(nf=cfg.nf, ch_mult=cfg.ch_mult, image_size=cfg.image_size, attn_resolutions=cfg.attn_resolutions,
+              n_fft=126, hop_length=32)
+    base = refshim.make_score_model(backbone="ncsnpp_v2", seed=seed, sde="sbve", k=2.6, c=0.4, N=3, **kw, **PRECOND["plain"])
+    sd = base.dnn.state_dict()
+    assert [k for k, _ in state_dict_manifest(cfg)] == list(sd.keys())
+    g = torch.Generator().manual_seed(seed + 100)
+    B, F, T = 2, 64, 64
+    x = torch.complex(torch.randn(B, 1, F, T, generator=g), torch.randn(B, 1, F, T, generator=g)) * 0.3
+    y = torch.complex(torch.randn(B, 1, F, T, generator=g), torch.randn(B, 1, F, T, generator=g)) * 0.3
+    t = torch.tensor([0.83, 0.11])
+    out = {}
+    with torch.no_grad():
+        out["dnn_out"] = _np(base.dnn(x, y, t))
+        for tag, pre in PRECOND.items():
+            m = refshim.make_score_model(backbone="ncsnpp_v2", seed=seed, sde="sbve", k=2.6, c=0.4, N=3, **kw, **pre)
+            m.dnn.load_state_dict(sd)
+            out[f"fwd_{tag}"] = _np(m(x, y, t))
+            for st in ("sde", "ode"):
+                draws = sde_mod.make_noise((B, 1, F, T), 3, seed=13)
+                with refshim.injected_noise(draws):
+                    smp, n = m.get_sb_sampler(m.sde, y, sampler_type=st)()
+                out[f"sb_{st}_{tag}"] = _np(smp)
+                out[f"sb_n_{st}_{tag}"] = np.int64(n)
+        # OUVE + PC sampler on a score-matching v2 model (c_skip = 0, c_out = 1/sigma, network output unscaled)
+        pre = dict(loss_type="score_matching", network_scaling=None, c_in="1", c_out="1/sigma", c_skip="0", sigma_data=0.1)
+        m = refshim.make_score_model(backbone="ncsnpp_v2", seed=seed, **kw, **pre)
+        m.dnn.load_state_dict(sd)
+        out["fwd_ouve_score"] = _np(m(x, y, t))
+        N = 3
+        draws = sde_mod.make_noise((B, 1, F, T), sde_mod.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=7)
+        with refshim.injected_noise(draws):
+            smp, nfe = m.get_pc_sampler("reverse_diffusion", "ald", y, N=N, corrector_steps=1, snr=0.5)()
+        out["pc_ouve_score"] = _np(smp)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **{"w/" + k: _np(v) for k, v in sd.items()},
+                        x=_np(x), y=_np(y), t=_np(t), **out)
+    print(name, "params", sum(v.numel() for v in sd.values()))
+
+
 def golden_ops():
     """Op-level outputs of the reference layer library (FIR resamplers, STFT chain)."""
     refshim.import_reference()
@@ -107,6 +155,7 @@ def main():
     golden_ops()
     golden_network("ncsnpp_small", "ncsnpp", NetConfig.ncsnpp(attn_resolutions=(16,), **SMALL), seed=1)
     golden_network("ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
+    golden_v2("ncsnpp_v2_small", NetConfig.ncsnpp_v2(attn_resolutions=(16,), **SMALL), seed=3)
 
 
 if __name__ == "__main__":

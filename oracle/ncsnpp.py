@@ -214,3 +214,48 @@ def forward(sd: Dict[str, torch.Tensor], cfg: NetConfig, x: torch.Tensor, t: tor
 def score(sd, cfg: NetConfig, x_t, y, t, dtype=torch.float32):
     """ScoreModel.forward, legacy branch (model.py:307-310): -dnn(cat[x_t, y], t)."""
     return -forward(sd, cfg, torch.cat([x_t, y], dim=1), t, dtype=dtype)
+
+
+# ---- ncsnpp_v2 + preconditioned forward (SURVEY.md §8f-1) -----------------------------------------------------
+def forward_v2(sd, cfg: NetConfig, x, y, t, dtype=torch.float32):
+    """NCSNpp_v2.forward(x, y, t) (ncsnpp_v2.py:241-395): the ncsnpp network on cat[x, y] without the ``/t``."""
+    assert cfg.backbone == "ncsnpp_v2" and not cfg.scale_by_sigma
+    return forward(sd, cfg, torch.cat([x, y], dim=1), t, dtype=dtype)
+
+
+def precond_forward(sd, cfg: NetConfig, pre, std_fn, x_t, y, t, dtype=torch.float32):
+    """ScoreModel.forward for backbone == 'ncsnpp_v2' (model.py:283-304).
+
+    ``pre``: dict(loss_type, network_scaling, c_in, c_out, c_skip, sigma_data) -- the ScoreModel attributes of the same
+    names (model.py:52-60); ``std_fn(t: Tensor[B]) -> Tensor[B]`` = ``sde._std``."""
+    sig = std_fn(t).to(dtype)
+    v = lambda a: a.view(-1, 1, 1, 1)
+    sd2 = pre.get("sigma_data", 0.1) ** 2
+
+    def c_in():                                           # model.py:312-319
+        return 1.0 if pre["c_in"] == "1" else v(1.0 / torch.sqrt(sig ** 2 + sd2))
+
+    def c_out():                                          # model.py:321-332
+        k = pre["c_out"]
+        if k == "1":
+            return 1.0
+        if k == "sigma":
+            return v(sig)
+        if k == "1/sigma":
+            return v(1.0 / sig)
+        return v(sig * pre["sigma_data"] / torch.sqrt(sd2 + sig ** 2))
+
+    def c_skip():                                         # model.py:334-341
+        return 0.0 if pre["c_skip"] == "0" else v(sd2 / (sig ** 2 + sd2))
+
+    Fo = forward_v2(sd, cfg, c_in() * x_t, c_in() * y, t, dtype=dtype)
+    if pre.get("network_scaling") == "1/sigma":
+        Fo = Fo / v(sig)
+    elif pre.get("network_scaling") == "1/t":
+        Fo = Fo / v(t.to(dtype))
+    lt = pre["loss_type"]
+    if lt in ("score_matching", "data_prediction"):
+        return c_skip() * x_t + c_out() * Fo
+    if lt == "denoiser":
+        return (Fo - x_t) / v(sig) ** 2
+    raise ValueError(lt)

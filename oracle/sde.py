@@ -129,3 +129,70 @@ def pc_sample(score_fn: Callable, y: torch.Tensor, sde: OUVE, N: int = 30, eps: 
             raise ValueError(f"Predictor with name '{predictor}' unknown.")
     nfe = N * ((corrector_steps if corrector != "none" else 0) + 1)
     return (xt_mean if denoise else xt), nfe
+
+
+# ---- Schroedinger bridge ---------------------------------------------------------------------
+@dataclass
+class SBVE:
+    """SBVESDE (sdes.py:235-312).  ``eps`` is the stabiliser of ``_sigmas_alphas`` (1e-8), not the end time.  All
+    scalars are evaluated on fp32 tensors like the reference does."""
+    k: float = 2.6
+    c: float = 0.4
+    eps: float = 1e-8
+    T: float = 1.0
+
+    def sigmas_alphas(self, t: torch.Tensor):
+        # sdes.py:276-287
+        alpha_t = torch.ones_like(t)
+        alpha_T = torch.ones_like(t)
+        logk2 = 2 * torch.log(torch.tensor(self.k))
+        sigma_t = torch.sqrt((self.c * (self.k ** (2 * t) - 1.0)) / logk2)
+        sigma_T = torch.sqrt((self.c * (self.k ** (2 * self.T) - 1.0)) / logk2)
+        alpha_bart = alpha_t / (alpha_T + self.eps)
+        sigma_bart = torch.sqrt(sigma_T ** 2 - sigma_t ** 2 + self.eps)
+        return sigma_t, sigma_T, sigma_bart, alpha_t, alpha_T, alpha_bart
+
+    def std(self, t: torch.Tensor):
+        # sdes.py:298-302
+        sigma_t, sigma_T, sigma_bart, alpha_t, _, _ = self.sigmas_alphas(t)
+        return (alpha_t * sigma_bart * sigma_t) / (sigma_T + self.eps)
+
+
+def sb_sample(model_fn: Callable, y: torch.Tensor, sde: SBVE, N: int = 50, eps: float = 1e-4, sampler_type: str = "ode",
+              noise: Optional[List[torch.Tensor]] = None, n_steps: int = 50):
+    """get_sb_sampler() of sampling/__init__.py:145-249.  ``model_fn(x_t, y, t_vec) -> current estimate`` (the
+    data-prediction output of ScoreModel.forward).  The SDE variant draws one complex normal per step (also in the
+    last one, where its weight is zeroed, sampling/__init__.py:176-179); ``noise`` is consumed in that order.
+    Returns ``(x, n_steps)`` -- the reference reports its ``n_steps`` argument, not the number of evaluations."""
+    B = y.shape[0]
+    xt = y[:, [0]] if sampler_type == "sde" else y
+    ts = torch.linspace(sde.T, eps, N + 1)
+    it = iter(noise) if noise is not None else None
+    time_prev = ts[0] * torch.ones(B)
+    sigma_prev, sigma_T, sigma_bar_prev, alpha_prev, alpha_T, _ = sde.sigmas_alphas(time_prev)
+    v = lambda a: a[:, None, None, None]
+    for t in ts[1:]:
+        time = t * torch.ones(B)
+        sigma_t, sigma_T, sigma_bart, alpha_t, alpha_T, _ = sde.sigmas_alphas(time)
+        est = model_fn(xt, y, time)
+        if sampler_type == "sde":
+            w_prev = alpha_t * sigma_t ** 2 / (alpha_prev * sigma_prev ** 2 + sde.eps)
+            tmp = 1 - sigma_t ** 2 / (sigma_prev ** 2 + sde.eps)
+            w_est = alpha_t * tmp
+            w_z = alpha_t * sigma_t * torch.sqrt(tmp)
+            if it is None:
+                raise ValueError("oracle sampler requires injected noise")
+            z = next(it)
+            if t == ts[-1]:
+                xt = v(w_prev) * xt + v(w_est) * est
+            else:
+                xt = v(w_prev) * xt + v(w_est) * est + v(w_z) * z
+        elif sampler_type == "ode":
+            w_prev = alpha_t * sigma_t * sigma_bart / (alpha_prev * sigma_prev * sigma_bar_prev + sde.eps)
+            w_est = alpha_t / (sigma_T ** 2 + sde.eps) * (sigma_bart ** 2 - sigma_bar_prev * sigma_t * sigma_bart / (sigma_prev + sde.eps))
+            w_y = alpha_t / (alpha_T * sigma_T ** 2 + sde.eps) * (sigma_t ** 2 - sigma_prev * sigma_t * sigma_bart / (sigma_bar_prev + sde.eps))
+            xt = v(w_prev) * xt + v(w_est) * est + v(w_y) * y
+        else:
+            raise ValueError("Invalid type. Choose 'ode' or 'sde'.")
+        alpha_prev, sigma_prev, sigma_bar_prev = alpha_t, sigma_t, sigma_bart
+    return xt, n_steps

@@ -93,3 +93,52 @@ def test_fir_and_stft_ops(golden_dir):
     assert _rel(S48, z["stft48"]) < 1e-5
     assert _rel(spec_mod.spec_fwd(S48, s48), z["spec_fwd48"]) < 1e-5
     assert _rel(spec_mod.istft(torch.from_numpy(z["stft48"]), s48, 6000), z["istft48"]) < 1e-5
+
+
+# ---- ncsnpp_v2 + preconditioned forward + Schroedinger-bridge samplers ----
+V2_CFG = NetConfig.ncsnpp_v2(attn_resolutions=(16,), **SMALL)
+PRECOND = {
+    "plain": dict(loss_type="data_prediction", network_scaling=None, c_in="1", c_out="1", c_skip="0", sigma_data=0.1),
+    "edm": dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1),
+}
+
+
+def test_v2_forward_and_preconditioning(golden_dir):
+    z, sd = _load(golden_dir, "ncsnpp_v2_small")
+    assert [k for k, _ in state_dict_manifest(V2_CFG)] == list(sd.keys())
+    x, y, t = (torch.from_numpy(z[k]) for k in ("x", "y", "t"))
+    sb = sde_mod.SBVE(2.6, 0.4)
+    assert _rel(ncsnpp.forward_v2(sd, V2_CFG, x, y, t), z["dnn_out"]) < 1e-5
+    for tag, pre in PRECOND.items():
+        assert _rel(ncsnpp.precond_forward(sd, V2_CFG, pre, sb.std, x, y, t), z[f"fwd_{tag}"]) < 1e-5
+    ou = sde_mod.OUVE()
+    pre = dict(loss_type="score_matching", network_scaling=None, c_in="1", c_out="1/sigma", c_skip="0", sigma_data=0.1)
+    std = lambda tt: torch.tensor([ou.std(float(v)) for v in tt])
+    assert _rel(ncsnpp.precond_forward(sd, V2_CFG, pre, std, x, y, t), z["fwd_ouve_score"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag", list(PRECOND))
+@pytest.mark.parametrize("sampler_type", ["sde", "ode"])
+def test_v2_sb_sampler(golden_dir, tag, sampler_type):
+    z, sd = _load(golden_dir, "ncsnpp_v2_small")
+    y = torch.from_numpy(z["y"])
+    sb = sde_mod.SBVE(2.6, 0.4)
+    draws = sde_mod.make_noise(tuple(y.shape), 3, seed=13)
+    fn = lambda a, b, c: ncsnpp.precond_forward(sd, V2_CFG, PRECOND[tag], sb.std, a, b, c)
+    with torch.no_grad():
+        got, n = sde_mod.sb_sample(fn, y, sb, N=3, sampler_type=sampler_type, noise=draws)
+    assert n == int(z[f"sb_n_{sampler_type}_{tag}"])
+    assert _rel(got, z[f"sb_{sampler_type}_{tag}"]) < 1e-4
+
+
+def test_v2_pc_sampler_on_ouve(golden_dir):
+    z, sd = _load(golden_dir, "ncsnpp_v2_small")
+    y = torch.from_numpy(z["y"])
+    ou = sde_mod.OUVE()
+    pre = dict(loss_type="score_matching", network_scaling=None, c_in="1", c_out="1/sigma", c_skip="0", sigma_data=0.1)
+    std = lambda tt: torch.tensor([ou.std(float(v)) for v in tt])
+    fn = lambda a, b, c: ncsnpp.precond_forward(sd, V2_CFG, pre, std, a, b, c)
+    draws = sde_mod.make_noise(tuple(y.shape), sde_mod.n_noise_draws(3, "reverse_diffusion", "ald", 1), seed=7)
+    with torch.no_grad():
+        got, nfe = sde_mod.pc_sample(fn, y, ou, N=3, noise=draws)
+    assert nfe == 6 and _rel(got, z["pc_ouve_score"]) < 1e-4
