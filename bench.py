@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=16)
     ap.add_argument("--N", type=int, default=30)
     ap.add_argument("--mode", default="fp16_tc")
-    ap.add_argument("--lanes", type=int, default=2, help="concurrent launch sequences inside the sampler graph")
+    ap.add_argument("--lanes", type=int, default=1, help="concurrent launch sequences inside the sampler graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
