@@ -15,9 +15,14 @@
  *   sgmse_b200_dnn_forward           NCSNpp.forward / NCSNpp_48k.forward   sgmse/backbones/ncsnpp.py:256-419,
  *                                    ncsnpp_48k.py:259-424 (incl. upfirdn2d, op/upfirdn2d.py:148-159)
  *   sgmse_b200_score                 ScoreModel.forward (legacy branch)    sgmse/model.py:307-310
+ *   sgmse_b200_model_forward         ScoreModel.forward, all branches      sgmse/model.py:261-341 (preconditioned
+ *                                    'ncsnpp_v2' branch :283-304 incl. _c_in/_c_out/_c_skip)
  *   sgmse_b200_pc_sample             sampling.get_pc_sampler()/pc_sampler  sgmse/sampling/__init__.py:26-70,
  *                                    predictors.py:41-76, correctors.py:37-94, sdes.py:72-137,188-229,
- *                                    ScoreModel.get_pc_sampler (minibatch loop) sgmse/model.py:348-368
+ *                                    ScoreModel.get_pc_sampler (minibatch loop) sgmse/model.py:348-368;
+ *                                    with sampler.kind = SB_ODE / SB_SDE: sampling.get_sb_sampler()
+ *                                    sgmse/sampling/__init__.py:145-249, SBVESDE sdes.py:235-312,
+ *                                    ScoreModel.get_sb_sampler model.py:392-397
  *   sgmse_b200_analysis              _stft + _forward_transform + pad_spec sgmse/data_module.py:162-175,212-214,
  *                                    sgmse/util/other.py:76-90, model.py:435-438
  *   sgmse_b200_synthesis             to_audio (spec_back + istft) + renorm sgmse/data_module.py:177-188,216-218,
@@ -40,7 +45,7 @@ extern "C" {
 
 typedef struct sgmse_b200_engine sgmse_b200_engine;
 
-enum { SGMSE_B200_BACKBONE_NCSNPP = 0, SGMSE_B200_BACKBONE_NCSNPP_48K = 1 };
+enum { SGMSE_B200_BACKBONE_NCSNPP = 0, SGMSE_B200_BACKBONE_NCSNPP_48K = 1, SGMSE_B200_BACKBONE_NCSNPP_V2 = 2 };
 /* arithmetic mode: 0 = fp32 activations, CUDA-core convolutions (validation);
  *                  1 = fp16 activations, CUDA-core convolutions (debug);
  *                  2 = fp16 activations, tcgen05 tensor-core convolutions (product path) */
@@ -48,6 +53,16 @@ enum { SGMSE_B200_MODE_FP32 = 0, SGMSE_B200_MODE_FP16_DIRECT = 1, SGMSE_B200_MOD
 enum { SGMSE_B200_PRED_REVERSE_DIFFUSION = 0, SGMSE_B200_PRED_EULER_MARUYAMA = 1, SGMSE_B200_PRED_NONE = 2 };
 enum { SGMSE_B200_CORR_ALD = 0, SGMSE_B200_CORR_LANGEVIN = 1, SGMSE_B200_CORR_NONE = 2 };
 enum { SGMSE_B200_PAD_ZERO = 0, SGMSE_B200_PAD_REFLECTION = 1 };
+/* SDE (sdes.py:144 'ouve', :235 'sbve') and the preconditioning of ScoreModel.forward for backbone 'ncsnpp_v2'
+ * (model.py:283-341) */
+enum { SGMSE_B200_SDE_OUVE = 0, SGMSE_B200_SDE_SBVE = 1 };
+enum { SGMSE_B200_LOSS_SCORE_MATCHING = 0, SGMSE_B200_LOSS_DENOISER = 1, SGMSE_B200_LOSS_DATA_PREDICTION = 2 };
+enum { SGMSE_B200_NETSCALE_NONE = 0, SGMSE_B200_NETSCALE_INV_SIGMA = 1, SGMSE_B200_NETSCALE_INV_T = 2 };
+enum { SGMSE_B200_CIN_ONE = 0, SGMSE_B200_CIN_EDM = 1 };
+enum { SGMSE_B200_COUT_ONE = 0, SGMSE_B200_COUT_SIGMA = 1, SGMSE_B200_COUT_INV_SIGMA = 2, SGMSE_B200_COUT_EDM = 3 };
+enum { SGMSE_B200_CSKIP_ZERO = 0, SGMSE_B200_CSKIP_EDM = 1 };
+/* sampler kind: predictor-corrector (sampling/__init__.py:26-70) or the Schroedinger-bridge samplers (:145-249) */
+enum { SGMSE_B200_SAMPLER_PC = 0, SGMSE_B200_SAMPLER_SB_ODE = 1, SGMSE_B200_SAMPLER_SB_SDE = 2 };
 
 typedef struct sgmse_b200_config {
   /* backbone (kwargs of NCSNpp.__init__, ncsnpp.py:50-74) */
@@ -72,6 +87,12 @@ typedef struct sgmse_b200_config {
   int mode;                  /* SGMSE_B200_MODE_* */
   int max_batch;             /* utterances processed together (micro-batch); larger batches are looped */
   int use_graphs;            /* capture the N-step sampler loop as one CUDA graph */
+  /* SDE kind + SBVESDE parameters (sdes.py:246-263) */
+  int sde_kind;              /* SGMSE_B200_SDE_* */
+  float sb_k, sb_c, sb_eps;  /* 2.6, 0.4, 1e-8 */
+  /* ScoreModel attributes used by the 'ncsnpp_v2' branch of forward (model.py:52-60); ignored by the other backbones */
+  int loss_type, network_scaling, c_in, c_out, c_skip;
+  float sigma_data;          /* 0.1 */
 } sgmse_b200_config;
 
 typedef struct sgmse_b200_sampler {
@@ -85,6 +106,9 @@ typedef struct sgmse_b200_sampler {
   unsigned long long seed;   /* Philox seed (ignored with injected noise) */
   int utt_offset;            /* global index of utterance 0 (noise is keyed by global utterance id) */
   int pad_mode;              /* SGMSE_B200_PAD_* (enhance/analysis only) */
+  int kind;                  /* SGMSE_B200_SAMPLER_*; the SB kinds use N, seed, utt_offset and the two fields below */
+  float sb_eps;              /* end time of the SB samplers (1e-4, sampling/__init__.py:145) */
+  int sb_n_steps;            /* value the SB samplers report as their second return value (50) */
 } sgmse_b200_sampler;
 
 const char* sgmse_b200_last_error(void);
@@ -115,13 +139,20 @@ int sgmse_b200_score(sgmse_b200_engine* e, const void* x_t, const void* y, const
 int sgmse_b200_pc_sample(sgmse_b200_engine* e, const void* y, int B, int F, int T, const sgmse_b200_sampler* s,
                          const void* noise, void* out, int* nfe, void* stream);
 int sgmse_b200_noise_draws(const sgmse_b200_sampler* s);
+/* ScoreModel.forward(x_t, y, t) for the configured backbone: the legacy branch returns the score -dnn(cat[x_t, y], t);
+ * the 'ncsnpp_v2' branch applies c_in / network_scaling / c_skip / c_out and returns the score (score_matching,
+ * denoiser) or the data prediction, exactly as model.py:283-304.  x_t, y, out: c64 [B,1,F,T] (device), t: f32 [B]. */
+int sgmse_b200_model_forward(sgmse_b200_engine* e, const void* x_t, const void* y, const float* t, void* out, int B,
+                             int F, int T, void* stream);
 /* The sampler's host-computed schedule, exactly as the captured launch sequence uses it (host-only; works without a
  * GPU): ts[N] = torch.linspace(1, t_eps, N) in fp32 (sampling/__init__.py:56), prior_std = OUVESDE._std(1)
  * (sdes.py:206-229), and one (cy, cs, cz) row per state update in execution order -- per step the corrector steps, then
  * the predictor: x_mean = x + cy (y - x) + cs * score ; x = x_mean + cz * z  (correctors.py:69-81: cy = 0,
  * cs = eps = 2 (snr std(t))^2, cz = sqrt(2 eps); predictors.py:60-65 + sdes.py:72-137: cy = -theta dt, cs = G^2,
  * cz = G = g(t) sqrt(dt)).  The Langevin corrector's data-dependent rows are returned as zeros (filled on the device).
- * coef: [cap_updates][3] floats; *n_updates receives the number of rows (also when coef is NULL). */
+ * coef: [cap_updates][3] floats; *n_updates receives the number of rows (also when coef is NULL).
+ * SB kinds: ts[N] = torch.linspace(1, sb_eps, N+1)[1:], prior_std = 0 and one row per step
+ * (weight_prev, weight_estimate, weight_z | weight_prior_mean) of sampling/__init__.py:165-179 / :211-231. */
 int sgmse_b200_sampler_schedule(const sgmse_b200_engine* e, const sgmse_b200_sampler* s, float* ts, float* prior_std,
                                 float* coef, int cap_updates, int* n_updates);
 

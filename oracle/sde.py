@@ -158,6 +158,34 @@ class SBVE:
         return (alpha_t * sigma_bart * sigma_t) / (sigma_T + self.eps)
 
 
+def sb_weights(sde: SBVE, N: int, eps: float, sampler_type: str):
+    """Per-step time and weights of the SB samplers, evaluated on fp32 tensors exactly as sampling/__init__.py:152-179
+    (sde: weight_prev, weight_estimate, weight_z -- zero in the last step) and :195-231 (ode: weight_prev, weight_estimate,
+    weight_prior_mean).  Returns ``(ts f32 [N], rows f32 [N, 3])``."""
+    ts = torch.linspace(sde.T, eps, N + 1)
+    one = torch.ones(1)
+    sigma_prev, sigma_T, sigma_bar_prev, alpha_prev, alpha_T, _ = sde.sigmas_alphas(ts[0] * one)
+    rows = []
+    for t in ts[1:]:
+        sigma_t, sigma_T, sigma_bart, alpha_t, alpha_T, _ = sde.sigmas_alphas(t * one)
+        if sampler_type == "sde":
+            w_prev = alpha_t * sigma_t ** 2 / (alpha_prev * sigma_prev ** 2 + sde.eps)
+            tmp = 1 - sigma_t ** 2 / (sigma_prev ** 2 + sde.eps)
+            w_est = alpha_t * tmp
+            w_3 = alpha_t * sigma_t * torch.sqrt(tmp)
+            if t == ts[-1]:
+                w_3 = torch.zeros(1)
+        elif sampler_type == "ode":
+            w_prev = alpha_t * sigma_t * sigma_bart / (alpha_prev * sigma_prev * sigma_bar_prev + sde.eps)
+            w_est = alpha_t / (sigma_T ** 2 + sde.eps) * (sigma_bart ** 2 - sigma_bar_prev * sigma_t * sigma_bart / (sigma_prev + sde.eps))
+            w_3 = alpha_t / (alpha_T * sigma_T ** 2 + sde.eps) * (sigma_t ** 2 - sigma_prev * sigma_t * sigma_bart / (sigma_bar_prev + sde.eps))
+        else:
+            raise ValueError("Invalid type. Choose 'ode' or 'sde'.")
+        rows.append(torch.cat([w_prev, w_est, w_3]))
+        alpha_prev, sigma_prev, sigma_bar_prev = alpha_t, sigma_t, sigma_bart
+    return ts[1:].clone(), torch.stack(rows)
+
+
 def sb_sample(model_fn: Callable, y: torch.Tensor, sde: SBVE, N: int = 50, eps: float = 1e-4, sampler_type: str = "ode",
               noise: Optional[List[torch.Tensor]] = None, n_steps: int = 50):
     """get_sb_sampler() of sampling/__init__.py:145-249.  ``model_fn(x_t, y, t_vec) -> current estimate`` (the
@@ -166,33 +194,15 @@ def sb_sample(model_fn: Callable, y: torch.Tensor, sde: SBVE, N: int = 50, eps: 
     Returns ``(x, n_steps)`` -- the reference reports its ``n_steps`` argument, not the number of evaluations."""
     B = y.shape[0]
     xt = y[:, [0]] if sampler_type == "sde" else y
-    ts = torch.linspace(sde.T, eps, N + 1)
+    ts, rows = sb_weights(sde, N, eps, sampler_type)
     it = iter(noise) if noise is not None else None
-    time_prev = ts[0] * torch.ones(B)
-    sigma_prev, sigma_T, sigma_bar_prev, alpha_prev, alpha_T, _ = sde.sigmas_alphas(time_prev)
-    v = lambda a: a[:, None, None, None]
-    for t in ts[1:]:
-        time = t * torch.ones(B)
-        sigma_t, sigma_T, sigma_bart, alpha_t, alpha_T, _ = sde.sigmas_alphas(time)
-        est = model_fn(xt, y, time)
+    for t, (w_prev, w_est, w_3) in zip(ts, rows):
+        est = model_fn(xt, y, t * torch.ones(B))
         if sampler_type == "sde":
-            w_prev = alpha_t * sigma_t ** 2 / (alpha_prev * sigma_prev ** 2 + sde.eps)
-            tmp = 1 - sigma_t ** 2 / (sigma_prev ** 2 + sde.eps)
-            w_est = alpha_t * tmp
-            w_z = alpha_t * sigma_t * torch.sqrt(tmp)
             if it is None:
                 raise ValueError("oracle sampler requires injected noise")
             z = next(it)
-            if t == ts[-1]:
-                xt = v(w_prev) * xt + v(w_est) * est
-            else:
-                xt = v(w_prev) * xt + v(w_est) * est + v(w_z) * z
-        elif sampler_type == "ode":
-            w_prev = alpha_t * sigma_t * sigma_bart / (alpha_prev * sigma_prev * sigma_bar_prev + sde.eps)
-            w_est = alpha_t / (sigma_T ** 2 + sde.eps) * (sigma_bart ** 2 - sigma_bar_prev * sigma_t * sigma_bart / (sigma_prev + sde.eps))
-            w_y = alpha_t / (alpha_T * sigma_T ** 2 + sde.eps) * (sigma_t ** 2 - sigma_prev * sigma_t * sigma_bart / (sigma_bar_prev + sde.eps))
-            xt = v(w_prev) * xt + v(w_est) * est + v(w_y) * y
+            xt = w_prev * xt + w_est * est + (w_3 * z if float(w_3) != 0.0 else 0.0)
         else:
-            raise ValueError("Invalid type. Choose 'ode' or 'sde'.")
-        alpha_prev, sigma_prev, sigma_bar_prev = alpha_t, sigma_t, sigma_bart
+            xt = w_prev * xt + w_est * est + w_3 * y
     return xt, n_steps

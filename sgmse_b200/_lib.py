@@ -22,6 +22,9 @@ class Config(C.Structure):
         ("n_fft", C.c_int), ("hop_length", C.c_int), ("sqrt_window", C.c_int),
         ("spec_factor", C.c_float), ("spec_abs_exponent", C.c_float), ("sample_rate", C.c_int),
         ("mode", C.c_int), ("max_batch", C.c_int), ("use_graphs", C.c_int),
+        ("sde_kind", C.c_int), ("sb_k", C.c_float), ("sb_c", C.c_float), ("sb_eps", C.c_float),
+        ("loss_type", C.c_int), ("network_scaling", C.c_int), ("c_in", C.c_int), ("c_out", C.c_int), ("c_skip", C.c_int),
+        ("sigma_data", C.c_float),
     ]
 
 
@@ -30,6 +33,7 @@ class Sampler(C.Structure):
         ("N", C.c_int), ("predictor", C.c_int), ("corrector", C.c_int), ("corrector_steps", C.c_int),
         ("snr", C.c_float), ("denoise", C.c_int), ("probability_flow", C.c_int),
         ("seed", C.c_ulonglong), ("utt_offset", C.c_int), ("pad_mode", C.c_int),
+        ("kind", C.c_int), ("sb_eps", C.c_float), ("sb_n_steps", C.c_int),
     ]
 
 
@@ -50,6 +54,7 @@ SYMBOLS = {
     "sgmse_b200_pc_sample": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Sampler), _P, _P,
                                        C.POINTER(C.c_int), _P]),
     "sgmse_b200_noise_draws": (C.c_int, [C.POINTER(Sampler)]),
+    "sgmse_b200_model_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "sgmse_b200_sampler_schedule": (C.c_int, [_P, C.POINTER(Sampler), _P, _P, _P, C.c_int, C.POINTER(C.c_int)]),
     "sgmse_b200_padded_frames": (C.c_int, [_P, C.c_int]),
     "sgmse_b200_analysis": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

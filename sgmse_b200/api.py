@@ -31,8 +31,8 @@ def config_from_score_model(model, mode="fp16_tc", max_batch=8, use_graphs=True)
     """Read every hyper-parameter of the hot path from a live ScoreModel."""
     dnn = model.dnn
     backbone = getattr(model, "backbone", None) or type(dnn).__name__.lower()
-    if backbone not in ("ncsnpp", "ncsnpp_48k"):
-        raise NotImplementedError(f"sgmse_b200 accelerates the 'ncsnpp' and 'ncsnpp_48k' backbones, not '{backbone}'")
+    if backbone not in ("ncsnpp", "ncsnpp_48k", "ncsnpp_v2"):
+        raise NotImplementedError(f"sgmse_b200 accelerates the 'ncsnpp', 'ncsnpp_48k' and 'ncsnpp_v2' backbones, not '{backbone}'")
     for attr, want in (("resblock_type", "biggan"), ("embedding_type", "fourier"), ("skip_rescale", True),
                        ("conditional", True), ("centered", True)):
         if getattr(dnn, attr, want) != want:
@@ -63,16 +63,29 @@ def config_from_score_model(model, mode="fp16_tc", max_batch=8, use_graphs=True)
     hann = torch.hann_window(dm.n_fft, periodic=True)
     window = "hann" if torch.allclose(dm.window.cpu().float(), hann, atol=1e-6) else "sqrthann"
     sde = model.sde
-    if type(sde).__name__ != "OUVESDE":
-        raise NotImplementedError("only the OUVE SDE is accelerated")
+    sde_name = type(sde).__name__
+    if sde_name == "OUVESDE":
+        sde_kw = dict(sde="ouve", theta=float(sde.theta), sigma_min=float(sde.sigma_min), sigma_max=float(sde.sigma_max))
+    elif sde_name == "SBVESDE":
+        if backbone != "ncsnpp_v2":
+            raise NotImplementedError("the Schroedinger-bridge SDE is driven by the preconditioned 'ncsnpp_v2' forward")
+        # get_sb_sampler works on sde.copy() = SBVESDE(k, c, N) (sdes.py:265-266): the stabiliser eps falls back to 1e-8
+        sde_kw = dict(sde="sbve", sb_k=float(sde.k), sb_c=float(sde.c), sb_eps=1e-8)
+    else:
+        raise NotImplementedError("only the OUVE and SBVE SDEs are accelerated")
+    pre_kw = {}
+    if backbone == "ncsnpp_v2":                          # ScoreModel attributes of model.py:52-60
+        pre_kw = dict(loss_type=model.loss_type, network_scaling=model.network_scaling, c_in=model.c_in, c_out=model.c_out,
+                      c_skip=model.c_skip, sigma_data=float(model.sigma_data))
     return EngineConfig(
         backbone=backbone, nf=nf, ch_mult=tuple(ch_mult), num_res_blocks=dnn.num_res_blocks,
         attn_resolutions=tuple(dnn.attn_resolutions), image_size=dnn.all_resolutions[0],
-        progressive=dnn.progressive, progressive_input=dnn.progressive_input, scale_by_sigma=bool(dnn.scale_by_sigma),
-        theta=float(sde.theta), sigma_min=float(sde.sigma_min), sigma_max=float(sde.sigma_max), t_eps=float(model.t_eps),
+        progressive=dnn.progressive, progressive_input=dnn.progressive_input,
+        scale_by_sigma=bool(getattr(dnn, "scale_by_sigma", False)) and backbone != "ncsnpp_v2",
+        t_eps=float(model.t_eps),
         n_fft=dm.n_fft, hop_length=dm.hop_length, window=window, spec_factor=float(dm.spec_factor),
         spec_abs_exponent=float(dm.spec_abs_exponent), sr=int(getattr(model, "sr", 16000)),
-        mode=mode, max_batch=max_batch, use_graphs=use_graphs)
+        mode=mode, max_batch=max_batch, use_graphs=use_graphs, **sde_kw, **pre_kw)
 
 
 def engine_from_score_model(model, load_weights=True, **kw) -> Engine:
@@ -122,17 +135,25 @@ def make_enhance(engine: Engine):
     def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="ald", N=30,
                 corrector_steps=1, snr=0.5, timeit=False, **kwargs):
         """One-call speech enhancement of noisy speech `y` [1, T] (or [B, T])."""
-        if getattr(self.sde, "sampler_type", "pc") != "pc":
-            raise NotImplementedError("only the PC sampler is accelerated (sde.sampler_type must be 'pc')")
         start = time.time()
         yy = y if y.dim() == 2 else y[None]
-        x_hat = engine.enhance(yy.detach().cpu().float(), N=N, predictor=predictor, corrector=corrector,
-                               corrector_steps=corrector_steps, snr=snr,
-                               seed=kwargs.get("seed", int(torch.randint(0, 2 ** 62, (1,)).item())),
-                               pad_mode=kwargs.get("pad_mode", "zero_pad"))
+        common = dict(seed=kwargs.get("seed", int(torch.randint(0, 2 ** 62, (1,)).item())), pad_mode=kwargs.get("pad_mode", "zero_pad"))
+        sde_name = type(self.sde).__name__
+        if sde_name == "SBVESDE":                     # model.py:450-452: get_sb_sampler(sde, Y, sampler_type=sde.sampler_type)
+            st = self.sde.sampler_type
+            if st not in ("ode", "sde"):
+                raise ValueError("Invalid type. Choose 'ode' or 'sde'.")
+            x_hat = engine.enhance(yy.detach().cpu().float(), N=self.sde.N, kind="sb_" + st, sb_eps=1e-4, sb_n_steps=50, **common)
+            sb_nfe = 50
+        else:
+            if getattr(self.sde, "sampler_type", "pc") != "pc":
+                raise NotImplementedError("only the PC sampler is accelerated on the OUVE SDE (sde.sampler_type must be 'pc')")
+            x_hat = engine.enhance(yy.detach().cpu().float(), N=N, predictor=predictor, corrector=corrector,
+                                   corrector_steps=corrector_steps, snr=snr, **common)
+            sb_nfe = None
         x_hat = x_hat.squeeze().numpy()
         end = time.time()
-        nfe = N * ((corrector_steps if corrector != "none" else 0) + 1)
+        nfe = sb_nfe if sb_nfe is not None else N * ((corrector_steps if corrector != "none" else 0) + 1)
         if timeit:
             rtf = (end - start) / (x_hat.shape[-1] / self.sr)
             return x_hat, nfe, rtf
@@ -150,8 +171,22 @@ def install(model, engine: Optional[Engine] = None, **kw) -> Engine:
     model.enhance = types.MethodType(make_enhance(engine), model)
 
     def forward(self, x_t, y, t):
-        return engine.score(x_t, y, t)
+        return engine.model_forward(x_t, y, t)        # legacy: score; 'ncsnpp_v2': model.py:283-304
     model.forward = types.MethodType(forward, model)
+
+    def get_sb_sampler(self, sde, y, sampler_type="ode", N=None, **kwargs):
+        # model.py:392-397 + sampling/__init__.py:145 (eps=1e-4, n_steps=50 defaults)
+        N_ = sde.N if N is None else N
+        kw = dict(sampler_type=sampler_type, N=N_, eps=kwargs.get("eps", 1e-4), n_steps=kwargs.get("n_steps", 50),
+                  seed=kwargs.get("seed", int(torch.randint(0, 2 ** 62, (1,)).item())))
+        noise = kwargs.get("noise", None)
+
+        def sb_sampler():
+            with torch.no_grad():
+                return engine.sb_sample(y, noise=noise, **kw)
+        return sb_sampler
+    model._sgmse_b200_saved["get_sb_sampler"] = model.__dict__.get("get_sb_sampler")
+    model.get_sb_sampler = types.MethodType(get_sb_sampler, model)
     return engine
 
 

@@ -95,7 +95,12 @@ void build_network(Engine& e) {
   SG_CHECK(c.nf > 0 && c.nf % 8 == 0, "nf=%d must be a positive multiple of 8", c.nf);
   SG_CHECK(c.num_levels >= 1 && c.num_levels <= 8, "num_levels=%d out of range", c.num_levels);
   SG_CHECK(c.num_res_blocks >= 1, "num_res_blocks must be >= 1");
-  SG_CHECK(c.backbone == SGMSE_B200_BACKBONE_NCSNPP || c.backbone == SGMSE_B200_BACKBONE_NCSNPP_48K, "unknown backbone %d", c.backbone);
+  SG_CHECK(c.backbone == SGMSE_B200_BACKBONE_NCSNPP || c.backbone == SGMSE_B200_BACKBONE_NCSNPP_48K ||
+               c.backbone == SGMSE_B200_BACKBONE_NCSNPP_V2, "unknown backbone %d", c.backbone);
+  SG_CHECK(c.backbone != SGMSE_B200_BACKBONE_NCSNPP_V2 || !c.scale_by_sigma, "'ncsnpp_v2' has no in-network scaling");
+  SG_CHECK(c.sde_kind == SGMSE_B200_SDE_OUVE || c.sde_kind == SGMSE_B200_SDE_SBVE, "unknown SDE kind %d", c.sde_kind);
+  SG_CHECK(c.loss_type >= 0 && c.loss_type <= 2 && c.network_scaling >= 0 && c.network_scaling <= 2 && c.c_in >= 0 &&
+               c.c_in <= 1 && c.c_out >= 0 && c.c_out <= 3 && c.c_skip >= 0 && c.c_skip <= 1, "bad preconditioning settings");
   Walker w{e};
   const int nf = c.nf, L = c.num_levels, temb_dim = 4 * nf;
   e.outl_w = w.add("output_layer.weight", 8);          // assigned before all_modules (ncsnpp.py:104)
@@ -345,6 +350,7 @@ struct Fwd {
   int temb_stride;       // 0: one row for all samples; totalC: one row per sample
   bool dry;
   DType dt;
+  float in_scale = 1.f;  // c_in of the preconditioned forward: multiplies the (x, y) state inside the input conv
 
   TensorDesc act(int N, int H, int W, int C, bool stats) {
     TensorDesc t;
@@ -510,7 +516,7 @@ struct Fwd {
     const sgmse_b200_config& c = e.cfg;
     const int L = c.num_levels;
     SG_CHECK(H % (1 << (L - 1)) == 0 && W % (1 << (L - 1)) == 0, "F=%d, T=%d must be multiples of %d", H, W, 1 << (L - 1));
-    if (c.num_attn_resolutions > 0 && c.backbone == SGMSE_B200_BACKBONE_NCSNPP)
+    if (c.num_attn_resolutions > 0 && c.backbone != SGMSE_B200_BACKBONE_NCSNPP_48K)
       SG_CHECK(H == c.image_size, "ncsnpp places attention for F == image_size == %d (got F=%d), see ncsnpp.py:84,308", c.image_size, H);
     e.arena.reset();
     e.launches_this_forward = 0;
@@ -526,7 +532,7 @@ struct Fwd {
     std::vector<TensorDesc> hs;
     {
       TensorDesc h0 = act(B, H, W, c.nf, true);
-      if (!dry) { launch_input_conv(st, state, B, H, W, e.inconv_w_packed, e.blob_dev + e.inconv_b, h0); count(); }
+      if (!dry) { launch_input_conv(st, state, B, H, W, e.inconv_w_packed, e.blob_dev + e.inconv_b, h0, in_scale); count(); }
       tap("in_conv", h0);
       hs.push_back(h0);
     }
@@ -751,20 +757,103 @@ std::vector<float> linspace_f32(float start, float end, int steps) {
 }
 
 int noise_draws(const sgmse_b200_sampler& s) {
+  if (s.kind == SGMSE_B200_SAMPLER_SB_SDE) return s.N;   // one draw per step, the last one with weight 0 (sampling/__init__.py:176-179)
+  if (s.kind == SGMSE_B200_SAMPLER_SB_ODE) return 0;
   const int c = s.corrector != SGMSE_B200_CORR_NONE ? s.corrector_steps : 0;
   const int p = s.predictor != SGMSE_B200_PRED_NONE ? 1 : 0;
   return 1 + s.N * (c + p);
 }
 
+// ---- SDE scalars (double on the host; the reference evaluates them on fp32 tensors) ----
+double ouve_std(const sgmse_b200_config& c, double t) {          // sdes.py:206-219
+  const double th = c.theta, smin = c.sigma_min, ls = log((double)c.sigma_max / c.sigma_min);
+  return sqrt(smin * smin * exp(-2 * th * t) * (exp(2 * (th + ls) * t) - 1) * ls / (th + ls));
+}
+struct SbSigmas { double sigma_t, sigma_T, sigma_bar; };           // alpha_t = alpha_T = 1 (sdes.py:277-278)
+SbSigmas sb_sigmas(const sgmse_b200_config& c, double t) {         // sdes.py:276-287
+  const double k = c.sb_k, logk2 = 2 * log(k);
+  SbSigmas r;
+  r.sigma_t = sqrt(c.sb_c * (pow(k, 2 * t) - 1.0) / logk2);
+  r.sigma_T = sqrt(c.sb_c * (pow(k, 2.0) - 1.0) / logk2);
+  r.sigma_bar = sqrt(r.sigma_T * r.sigma_T - r.sigma_t * r.sigma_t + c.sb_eps);
+  return r;
+}
+double sde_std(const sgmse_b200_config& c, double t) {
+  if (c.sde_kind == SGMSE_B200_SDE_OUVE) return ouve_std(c, t);
+  const SbSigmas g = sb_sigmas(c, t);                              // sdes.py:298-302
+  return g.sigma_bar * g.sigma_t / (g.sigma_T + c.sb_eps);
+}
+// ScoreModel.forward of the 'ncsnpp_v2' branch as  M(x_t, y, t) = a * x_t + b * dnn(c_in x_t, c_in y, t)  (model.py:283-341)
+struct Precond { double c_in, a, b; };
+Precond precond(const sgmse_b200_config& c, double t) {
+  const double sig = sde_std(c, t), sd2 = (double)c.sigma_data * c.sigma_data;
+  Precond p;
+  p.c_in = c.c_in == SGMSE_B200_CIN_ONE ? 1.0 : 1.0 / sqrt(sig * sig + sd2);
+  const double c_out = c.c_out == SGMSE_B200_COUT_ONE ? 1.0 : c.c_out == SGMSE_B200_COUT_SIGMA ? sig :
+                       c.c_out == SGMSE_B200_COUT_INV_SIGMA ? 1.0 / sig : sig * c.sigma_data / sqrt(sd2 + sig * sig);
+  const double c_skip = c.c_skip == SGMSE_B200_CSKIP_ZERO ? 0.0 : sd2 / (sig * sig + sd2);
+  const double ns = c.network_scaling == SGMSE_B200_NETSCALE_INV_SIGMA ? 1.0 / sig :
+                    c.network_scaling == SGMSE_B200_NETSCALE_INV_T ? 1.0 / t : 1.0;
+  if (c.loss_type == SGMSE_B200_LOSS_DENOISER) { p.a = -1.0 / (sig * sig); p.b = ns / (sig * sig); }
+  else { p.a = c_skip; p.b = c_out * ns; }
+  return p;
+}
+bool is_v2(const Engine& e) { return e.cfg.backbone == SGMSE_B200_BACKBONE_NCSNPP_V2; }
+
 struct SamplerTables {
   std::vector<float> ts;
   std::vector<UpdateCoef> coef;    // one per update, in execution order (langevin entries filled on device)
+  // general path (SB samplers; every sampler on the preconditioned v2 model): x_mean = cx x + cF F + cy y, x = x_mean + cz z
+  bool affine = false;
+  std::vector<AffineCoef> acoef;   // one per update
+  std::vector<float> in_scale;     // c_in(t_i), one per time step
+  std::vector<float> sb_raw;       // SB kinds: (weight_prev, weight_estimate, weight_z | weight_prior_mean) per step, as the reference names them
 };
 
 SamplerTables make_tables(const Engine& e, const sgmse_b200_sampler& s) {
   // sdes.py:188-219, predictors.py:41-65, correctors.py:69-81, sampling/__init__.py:56-62
   SamplerTables tb;
   const sgmse_b200_config& c = e.cfg;
+  if (s.kind != SGMSE_B200_SAMPLER_PC) {
+    // Schroedinger-bridge samplers (sampling/__init__.py:145-249): N steps over linspace(T, eps, N+1)[1:]
+    SG_CHECK(c.sde_kind == SGMSE_B200_SDE_SBVE, "the SB samplers need the 'sbve' SDE");
+    SG_CHECK(is_v2(e), "the SB samplers are driven by ScoreModel.forward(x_t, y, t) of backbone 'ncsnpp_v2'");
+    const std::vector<float> all = linspace_f32(1.0f, s.sb_eps, s.N + 1);
+    tb.ts.assign(all.begin() + 1, all.end());
+    tb.affine = true;
+    SbSigmas prev = sb_sigmas(c, all[0]);
+    const double eps = c.sb_eps;
+    for (int i = 0; i < s.N; ++i) {
+      const double t = tb.ts[i];
+      const SbSigmas cur = sb_sigmas(c, t);
+      double w_prev, w_est, w_third;
+      if (s.kind == SGMSE_B200_SAMPLER_SB_SDE) {                     // :165-179
+        w_prev = cur.sigma_t * cur.sigma_t / (prev.sigma_t * prev.sigma_t + eps);
+        const double tmp = 1 - cur.sigma_t * cur.sigma_t / (prev.sigma_t * prev.sigma_t + eps);
+        w_est = tmp;
+        w_third = i == s.N - 1 ? 0.0 : cur.sigma_t * sqrt(tmp);      // weight_z
+      } else {                                                       // :211-231
+        w_prev = cur.sigma_t * cur.sigma_bar / (prev.sigma_t * prev.sigma_bar + eps);
+        w_est = 1.0 / (cur.sigma_T * cur.sigma_T + eps) *
+                (cur.sigma_bar * cur.sigma_bar - prev.sigma_bar * cur.sigma_t * cur.sigma_bar / (prev.sigma_t + eps));
+        w_third = 1.0 / (cur.sigma_T * cur.sigma_T + eps) *
+                  (cur.sigma_t * cur.sigma_t - prev.sigma_t * cur.sigma_t * cur.sigma_bar / (prev.sigma_bar + eps));   // weight_prior_mean
+      }
+      tb.sb_raw.push_back((float)w_prev); tb.sb_raw.push_back((float)w_est); tb.sb_raw.push_back((float)w_third);
+      const Precond pc = precond(c, t);
+      tb.in_scale.push_back((float)pc.c_in);
+      // x' = w_prev x + w_est (a x + b F) + [w_y y | w_z z]
+      AffineCoef a;
+      a.cx = (float)(w_prev + w_est * pc.a);
+      a.cF = (float)(w_est * pc.b);
+      a.cy = s.kind == SGMSE_B200_SAMPLER_SB_ODE ? (float)w_third : 0.f;
+      a.cz = s.kind == SGMSE_B200_SAMPLER_SB_SDE ? (float)w_third : 0.f;
+      tb.acoef.push_back(a);
+      prev = cur;
+    }
+    return tb;
+  }
+  SG_CHECK(c.sde_kind == SGMSE_B200_SDE_OUVE, "the predictor-corrector sampler is implemented for the 'ouve' SDE");
   tb.ts = linspace_f32(1.0f, c.t_eps, s.N);
   const double th = c.theta, smin = c.sigma_min, smax = c.sigma_max, ls = log(smax / smin);
   const double pf = s.probability_flow ? 0.5 : 1.0;
@@ -788,6 +877,21 @@ SamplerTables make_tables(const Engine& e, const sgmse_b200_sampler& s) {
       tb.coef.push_back(UpdateCoef{(float)(th * dt), (float)(-g * g * pf * dt), s.probability_flow ? 0.f : (float)(g * sqrt(-dt))});
     }
   }
+  if (is_v2(e)) {
+    // the same updates driven by the preconditioned model: score = a x + b F  ->
+    // x_mean = x + cy (y - x) + cs score = (1 - cy + cs a) x + cs b F + cy y
+    SG_CHECK(s.corrector != SGMSE_B200_CORR_LANGEVIN, "the Langevin corrector (data-dependent step) is not available on 'ncsnpp_v2'");
+    SG_CHECK(c.loss_type != SGMSE_B200_LOSS_DATA_PREDICTION, "the predictor-corrector sampler needs a score model (loss_type)");
+    tb.affine = true;
+    const int per_step = (int)tb.coef.size() / s.N;
+    for (size_t u = 0; u < tb.coef.size(); ++u) {
+      const int i = per_step ? (int)u / per_step : 0;
+      const Precond pc = precond(c, tb.ts[i]);
+      const UpdateCoef& k = tb.coef[u];
+      tb.acoef.push_back(AffineCoef{(float)(1.0 - k.cy + k.cs * pc.a), (float)(k.cs * pc.b), k.cy, k.cz});
+    }
+    for (int i = 0; i < s.N; ++i) tb.in_scale.push_back((float)precond(c, tb.ts[i]).c_in);
+  }
   return tb;
 }
 
@@ -799,6 +903,44 @@ void sample_chunk(Engine& e, const float2* y, int Bc, int F, int T, const sgmse_
   const RngParams* rng = e.rng_dev;
   auto nz = [&](int draw) { return noise ? noise + (size_t)draw * noise_draw_stride : nullptr; };
   const sgmse_b200_config& c = e.cfg;
+  if (tb.affine) {
+    // general update path: Schroedinger-bridge samplers, and the predictor-corrector sampler on the preconditioned
+    // 'ncsnpp_v2' model.  Coefficient rows live in coef_dev (reinterpreted), one per update in execution order.
+    const AffineCoef* ac = reinterpret_cast<const AffineCoef*>(e.coef_dev);
+    launch_pack_state(st, y, y, Bc, F, T, e.state); ++e.kernel_launches;       // x = y (SB: sampling/__init__.py:150,193)
+    int draw = 0, ci = 0;
+    const bool pc = s.kind == SGMSE_B200_SAMPLER_PC;
+    if (pc) {                                                                    // x = y + std(1) z (sdes.py:224-229)
+      launch_prior(st, e.state, Bc, F, T, (float)ouve_std(c, 1.0), nz(draw), rng, draw); ++e.kernel_launches;
+      ++draw;
+    }
+    Fwd f{e, st, nullptr, 0, false, e.cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
+    bool have_mean = false;
+    for (int i = 0; i < s.N; ++i) {
+      f.temb = e.temb_table + (size_t)i * e.total_temb_c;
+      f.in_scale = tb.in_scale[i];
+      const int ncorr = pc && s.corrector != SGMSE_B200_CORR_NONE ? s.corrector_steps : 0;
+      const int npred = pc ? (s.predictor != SGMSE_B200_PRED_NONE ? 1 : 0) : 1;
+      for (int u = 0; u < ncorr + npred; ++u) {
+        const float4* p = f.run(e.state, Bc, F, T);
+        const bool is_pred = u >= ncorr;
+        const bool last = pc && is_pred && i == s.N - 1;
+        const bool use_noise = pc || s.kind == SGMSE_B200_SAMPLER_SB_SDE;
+        launch_affine_update(st, e.state, p, Bc, F, T, e.out_layer, ac + ci, use_noise ? nz(draw) : nullptr, rng, draw, use_noise,
+                             (last && s.denoise) ? e.xmean : nullptr);
+        ++e.kernel_launches; ++ci;
+        if (use_noise) ++draw;
+        have_mean = last && s.denoise;
+      }
+    }
+    if (have_mean) {
+      CUDA_OK(cudaMemcpyAsync(out, e.xmean, px * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    } else {
+      extract_x_kernel<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(e.state, px, out);
+      CUDA_OK(cudaGetLastError()); ++e.kernel_launches;
+    }
+    return;
+  }
   const double th = c.theta, smin = c.sigma_min, smax = c.sigma_max, ls = log(smax / smin);
   const float std1 = (float)sqrt(smin * smin * exp(-2 * th) * (exp(2 * (th + ls)) - 1) * ls / (th + ls));
 
@@ -847,7 +989,10 @@ void ensure_stft_buf(Engine& e, int slot, size_t bytes);
 void prepare_tables(Engine& e, const sgmse_b200_sampler& s, cudaStream_t st) {
   const SamplerTables tb = make_tables(e, s);
   CUDA_OK(cudaMemcpyAsync(e.t_dev, tb.ts.data(), tb.ts.size() * 4, cudaMemcpyHostToDevice, st));
-  if (!tb.coef.empty())
+  if (tb.affine) {
+    if (!tb.acoef.empty())
+      CUDA_OK(cudaMemcpyAsync(e.coef_dev, tb.acoef.data(), tb.acoef.size() * sizeof(AffineCoef), cudaMemcpyHostToDevice, st));
+  } else if (!tb.coef.empty())
     CUDA_OK(cudaMemcpyAsync(e.coef_dev, tb.coef.data(), tb.coef.size() * sizeof(UpdateCoef), cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaStreamSynchronize(st));   // tb is a temporary; keep the host buffers alive until copied
   launch_temb(st, temb_weights(e), e.t_dev, s.N, e.temb_scratch, e.temb_table); e.kernel_launches += 2;
@@ -864,6 +1009,7 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
   }
   struct SyncOnExit { cudaStream_t s; bool on; ~SyncOnExit() { if (on) cudaStreamSynchronize(s); } } sync_guard{st, st_in == nullptr};
   SG_CHECK(s.N >= 1 && s.corrector_steps >= 0, "bad sampler settings");
+  SG_CHECK(s.kind >= SGMSE_B200_SAMPLER_PC && s.kind <= SGMSE_B200_SAMPLER_SB_SDE, "Invalid type. Choose 'ode' or 'sde'.");
   SG_CHECK(s.predictor >= 0 && s.predictor <= 2, "Predictor with id %d unknown.", s.predictor);
   SG_CHECK(s.corrector >= 0 && s.corrector <= 2, "Corrector with id %d unknown.", s.corrector);
   const int mb = std::max(1, e.cfg.max_batch);
@@ -909,7 +1055,7 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
       e.graphs.clear();
       e.lanes_generation_seen = gen;
     }
-    GraphKey key{Bc * 64 + L, F, T, s.N, s.predictor, s.corrector, csteps, s.denoise, s.probability_flow, s.snr};
+    GraphKey key{Bc * 64 + L, F, T, s.N, s.predictor, s.corrector, csteps, s.denoise, s.probability_flow, s.snr, s.kind, s.sb_eps};
     auto it = e.graphs.find(key);
     if (it == e.graphs.end()) {
       // one eager network evaluation first: sets function attributes and surfaces launch errors early
@@ -956,7 +1102,7 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
       if (ln[i] > 0)
         CUDA_OK(cudaMemcpyAsync(out + (b0 + lb[i]) * px1, e.lanes[i]->stft_buf[3], ln[i] * px1 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
   }
-  if (nfe) *nfe = s.N * (csteps + 1);
+  if (nfe) *nfe = s.kind == SGMSE_B200_SAMPLER_PC ? s.N * (csteps + 1) : s.sb_n_steps;   // the SB samplers report their n_steps argument
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1136,12 +1282,62 @@ int sgmse_b200_score(sgmse_b200_engine* e, const void* x_t, const void* y, const
 
 int sgmse_b200_noise_draws(const sgmse_b200_sampler* s) { return s ? noise_draws(*s) : -1; }
 
+int sgmse_b200_model_forward(sgmse_b200_engine* e, const void* x_t, const void* y, const float* t, void* out, int B, int F,
+                             int T, void* stream) {
+  API_BEGIN
+  SG_CHECK(e && x_t && y && t && out && B > 0, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!is_v2(*e)) {                                  // legacy branch (model.py:307-310)
+    dnn_forward(*e, (const float2*)x_t, (const float2*)y, t, (float2*)out, B, F, T, true, st);
+  } else {
+    // per-sample scalars of model.py:283-304 on the host (this is the parity entry point, not the sampler's hot path)
+    SG_CHECK(e->loaded, "weights not loaded");
+    std::vector<float> th(B);
+    CUDA_OK(cudaMemcpyAsync(th.data(), t, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const int mb = std::max(1, e->cfg.max_batch);
+    ensure_arena(*e, std::min(B, mb), F, T);
+    ensure_persistent(*e, (size_t)std::min(B, mb) * F * T, std::max(mb, 64));
+    const size_t px1 = (size_t)F * T;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int Bc = std::min(mb, B - b0);
+      std::vector<float> sc(3 * (size_t)Bc);
+      for (int i = 0; i < Bc; ++i) {
+        const Precond p = precond(e->cfg, th[b0 + i]);
+        sc[i] = (float)p.c_in; sc[Bc + i] = (float)p.a; sc[2 * Bc + i] = (float)p.b;
+      }
+      // the three per-sample vectors (c_in, a, b) are staged in coef_dev (capacity: rows x 48 B >= 3 x Bc floats)
+      float* vec = reinterpret_cast<float*>(e->coef_dev);
+      CUDA_OK(cudaMemcpyAsync(vec, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      launch_pack_state_scaled(st, (const float2*)x_t + b0 * px1, (const float2*)y + b0 * px1, vec, Bc, F, T, e->state);
+      ++e->kernel_launches;
+      launch_temb(st, temb_weights(*e), t + b0, Bc, e->temb_scratch, e->temb_table); e->kernel_launches += 2;
+      Fwd f{*e, st, e->temb_table, e->total_temb_c, false, e->cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
+      const float4* p = f.run(e->state, Bc, F, T);
+      launch_precond_out(st, (const float2*)x_t + b0 * px1, p, Bc, F, T, e->out_layer, vec + Bc, vec + 2 * Bc,
+                         (float2*)out + b0 * px1);
+      ++e->kernel_launches;
+    }
+  }
+  API_END
+}
+
 int sgmse_b200_sampler_schedule(const sgmse_b200_engine* e, const sgmse_b200_sampler* s, float* ts, float* prior_std,
                                 float* coef, int cap_updates, int* n_updates) {
   API_BEGIN
   SG_CHECK(e && s && s->N >= 1, "bad argument");
   const SamplerTables tb = make_tables(*e, *s);
   if (ts) for (int i = 0; i < s->N; ++i) ts[i] = tb.ts[i];
+  if (s->kind != SGMSE_B200_SAMPLER_PC) {
+    if (prior_std) *prior_std = 0.f;
+    if (n_updates) *n_updates = s->N;
+    if (coef) {
+      SG_CHECK(cap_updates >= s->N, "coef buffer holds %d rows, the schedule has %d", cap_updates, s->N);
+      for (int i = 0; i < 3 * s->N; ++i) coef[i] = tb.sb_raw[i];
+    }
+    return 0;
+  }
   if (prior_std) {
     const sgmse_b200_config& c = e->cfg;
     const double th = c.theta, smin = c.sigma_min, smax = c.sigma_max, ls = log(smax / smin);

@@ -67,9 +67,11 @@ struct Arena {
 struct GraphKey {
   int B, F, T, N, pred, corr, csteps, denoise, pf;
   float snr;
+  int kind;
+  float sb_eps;
   bool operator<(const GraphKey& o) const {
-    return std::tie(B, F, T, N, pred, corr, csteps, denoise, pf, snr) <
-           std::tie(o.B, o.F, o.T, o.N, o.pred, o.corr, o.csteps, o.denoise, o.pf, o.snr);
+    return std::tie(B, F, T, N, pred, corr, csteps, denoise, pf, snr, kind, sb_eps) <
+           std::tie(o.B, o.F, o.T, o.N, o.pred, o.corr, o.csteps, o.denoise, o.pf, o.snr, o.kind, o.sb_eps);
   }
 };
 

@@ -95,8 +95,9 @@ extern int g_tc_variant;   // 0 (= 7, 8): newest applicable kernels (v6 with fus
                            // 10: the same with half2 math on the split-mean coefficient table (mode 3)
 
 // input layer: state float4 (x.re,x.im,y.re,y.im) -> conv3x3(4->C); w [36][C] (k = tap*4+cin), bias [C]
+// in_scale multiplies the state on the way in (c_in of the preconditioned 'ncsnpp_v2' forward, model.py:284,312-319)
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
-                       const float* bias, TensorDesc& out);
+                       const float* bias, TensorDesc& out, float in_scale = 1.f);
 // Combine('sum'): out = conv1x1_{4->C}(pyr) + bias + h ; pyr float4 [N,H,W]; w [4][C]
 void launch_combine(cudaStream_t st, const float4* pyr, const float* w, const float* bias, const TensorDesc& h,
                     TensorDesc& out);
@@ -155,6 +156,21 @@ void launch_pc_update(cudaStream_t st, float4* state, const float4* pyr, int N, 
 void launch_out_layer(cudaStream_t st, const float4* pyr, int N, int H, int W, const OutLayer& ol, const float* t_dev,
                       float2* out, bool negate);
 void launch_pack_state(cudaStream_t st, const float2* x, const float2* y, int N, int H, int W, float4* state);
+// state = scale[n] * (x, y)   (per-sample c_in of ScoreModel.forward with a vector of times)
+void launch_pack_state_scaled(cudaStream_t st, const float2* x, const float2* y, const float* scale_dev, int N, int H, int W,
+                              float4* state);
+// General one-step update (Schroedinger-bridge samplers, sampling/__init__.py:165-181,211-233, and every sampler on the
+// preconditioned 'ncsnpp_v2' model): with F = output_layer(pyr) (no in-network scaling),
+//   x_mean = cx * x + cF * F + cy * y ;  x = x_mean + cz * z     (z drawn only when use_noise)
+struct AffineCoef {
+  float cx, cF, cy, cz;
+};
+void launch_affine_update(cudaStream_t st, float4* state, const float4* pyr, int N, int H, int W, const OutLayer& ol,
+                          const AffineCoef* coef_dev, const float2* noise, const RngParams* rng, int draw, bool use_noise,
+                          float2* x_mean_out /*nullable*/);
+// out[n] = a[n] * x_t + b[n] * output_layer(pyr)   (ScoreModel.forward of the 'ncsnpp_v2' branch, model.py:296-304)
+void launch_precond_out(cudaStream_t st, const float2* x_t, const float4* pyr, int N, int H, int W, const OutLayer& ol,
+                        const float* a_dev, const float* b_dev, float2* out);
 // state.x = y + std1 * z
 void launch_prior(cudaStream_t st, float4* state, int N, int H, int W, float std1, const float2* noise,
                   const RngParams* rng, int draw);

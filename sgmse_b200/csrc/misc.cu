@@ -139,6 +139,51 @@ void launch_pc_update(cudaStream_t st, float4* state, const float4* pyr, int N, 
   CUDA_OK(cudaGetLastError());
 }
 
+__global__ void affine_update_kernel(float4* __restrict__ state, const float4* __restrict__ pyr, int HW, size_t total,
+                                     OutLayer ol, const AffineCoef* __restrict__ coef_dev, const float2* __restrict__ noise,
+                                     const RngParams* rng, int draw, int use_noise, float2* __restrict__ x_mean_out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx / HW);
+  const AffineCoef cf = *coef_dev;
+  const float2 d = out_layer(ol, pyr[idx], 1.0f);
+  float4 s = state[idx];
+  const float mre = cf.cx * s.x + cf.cF * d.x + cf.cy * s.z;
+  const float mim = cf.cx * s.y + cf.cF * d.y + cf.cy * s.w;
+  float2 z = make_float2(0.f, 0.f);
+  if (use_noise) z = draw_noise(noise, idx, rng, n, draw, (uint32_t)(idx - (size_t)n * HW));
+  s.x = mre + cf.cz * z.x;
+  s.y = mim + cf.cz * z.y;
+  state[idx] = s;
+  if (x_mean_out) x_mean_out[idx] = make_float2(mre, mim);
+}
+void launch_affine_update(cudaStream_t st, float4* state, const float4* pyr, int N, int H, int W, const OutLayer& ol,
+                          const AffineCoef* coef_dev, const float2* noise, const RngParams* rng, int draw, bool use_noise,
+                          float2* x_mean_out) {
+  const size_t total = (size_t)N * H * W;
+  affine_update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(state, pyr, H * W, total, ol, coef_dev, noise, rng,
+                                                                        draw, use_noise ? 1 : 0, x_mean_out);
+  CUDA_OK(cudaGetLastError());
+}
+
+__global__ void precond_out_kernel(const float2* __restrict__ x_t, const float4* __restrict__ pyr, int HW, size_t total,
+                                   OutLayer ol, const float* __restrict__ a_dev, const float* __restrict__ b_dev,
+                                   float2* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx / HW);
+  const float2 d = out_layer(ol, pyr[idx], 1.0f);
+  const float2 x = x_t[idx];
+  const float a = a_dev[n], b = b_dev[n];
+  out[idx] = make_float2(a * x.x + b * d.x, a * x.y + b * d.y);
+}
+void launch_precond_out(cudaStream_t st, const float2* x_t, const float4* pyr, int N, int H, int W, const OutLayer& ol,
+                        const float* a_dev, const float* b_dev, float2* out) {
+  const size_t total = (size_t)N * H * W;
+  precond_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_t, pyr, H * W, total, ol, a_dev, b_dev, out);
+  CUDA_OK(cudaGetLastError());
+}
+
 __global__ void out_layer_kernel(const float4* __restrict__ pyr, int HW, size_t total, OutLayer ol,
                                  const float* __restrict__ t_dev, float2* __restrict__ out, float sign) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,6 +209,21 @@ __global__ void pack_state_kernel(const float2* __restrict__ x, const float2* __
 void launch_pack_state(cudaStream_t st, const float2* x, const float2* y, int N, int H, int W, float4* state) {
   const size_t total = (size_t)N * H * W;
   pack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, y, total, state);
+  CUDA_OK(cudaGetLastError());
+}
+
+__global__ void pack_state_scaled_kernel(const float2* __restrict__ x, const float2* __restrict__ y,
+                                         const float* __restrict__ scale, int HW, size_t total, float4* __restrict__ state) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const float c = scale[idx / HW];
+  const float2 a = x[idx], b = y[idx];
+  state[idx] = make_float4(c * a.x, c * a.y, c * b.x, c * b.y);
+}
+void launch_pack_state_scaled(cudaStream_t st, const float2* x, const float2* y, const float* scale_dev, int N, int H, int W,
+                              float4* state) {
+  const size_t total = (size_t)N * H * W;
+  pack_state_scaled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, y, scale_dev, H * W, total, state);
   CUDA_OK(cudaGetLastError());
 }
 

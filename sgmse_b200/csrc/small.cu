@@ -24,7 +24,8 @@ __device__ __forceinline__ void oc_mma(float (&d)[4], const uint32_t (&a)[4], ui
 template <typename T, int TP>
 __global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restrict__ state, int H, int W, int C,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
-                                                         T* __restrict__ out, float* __restrict__ stats, int slots) {
+                                                         T* __restrict__ out, float* __restrict__ stats, int slots,
+                                                         float in_scale) {
   __shared__ __align__(16) float in[TP][36];
   const int HW = H * W;
   const int m0 = blockIdx.x * TP;
@@ -36,7 +37,8 @@ __global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restric
     const int y = r / W + tap / 3 - 1, x = r % W + tap % 3 - 1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) v = state[(size_t)n * HW + (size_t)y * W + x];
-    in[p][tap * 4 + 0] = v.x; in[p][tap * 4 + 1] = v.y; in[p][tap * 4 + 2] = v.z; in[p][tap * 4 + 3] = v.w;
+    in[p][tap * 4 + 0] = in_scale * v.x; in[p][tap * 4 + 1] = in_scale * v.y;
+    in[p][tap * 4 + 2] = in_scale * v.z; in[p][tap * 4 + 3] = in_scale * v.w;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -79,7 +81,7 @@ template <int NT>   // NT = C / 8
 __global__ void __launch_bounds__(128) input_conv_mma_kernel(const float4* __restrict__ state, int H, int W,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              __half* __restrict__ out, float* __restrict__ stats, int slots,
-                                                             int num_tiles) {
+                                                             int num_tiles, float in_scale) {
   constexpr int C = NT * 8;
   constexpr int PITCH = C + 8;                       // halfs per staged row: conflict-free 32-bit writes, 16-B aligned rows
   extern __shared__ __align__(16) uint8_t ic_smem[];
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(128) input_conv_mma_kernel(const float4* __res
             if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W)
               v = reinterpret_cast<const float2*>(sp + (size_t)y * W + x)[t & 1];
           }
-          const __half2 hv = __floats2half2_rn(v.x, v.y);
+          const __half2 hv = __floats2half2_rn(in_scale * v.x, in_scale * v.y);
           af[q >> 1][(q & 1) * 2 + hr] = *reinterpret_cast<const uint32_t*>(&hv);
         }
       }
@@ -189,32 +191,32 @@ __global__ void __launch_bounds__(128) input_conv_mma_kernel(const float4* __res
 
 template <int NT>
 static void input_conv_mma_launch(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
-                                  const float* bias, TensorDesc& out) {
+                                  const float* bias, TensorDesc& out, float in_scale) {
   constexpr int C = NT * 8;
   const int num_tiles = N * H * W / 128;
   const size_t smem = (size_t)3 * NT * 32 * sizeof(uint2) + (size_t)4 * 32 * (C + 8) * 2 + (size_t)4 * C * 2 * 4;
   auto k = input_conv_mma_kernel<NT>;
   CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(num_tiles, 148 * 4);
-  k<<<grid, 128, smem, st>>>(state, H, W, w, bias, (__half*)out.p, out.stats, out.slots, num_tiles);
+  k<<<grid, 128, smem, st>>>(state, H, W, w, bias, (__half*)out.p, out.stats, out.slots, num_tiles, in_scale);
   CUDA_OK(cudaGetLastError());
 }
 
 void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
-                       const float* bias, TensorDesc& out) {
+                       const float* bias, TensorDesc& out, float in_scale) {
   const int HW = H * W;
   SG_CHECK(HW % 32 == 0, "input conv: H*W must be a multiple of 32");
   if (out.dt == DT_F16 && g_inconv_variant == 0 && HW % 128 == 0 && (out.C == 128 || out.C == 64 || out.C == 32)) {
     out.slots = HW / 128;
-    if (out.C == 128) input_conv_mma_launch<16>(st, state, N, H, W, w, bias, out);
-    else if (out.C == 64) input_conv_mma_launch<8>(st, state, N, H, W, w, bias, out);
-    else input_conv_mma_launch<4>(st, state, N, H, W, w, bias, out);
+    if (out.C == 128) input_conv_mma_launch<16>(st, state, N, H, W, w, bias, out, in_scale);
+    else if (out.C == 64) input_conv_mma_launch<8>(st, state, N, H, W, w, bias, out, in_scale);
+    else input_conv_mma_launch<4>(st, state, N, H, W, w, bias, out, in_scale);
     return;
   }
   const int TP = (HW % 128 == 0) ? 128 : 32;
   out.slots = HW / TP;
   const int grid = N * HW / TP;
-#define GO(T, TP_) input_conv_kernel<T, TP_><<<grid, 128, 0, st>>>(state, H, W, out.C, w, bias, (T*)out.p, out.stats, out.slots)
+#define GO(T, TP_) input_conv_kernel<T, TP_><<<grid, 128, 0, st>>>(state, H, W, out.C, w, bias, (T*)out.p, out.stats, out.slots, in_scale)
   if (out.dt == DT_F16) { if (TP == 128) GO(__half, 128); else GO(__half, 32); }
   else { if (TP == 128) GO(float, 128); else GO(float, 32); }
 #undef GO

@@ -19,6 +19,14 @@ MODES = {"fp32": 0, "fp16_direct": 1, "fp16_tc": 2}
 PREDICTORS = {"reverse_diffusion": 0, "euler_maruyama": 1, "none": 2}
 CORRECTORS = {"ald": 0, "langevin": 1, "none": 2}
 PAD_MODES = {"zero_pad": 0, "reflection": 1}
+BACKBONES = {"ncsnpp": 0, "ncsnpp_48k": 1, "ncsnpp_v2": 2}
+SDES = {"ouve": 0, "sbve": 1}
+LOSS_TYPES = {"score_matching": 0, "denoiser": 1, "data_prediction": 2}
+NETWORK_SCALINGS = {None: 0, "1/sigma": 1, "1/t": 2}
+C_IN = {"1": 0, "edm": 1}
+C_OUT = {"1": 0, "sigma": 1, "1/sigma": 2, "edm": 3}
+C_SKIP = {"0": 0, "edm": 1}
+SAMPLER_KINDS = {"pc": 0, "sb_ode": 1, "sb_sde": 2}
 
 
 def _lookup(table: Dict[str, int], name: str, what: str) -> int:
@@ -30,7 +38,7 @@ def _lookup(table: Dict[str, int], name: str, what: str) -> int:
 
 @dataclass
 class EngineConfig:
-    backbone: str = "ncsnpp"                       # 'ncsnpp' | 'ncsnpp_48k'
+    backbone: str = "ncsnpp"                       # 'ncsnpp' | 'ncsnpp_48k' | 'ncsnpp_v2'
     nf: int = 128
     ch_mult: Sequence[int] = (1, 1, 2, 2, 2, 2, 2)
     num_res_blocks: int = 2
@@ -52,6 +60,25 @@ class EngineConfig:
     mode: str = "fp16_tc"
     max_batch: int = 8
     use_graphs: bool = True
+    # SDE registry name (sdes.py:144 'ouve', :235 'sbve') + SBVESDE parameters
+    sde: str = "ouve"
+    sb_k: float = 2.6
+    sb_c: float = 0.4
+    sb_eps: float = 1e-8
+    # ScoreModel attributes of the 'ncsnpp_v2' branch of forward (model.py:52-60, 283-341); argparse strings as in the reference
+    loss_type: str = "score_matching"
+    network_scaling: Optional[str] = None
+    c_in: str = "1"
+    c_out: str = "1"
+    c_skip: str = "0"
+    sigma_data: float = 0.1
+
+    @staticmethod
+    def ncsnpp_v2(**kw) -> "EngineConfig":
+        # same module list as 'ncsnpp', no in-network /t (ncsnpp_v2.py:241-395)
+        base = dict(backbone="ncsnpp_v2", scale_by_sigma=False)
+        base.update(kw)
+        return EngineConfig(**base)
 
     @staticmethod
     def ncsnpp_16k(**kw) -> "EngineConfig":
@@ -67,14 +94,16 @@ class EngineConfig:
         return EngineConfig(**base)
 
     def to_c(self) -> _lib.Config:
-        if self.backbone not in ("ncsnpp", "ncsnpp_48k"):
+        if self.backbone not in BACKBONES:
             raise ValueError(f"Backbone with name '{self.backbone}' unknown.")
+        if self.backbone == "ncsnpp_v2" and self.scale_by_sigma:
+            raise ValueError("'ncsnpp_v2' has no in-network scaling (scale_by_sigma must be False)")
         if self.progressive not in ("output_skip", "none") or self.progressive_input not in ("input_skip", "none"):
             raise NotImplementedError("only progressive in {output_skip, none} / progressive_input in {input_skip, none}")
         if len(self.ch_mult) > 8 or len(self.attn_resolutions) > 8:
             raise ValueError("at most 8 levels / attention resolutions")
         c = _lib.Config()
-        c.backbone = 0 if self.backbone == "ncsnpp" else 1
+        c.backbone = BACKBONES[self.backbone]
         c.nf = self.nf
         c.num_levels = len(self.ch_mult)
         for i, m in enumerate(self.ch_mult):
@@ -94,6 +123,14 @@ class EngineConfig:
         c.mode = _lookup(MODES, self.mode, "Mode")
         c.max_batch = self.max_batch
         c.use_graphs = int(self.use_graphs)
+        c.sde_kind = _lookup(SDES, self.sde, "SDE")
+        c.sb_k, c.sb_c, c.sb_eps = self.sb_k, self.sb_c, self.sb_eps
+        c.loss_type = _lookup(LOSS_TYPES, self.loss_type, "Loss type")
+        c.network_scaling = _lookup(NETWORK_SCALINGS, self.network_scaling, "Network scaling")
+        c.c_in = _lookup(C_IN, self.c_in, "c_in type")
+        c.c_out = _lookup(C_OUT, self.c_out, "c_out type")
+        c.c_skip = _lookup(C_SKIP, self.c_skip, "c_skip type")
+        c.sigma_data = self.sigma_data
         return c
 
 
@@ -201,9 +238,30 @@ class Engine:
         _lib.check(self.lib.sgmse_b200_score(self._h, x_t.data_ptr(), y.data_ptr(), t.data_ptr(), out.data_ptr(), B, F, T, _stream_ptr()))
         return out
 
+    def model_forward(self, x_t: torch.Tensor, y: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """ScoreModel.forward for the configured backbone (model.py:261-341): the score, or for
+        ``loss_type='data_prediction'`` the clean-speech estimate of the preconditioned 'ncsnpp_v2' network."""
+        x_t, y = self._c64(x_t), self._c64(y)
+        self._use_device()
+        B, _, F, T = y.shape
+        t = t.to(device=y.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(y)
+        _lib.check(self.lib.sgmse_b200_model_forward(self._h, x_t.data_ptr(), y.data_ptr(), t.data_ptr(), out.data_ptr(),
+                                                     B, F, T, _stream_ptr()))
+        return out
+
+    def sb_sample(self, y: torch.Tensor, sampler_type: str = "ode", N: int = 50, eps: float = 1e-4, n_steps: int = 50,
+                  noise: Optional[torch.Tensor] = None, **kw):
+        """sampling.get_sb_sampler(sde, model, y, eps, n_steps, sampler_type)() (sampling/__init__.py:145-249):
+        y c64 [B,1,F,T] -> (sample, n_steps).  ``noise``: optional c64 [N,B,1,F,T] for ``sampler_type='sde'``."""
+        if sampler_type not in ("ode", "sde"):
+            raise ValueError("Invalid type. Choose 'ode' or 'sde'.")
+        return self.pc_sample(y, noise=noise, N=N, kind="sb_" + sampler_type, sb_eps=eps, sb_n_steps=n_steps, **kw)
+
     # ---- sampler ---------------------------------------------------------------------------------
     def sampler_struct(self, N=30, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.5,
-                       denoise=True, probability_flow=False, seed=0, utt_offset=0, pad_mode="zero_pad") -> _lib.Sampler:
+                       denoise=True, probability_flow=False, seed=0, utt_offset=0, pad_mode="zero_pad",
+                       kind="pc", sb_eps=1e-4, sb_n_steps=50) -> _lib.Sampler:
         s = _lib.Sampler()
         s.N = int(N)
         s.predictor = _lookup(PREDICTORS, predictor, "Predictor")
@@ -215,6 +273,9 @@ class Engine:
         s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         s.utt_offset = int(utt_offset)
         s.pad_mode = _lookup(PAD_MODES, pad_mode, "Pad mode")
+        s.kind = _lookup(SAMPLER_KINDS, kind, "Sampler kind")
+        s.sb_eps = float(sb_eps)
+        s.sb_n_steps = int(sb_n_steps)
         return s
 
     def noise_draws(self, **kw) -> int:

@@ -72,3 +72,25 @@ def test_no_cpu_fallback():
         eng.score(torch.zeros(1, 1, 64, 64, dtype=torch.complex64), torch.zeros(1, 1, 64, 64, dtype=torch.complex64),
                   torch.ones(1))
     eng.close()
+
+
+@pytest.mark.parametrize("sampler_type", ["ode", "sde"])
+@pytest.mark.parametrize("N,eps", [(50, 1e-4), (7, 1e-4), (30, 1e-3)])
+def test_sb_schedule_matches_oracle(sampler_type, N, eps):
+    """Host-computed Schroedinger-bridge schedule (engine.cu: make_tables, double precision) against the oracle's fp32
+    restatement of sampling/__init__.py:152-231, which tests/test_oracle_golden.py pins to the reference's sampler
+    outputs.  The reference evaluates k**(2t) - 1 in fp32, a cancellation that costs ~3e-4 relative at t = 1e-4;
+    the weights it feeds stay within 1e-5 of the double-precision values."""
+    from oracle import sde as o_sde
+    eng = Engine(EngineConfig.ncsnpp_v2(sde="sbve", loss_type="data_prediction", sb_k=2.6, sb_c=0.4))
+    ts, std1, rows = eng.sampler_schedule(N=N, kind="sb_" + sampler_type, sb_eps=eps)
+    eng.close()
+    ref_ts, ref_rows = o_sde.sb_weights(o_sde.SBVE(2.6, 0.4), N, eps, sampler_type)
+    assert std1 == 0.0 and rows.shape == (N, 3)
+    assert torch.allclose(ts, ref_ts, rtol=2.5e-7, atol=1e-9)
+    # the first ODE step divides by sigma_bar(T) = sqrt(eps) = 1e-4: weight_prev and weight_prior_mean are +-2.25e3 and
+    # cancel (x_0 = y); their fp32 evaluation in the reference carries a relative error of a few 1e-6
+    assert ((rows - ref_rows).abs() / ref_rows.abs().clamp(min=1.0)).max().item() < 1e-5
+    assert ((rows[:, 0] + rows[:, 2]) - (ref_rows[:, 0] + ref_rows[:, 2])).abs().max().item() < 6e-4 or sampler_type == "sde"   # 2 ulp of 2.8e3
+    if sampler_type == "sde":
+        assert rows[-1, 2].item() == 0.0          # weight_z of the last step (sampling/__init__.py:176-179)

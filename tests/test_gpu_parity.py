@@ -94,6 +94,65 @@ def test_golden_enhance_chain(golden_dir, name):
     eng.close()
 
 
+# ---- ncsnpp_v2 behind ScoreModel.forward's preconditioning, Schroedinger-bridge samplers ----
+V2_PRECOND = {
+    "plain": dict(loss_type="data_prediction", network_scaling=None, c_in="1", c_out="1", c_skip="0", sigma_data=0.1),
+    "edm": dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1),
+}
+
+
+def v2_engine(mode, sde="sbve", **pre):
+    return Engine(EngineConfig.ncsnpp_v2(attn_resolutions=(16,), mode=mode, sde=sde, sb_k=2.6, sb_c=0.4, **SMALL_E, **pre))
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("fp16_direct", 2e-2)])
+def test_golden_v2_forward_and_preconditioning(golden_dir, mode, tol):
+    z, sd = load_golden(golden_dir, "ncsnpp_v2_small")
+    x, y, t = (torch.from_numpy(z[k]).cuda() for k in ("x", "y", "t"))
+    for tag, pre in V2_PRECOND.items():
+        eng = v2_engine(mode, **pre)
+        eng.load_state_dict(sd)
+        if tag == "plain":
+            assert rel_l2(eng.dnn_forward(torch.cat([x, y], 1), t), z["dnn_out"]) < tol      # NCSNpp_v2.forward(x, y, t)
+        assert rel_l2(eng.model_forward(x, y, t), z[f"fwd_{tag}"]) < tol
+        eng.close()
+    eng = v2_engine(mode, sde="ouve", loss_type="score_matching", c_out="1/sigma")
+    eng.load_state_dict(sd)
+    assert rel_l2(eng.model_forward(x, y, t), z["fwd_ouve_score"]) < tol
+    eng.close()
+
+
+@pytest.mark.parametrize("tag", list(V2_PRECOND))
+@pytest.mark.parametrize("sampler_type", ["sde", "ode"])
+def test_golden_v2_sb_sampler(golden_dir, tag, sampler_type):
+    z, sd = load_golden(golden_dir, "ncsnpp_v2_small")
+    eng = v2_engine("fp32", **V2_PRECOND[tag])
+    eng.load_state_dict(sd)
+    y = torch.from_numpy(z["y"]).cuda()
+    noise = torch.stack(o_sde.make_noise(tuple(y.shape), 3, seed=13)).cuda() if sampler_type == "sde" else None
+    smp, n = eng.sb_sample(y, sampler_type=sampler_type, N=3, noise=noise)
+    assert n == int(z[f"sb_n_{sampler_type}_{tag}"])
+    # the first ODE step multiplies x and y (equal at that point) by +-2.25e3: ~2e-4 of fp32 noise in the reference itself
+    assert rel_l2(smp, z[f"sb_{sampler_type}_{tag}"]) < 1e-3
+    # Philox noise + CUDA-graph replay: finite, reproducible, and independent of the micro-batch split
+    a, _ = eng.sb_sample(y, sampler_type=sampler_type, N=3, seed=5)
+    b, _ = eng.sb_sample(y, sampler_type=sampler_type, N=3, seed=5)
+    assert torch.isfinite(torch.view_as_real(a)).all() and torch.equal(a, b)
+    eng.close()
+
+
+def test_golden_v2_pc_sampler_on_ouve(golden_dir):
+    z, sd = load_golden(golden_dir, "ncsnpp_v2_small")
+    eng = v2_engine("fp32", sde="ouve", loss_type="score_matching", c_out="1/sigma")
+    eng.load_state_dict(sd)
+    y = torch.from_numpy(z["y"]).cuda()
+    draws = o_sde.make_noise(tuple(y.shape), o_sde.n_noise_draws(3, "reverse_diffusion", "ald", 1), seed=7)
+    smp, nfe = eng.pc_sample(y, noise=torch.stack(draws).cuda(), N=3, predictor="reverse_diffusion", corrector="ald",
+                             corrector_steps=1, snr=0.5)
+    assert nfe == 6 and rel_l2(smp, z["pc_ouve_score"]) < 1e-3
+    eng.close()
+
+
 def test_golden_stft_ops(golden_dir):
     z = np.load(os.path.join(golden_dir, "ops.npz"))
     eng = Engine(EngineConfig(mode="fp32", **SMALL_E))

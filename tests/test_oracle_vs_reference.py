@@ -118,3 +118,25 @@ def test_sampler_schedule_matches_reference_scalars(sde_kw, N, snr):
         cy, cs, cz = coef[2 * i + 1].tolist()                  # predictor row: x_mean = x - (f - G^2 score)
         assert abs(cy + float(f.real)) <= 2e-6 * abs(float(f.real))
         assert abs(cz - float(G)) <= 2e-6 * float(G) and abs(cs - float(G) ** 2) <= 4e-6 * float(G) ** 2
+
+
+def test_config_v2_sbve_is_recovered_and_rebound():
+    """a live ScoreModel(backbone='ncsnpp_v2', sde='sbve') is read back completely (architecture, SB
+    parameters, preconditioning attributes) and install() rebinds forward / get_sb_sampler / enhance (host side only)."""
+    import sgmse_b200
+    from sgmse_b200 import config_from_score_model, Engine
+    m = refshim.make_score_model("ncsnpp_v2", seed=0, sde="sbve", k=2.6, c=0.4, sampler_type="sde", N=50,
+                                 loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm")
+    cfg = config_from_score_model(m)
+    assert cfg.backbone == "ncsnpp_v2" and not cfg.scale_by_sigma and cfg.sde == "sbve"
+    assert (cfg.sb_k, cfg.sb_c) == (2.6, 0.4) and cfg.nf == 128 and tuple(cfg.ch_mult) == (1, 1, 2, 2, 2, 2, 2)
+    assert (cfg.loss_type, cfg.network_scaling, cfg.c_in, cfg.c_out, cfg.c_skip) == ("data_prediction", "1/sigma", "edm", "edm", "edm")
+    eng = Engine(cfg)
+    assert eng.flatten_state_dict(m.dnn.state_dict()).numel() == eng.weights_numel()
+    ts, _, rows = eng.sampler_schedule(N=m.sde.N, kind="sb_sde")
+    assert ts.shape == (50,) and rows.shape == (50, 3) and abs(float(ts[-1]) - 1e-4) < 1e-9
+    sgmse_b200.install(m, engine=eng)
+    assert m.get_sb_sampler.__func__.__name__ == "get_sb_sampler" and "_sgmse_b200_engine" in m.__dict__
+    sgmse_b200.uninstall(m)
+    assert "get_sb_sampler" not in m.__dict__
+    eng.close()
