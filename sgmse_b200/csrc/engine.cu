@@ -549,7 +549,8 @@ struct Fwd {
         if (c.progressive_input_skip) {
           const Layer& l = next(LK_COMBINE);
           float4* pd = act4(B, ph / 2, pw / 2);
-          if (!dry) { launch_fir4(st, pyr_in, B, ph, pw, RS_DOWN, pd); count(); }
+          // the input pyramid starts at the network input c_in * (x, y) (ncsnpp.py:293-296): the first level carries c_in
+          if (!dry) { launch_fir4(st, pyr_in, B, ph, pw, RS_DOWN, pd, pyr_in == state ? in_scale : 1.f); count(); }
           pyr_in = pd; ph /= 2; pw /= 2;
           TensorDesc o = act(B, h.H, h.W, h.C, true);
           if (!dry) { launch_combine(st, pyr_in, l.small_w, l.small_b, h, o); count(); }

@@ -102,7 +102,8 @@ void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W
 void launch_combine(cudaStream_t st, const float4* pyr, const float* w, const float* bias, const TensorDesc& h,
                     TensorDesc& out);
 // 4-channel FIR resample of the input/output pyramids
-void launch_fir4(cudaStream_t st, const float4* in, int N, int H, int W, Resample rs, float4* out);
+// `scale` multiplies the result (the input pyramid of a c_in-scaled network input starts from the unscaled state)
+void launch_fir4(cudaStream_t st, const float4* in, int N, int H, int W, Resample rs, float4* out, float scale = 1.f);
 // out4 = conv3x3_{C->4}(act) + bias (+ addend);  w [9*C][4] (device), bias: HOST pointer to 4 floats
 // gn_ab != nullptr: `act` is the RAW tensor and silu(a*x+b) is applied while staging (only when out_conv_fuses_gn(act))
 bool out_conv_fuses_gn(const TensorDesc& act);
