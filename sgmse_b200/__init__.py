@@ -2,5 +2,7 @@
 ``ScoreModel.enhance()`` / ``get_pc_sampler()``.  See DESIGN.md and include/sgmse_b200.h."""
 from .engine import Engine, EngineConfig  # noqa: F401
 from .api import install, uninstall, engine_from_score_model, config_from_score_model  # noqa: F401
+from .service import BatchedEnhancer, plan_batches  # noqa: F401
 
-__all__ = ["Engine", "EngineConfig", "install", "uninstall", "engine_from_score_model", "config_from_score_model"]
+__all__ = ["Engine", "EngineConfig", "install", "uninstall", "engine_from_score_model", "config_from_score_model",
+           "BatchedEnhancer", "plan_batches"]

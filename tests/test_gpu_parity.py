@@ -153,6 +153,26 @@ def test_golden_v2_pc_sampler_on_ouve(golden_dir):
     eng.close()
 
 
+def test_batched_service_equals_clip_by_clip_enhancement(golden_dir):
+    """clips of different lengths bucketed by padded frame count and sampled together give, clip by
+    clip, exactly what enhancing each clip alone gives with the same (seed, utterance id)."""
+    from sgmse_b200 import BatchedEnhancer
+    z, sd = load_golden(golden_dir, "ncsnpp_small")
+    eng = small_engine("ncsnpp_small", "fp32", max_batch=2)
+    eng.load_state_dict(sd)
+    g = torch.Generator().manual_seed(31)
+    lengths = [2000, 4200, 1900, 2047, 4100]                 # 63/132/60/64/129 frames -> padded 64 / 192 / 64 / 64 / 192
+    waves = [0.1 * torch.randn(L, generator=g) for L in lengths]
+    kw = dict(N=2, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.5)
+    outs, ids = BatchedEnhancer(eng)(waves, seed=9, **kw)
+    assert sorted(ids) == list(range(5))
+    for w, o, i in zip(waves, outs, ids):
+        alone = eng.enhance(w[None].cuda(), seed=9, utt_offset=i, **kw)[0]
+        assert o.shape == w.shape and torch.isfinite(o).all()
+        assert torch.equal(o, alone)
+    eng.close()
+
+
 def test_golden_stft_ops(golden_dir):
     z = np.load(os.path.join(golden_dir, "ops.npz"))
     eng = Engine(EngineConfig(mode="fp32", **SMALL_E))
