@@ -161,18 +161,44 @@ def make_enhance(engine: Engine):
     return enhance
 
 
-def install(model, engine: Optional[Engine] = None, **kw) -> Engine:
-    """Route ``model.get_pc_sampler`` / ``model.enhance`` / ``model.forward`` through the engine."""
+def refresh(model):
+    """Re-snapshot the weights of an installed model (e.g. after a training epoch; call it with the model in ``eval()``
+    so that the EMA weights are the ones in ``model.dnn``, model.py:111-122)."""
+    eng = model.__dict__.get("_sgmse_b200_engine")
+    if eng is None:
+        raise RuntimeError("sgmse_b200 is not installed on this model")
+    sd = model.dnn.state_dict()
+    eng.load_state_dict(sd, on_device=next(iter(sd.values())).is_cuda)
+    return eng
+
+
+def install(model, engine: Optional[Engine] = None, rebind_forward: bool = True, refresh_on_eval: bool = False, **kw) -> Engine:
+    """Route ``model.get_pc_sampler`` / ``model.get_sb_sampler`` / ``model.enhance`` (and ``model.forward``) through the engine.
+
+    In-training evaluation (SURVEY.md §8f-3: ``validation_step`` calls ``self.enhance`` per file, model.py:205-257;
+    ``evaluate_model`` calls ``model.get_pc_sampler``, util/inference.py:16-63): install with
+    ``rebind_forward=False`` -- training steps keep the differentiable torch forward -- and ``refresh_on_eval=True`` --
+    every ``model.eval()`` (which swaps in the EMA weights) re-snapshots ``model.dnn`` into the engine."""
     if engine is None:
         engine = engine_from_score_model(model, **kw)
-    model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "enhance", "forward")}
+    model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "enhance", "forward", "eval")}
     model._sgmse_b200_engine = engine
     model.get_pc_sampler = types.MethodType(make_pc_sampler(engine, default_N=model.sde.N), model)
     model.enhance = types.MethodType(make_enhance(engine), model)
 
-    def forward(self, x_t, y, t):
-        return engine.model_forward(x_t, y, t)        # legacy: score; 'ncsnpp_v2': model.py:283-304
-    model.forward = types.MethodType(forward, model)
+    if rebind_forward:
+        def forward(self, x_t, y, t):
+            return engine.model_forward(x_t, y, t)    # legacy: score; 'ncsnpp_v2': model.py:283-304
+        model.forward = types.MethodType(forward, model)
+
+    if refresh_on_eval:
+        orig_eval = model.eval
+
+        def eval_and_refresh(self, *a, **k):
+            res = orig_eval(*a, **k)                  # EMA store + copy_to (model.py:111-122)
+            refresh(self)
+            return res
+        model.eval = types.MethodType(eval_and_refresh, model)
 
     def get_sb_sampler(self, sde, y, sampler_type="ode", N=None, **kwargs):
         # model.py:392-397 + sampling/__init__.py:145 (eps=1e-4, n_steps=50 defaults)

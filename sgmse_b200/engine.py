@@ -175,8 +175,8 @@ class Engine:
     def weights_numel(self) -> int:
         return int(self.lib.sgmse_b200_weights_numel(self._h))
 
-    def flatten_state_dict(self, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """fp32 CPU blob in manifest (= ``state_dict()``) order; verifies names and sizes."""
+    def flatten_state_dict(self, sd: Dict[str, torch.Tensor], device="cpu") -> torch.Tensor:
+        """fp32 blob in manifest (= ``state_dict()``) order on ``device``; verifies names and sizes."""
         man = self.manifest()
         missing = [k for k, _ in man if k not in sd]
         if missing:
@@ -189,7 +189,7 @@ class Engine:
             t = sd[k]
             if t.numel() != n:
                 raise ValueError(f"{k}: expected {n} elements, state dict has {tuple(t.shape)}")
-            parts.append(t.detach().reshape(-1).to(dtype=torch.float32, device="cpu"))
+            parts.append(t.detach().reshape(-1).to(dtype=torch.float32, device=device))
         return torch.cat(parts).contiguous()
 
     def _use_device(self):
@@ -207,8 +207,11 @@ class Engine:
         else:
             _lib.check(self.lib.sgmse_b200_load_weights(self._h, blob.data_ptr(), blob.numel()))
 
-    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
-        self.load_blob(self.flatten_state_dict(sd))
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], on_device: bool = False):
+        """``on_device``: flatten where the parameters live (no host round trip; used when weights are refreshed between
+        training epochs)."""
+        dev = next(iter(sd.values())).device if on_device else "cpu"
+        self.load_blob(self.flatten_state_dict(sd, device=dev))
 
     # ---- network ---------------------------------------------------------------------------------
     @staticmethod

@@ -140,3 +140,28 @@ def test_config_v2_sbve_is_recovered_and_rebound():
     sgmse_b200.uninstall(m)
     assert "get_sb_sampler" not in m.__dict__
     eng.close()
+
+
+def test_install_for_in_training_evaluation(model16k):
+    """with rebind_forward=False the differentiable torch forward stays in place (training steps), the
+    samplers and enhance() go to the engine, and every model.eval() re-snapshots model.dnn (EMA swap, model.py:111-122)."""
+    import sgmse_b200
+    from sgmse_b200 import config_from_score_model, Engine
+    eng = Engine(config_from_score_model(model16k))
+    loads = []
+    eng.load_blob = lambda blob: loads.append((blob.numel(), float(blob[0])))      # no GPU here: record instead of uploading
+    sgmse_b200.install(model16k, engine=eng, rebind_forward=False, refresh_on_eval=True)
+    try:
+        assert "forward" not in model16k.__dict__ and "enhance" in model16k.__dict__ and "get_pc_sampler" in model16k.__dict__
+        with torch.no_grad():
+            model16k.dnn.output_layer.weight.view(-1)[0] = 0.25                      # "an optimiser step"
+        model16k.eval()
+        assert loads and loads[-1] == (eng.weights_numel(), 0.25)                    # output_layer.weight leads the blob
+        model16k.train(True)                                                         # ScoreModel.train(mode, no_ema=False), model.py:98-109
+        model16k.eval(no_ema=True)
+        assert len(loads) == 2
+    finally:
+        sgmse_b200.uninstall(model16k)
+        model16k.eval()
+    assert "eval" not in model16k.__dict__ and "enhance" not in model16k.__dict__
+    eng.close()
