@@ -150,12 +150,44 @@ def golden_ops():
         wav48=_np(wav48), stft48=_np(S48), spec_fwd48=_np(dm48.spec_fwd(S48)), istft48=_np(dm48.istft(S48, 6000)))
 
 
+def golden_ode(name, src_name, backbone, cfg: NetConfig, seed):
+    """the probability-flow ODE sampler (sampling/__init__.py:72-143; scipy RK45 through host numpy
+    round trips) of the unmodified reference, prior draw injected, ``denoise=False`` (``denoise=True`` raises TypeError in
+    the reference, predictors.py:60).  The network is the one of ``src_name``.npz (same seed -> same init; asserted)."""
+    model = refshim.make_score_model(backbone=backbone, seed=seed, nf=cfg.nf, ch_mult=cfg.ch_mult,
+                                     image_size=cfg.image_size, attn_resolutions=cfg.attn_resolutions,
+                                     n_fft=126, hop_length=32)
+    z = np.load(os.path.join(OUT, src_name + ".npz"))
+    for k, v in model.dnn.state_dict().items():
+        assert np.array_equal(z["w/" + k], _np(v)), k
+    y = torch.from_numpy(z["y"])
+    out = {}
+    for tag, tol in (("loose", 1e-3), ("default", 1e-5)):
+        draws = sde_mod.make_noise(tuple(y.shape), 1, seed=17)
+        with refshim.injected_noise(draws):
+            smp, nfe = model.get_ode_sampler(y, denoise=False, device="cpu", rtol=tol, atol=tol)()
+        out[f"x_{tag}"] = _np(smp)
+        out[f"nfe_{tag}"] = np.int64(nfe)
+        out[f"tol_{tag}"] = np.float64(tol)
+        print(name, tag, "nfe", nfe)
+    try:
+        with refshim.injected_noise(sde_mod.make_noise(tuple(y.shape), 1, seed=17)):
+            model.get_ode_sampler(y, device="cpu", rtol=1e-3, atol=1e-3)()
+        out["denoise_default_raises"] = np.int64(0)
+    except TypeError as exc:
+        out["denoise_default_raises"] = np.int64(1)
+        print("denoise=True ->", type(exc).__name__, exc)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), y=_np(y), prior_seed=np.int64(17), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     golden_ops()
     golden_network("ncsnpp_small", "ncsnpp", NetConfig.ncsnpp(attn_resolutions=(16,), **SMALL), seed=1)
     golden_network("ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
     golden_v2("ncsnpp_v2_small", NetConfig.ncsnpp_v2(attn_resolutions=(16,), **SMALL), seed=3)
+    golden_ode("ode_small", "ncsnpp_small", "ncsnpp", NetConfig.ncsnpp(attn_resolutions=(16,), **SMALL), seed=1)
+    golden_ode("ode48k_small", "ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
 
 
 if __name__ == "__main__":

@@ -142,3 +142,48 @@ def test_v2_pc_sampler_on_ouve(golden_dir):
     with torch.no_grad():
         got, nfe = sde_mod.pc_sample(fn, y, ou, N=3, noise=draws)
     assert nfe == 6 and _rel(got, z["pc_ouve_score"]) < 1e-4
+
+
+# ---- probability-flow ODE sampler ------------------------------------------------------------
+def test_rk45_restatement_equals_scipy():
+    """The integrator is third-party (scipy.integrate.solve_ivp, method RK45): the oracle's restatement of its
+    published algorithm takes the same steps, the same number of evaluations and returns the same state, bit for bit,
+    on a complex system whose right-hand side is rounded to complex64 like the sampler's."""
+    from scipy.integrate import solve_ivp
+    from oracle import ode
+    rng = np.random.default_rng(0)
+    n = 200
+    M = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) * 0.3 / np.sqrt(n)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+
+    def fun(t, y):
+        return (-1.5 * y + M @ np.tanh(y.real) + 1j * np.sin(3 * t) * b).astype(np.complex64)
+
+    y0 = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    for rtol, atol, tb in [(1e-5, 1e-5, 0.03), (1e-3, 1e-6, 0.03), (1e-8, 1e-10, 0.5), (1e-5, 1e-5, 2.0), (1e-5, 1e-5, 1.0)]:
+        s = solve_ivp(fun, (1.0, tb), y0, rtol=rtol, atol=atol, method="RK45")
+        r = ode.rk45_solve(fun, 1.0, y0, tb, rtol=rtol, atol=atol)
+        assert (s.nfev, s.status) == (r.nfev, r.status)
+        assert np.array_equal(s.y[:, -1], r.y)
+        if tb != 1.0:                                   # (an empty interval is reported by scipy as one zero-length step)
+            assert np.array_equal(np.diff(s.t), np.asarray(r.hs))
+
+
+@pytest.mark.parametrize("name,src", [("ode_small", "ncsnpp_small"), ("ode48k_small", "ncsnpp48k_small")])
+def test_ode_sampler(golden_dir, name, src):
+    """oracle/ode.py against get_ode_sampler() of the unmodified reference (denoise=False, prior draw injected):
+    same number of function evaluations, same state."""
+    from oracle import ode
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    _, sd = _load(golden_dir, src)
+    cfg = CASES[src]
+    y = torch.from_numpy(z["y"])
+    prior = sde_mod.make_noise(tuple(y.shape), 1, seed=int(z["prior_seed"]))[0]
+    tol = float(z["tol_loose"])
+    x, nfe = ode.ode_sample(lambda a, b, c: ncsnpp.score(sd, cfg, a, b, c), y, sde_mod.OUVE(), eps=0.03, rtol=tol,
+                            atol=tol, prior_noise=prior)
+    assert nfe == int(z["nfe_loose"])
+    assert _rel(x, z["x_loose"]) < 1e-6
+    assert int(z["denoise_default_raises"]) == 1        # the reference's default denoise=True is a TypeError
+    with pytest.raises(TypeError):
+        ode.ode_sample(lambda a, b, c: None, y, sde_mod.OUVE(), prior_noise=prior, denoise=True)
