@@ -23,6 +23,11 @@
  *                                    with sampler.kind = SB_ODE / SB_SDE: sampling.get_sb_sampler()
  *                                    sgmse/sampling/__init__.py:145-249, SBVESDE sdes.py:235-312,
  *                                    ScoreModel.get_sb_sampler model.py:392-397
+ *   sgmse_b200_ode_sample            sampling.get_ode_sampler()/ode_sampler sgmse/sampling/__init__.py:72-143 (probability-flow
+ *                                    ODE, RSDE.sde sdes.py:113-127; the scipy RK45 loop with its per-evaluation host numpy
+ *                                    round trips :117-141), ScoreModel.get_ode_sampler model.py:370-390
+ *   sgmse_b200_rk45_host             scipy.integrate.solve_ivp(method='RK45') as called at sampling/__init__.py:127-130
+ *                                    (the controller sgmse_b200_ode_sample runs, on a host callback; test hook)
  *   sgmse_b200_analysis              _stft + _forward_transform + pad_spec sgmse/data_module.py:162-175,212-214,
  *                                    sgmse/util/other.py:76-90, model.py:435-438
  *   sgmse_b200_synthesis             to_audio (spec_back + istft) + renorm sgmse/data_module.py:177-188,216-218,
@@ -144,6 +149,32 @@ int sgmse_b200_noise_draws(const sgmse_b200_sampler* s);
  * denoiser) or the data prediction, exactly as model.py:283-304.  x_t, y, out: c64 [B,1,F,T] (device), t: f32 [B]. */
 int sgmse_b200_model_forward(sgmse_b200_engine* e, const void* x_t, const void* y, const float* t, void* out, int B,
                              int F, int T, void* stream);
+/* Probability-flow ODE sampler (sampling/__init__.py:72-143 with denoise=False; the reference's default denoise=True
+ * raises TypeError at predictors.py:60, the host mirror reproduces that).  x(1) = y + std(1) z, then
+ * dx/dt = theta (y - x) - 0.5 g(t)^2 score(x, y, t) from t = 1 to t = eps with scipy's RK45 (Dormand-Prince 5(4), rtol /
+ * atol error control, RMS norm over ALL bins of the batch: the utterances of one call share one adaptive step sequence,
+ * as in the reference).  The integrator state is complex128 and stays in HBM; one double per norm crosses to the host.
+ * OUVE SDE and the 'ncsnpp' / 'ncsnpp_48k' backbones. */
+typedef struct sgmse_b200_ode {
+  double rtol, atol;         /* 1e-5, 1e-5 (sampling/__init__.py:74) */
+  double eps;                /* end time; ScoreModel.get_ode_sampler passes t_eps = 0.03 (model.py:375) */
+  int max_attempts;          /* bound on Runge-Kutta step attempts, accepted + rejected (<= 0: 100000) */
+  unsigned long long seed;   /* Philox seed of the prior draw (ignored with injected noise) */
+  int utt_offset;            /* global index of utterance 0 */
+} sgmse_b200_ode;
+/* y, out: c64 [B,1,F,T] (device).  prior_noise: NULL (Philox) or device c64 [B,1,F,T], the one draw of prior_sampling
+ * (sdes.py:224-229).  *nfe = number of network evaluations (scipy's nfev).  stats (nullable) receives
+ * {accepted steps, rejected attempts, status (0 reached eps, -1 step size underflow = scipy "failed", whose last state
+ * the reference silently returns, -2 max_attempts exhausted), 0}. */
+int sgmse_b200_ode_sample(sgmse_b200_engine* e, const void* y, int B, int F, int T, const sgmse_b200_ode* o,
+                          const void* prior_noise, void* out, int* nfe, int stats[4], void* stream);
+/* The same controller on a host right-hand side (host-only; works without a GPU).  y: n complex128 values,
+ * interleaved (re, im), in/out.  rhs(t, y, dydt, n, user) fills dydt.  Mirrors
+ * solve_ivp(rhs, (t0, t_bound), y, method='RK45', rtol=rtol, atol=atol): y receives solution.y[:, -1]. */
+typedef void (*sgmse_b200_ode_rhs)(double t, const double* y, double* dydt, long long n, void* user);
+int sgmse_b200_rk45_host(sgmse_b200_ode_rhs rhs, void* user, double t0, double t_bound, double* y, long long n,
+                         double rtol, double atol, int max_attempts, int* nfev, int stats[4]);
+
 /* The sampler's host-computed schedule, exactly as the captured launch sequence uses it (host-only; works without a
  * GPU): ts[N] = torch.linspace(1, t_eps, N) in fp32 (sampling/__init__.py:56), prior_std = OUVESDE._std(1)
  * (sdes.py:206-229), and one (cy, cs, cz) row per state update in execution order -- per step the corrector steps, then

@@ -37,6 +37,15 @@ class Sampler(C.Structure):
     ]
 
 
+class Ode(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("eps", C.c_double), ("max_attempts", C.c_int),
+                ("seed", C.c_ulonglong), ("utt_offset", C.c_int)]
+
+
+# right-hand side of sgmse_b200_rk45_host: rhs(t, y, dydt, n, user)
+ODE_RHS = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_longlong, C.c_void_p)
+
+
 # every symbol include/sgmse_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -56,6 +65,10 @@ SYMBOLS = {
     "sgmse_b200_noise_draws": (C.c_int, [C.POINTER(Sampler)]),
     "sgmse_b200_model_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "sgmse_b200_sampler_schedule": (C.c_int, [_P, C.POINTER(Sampler), _P, _P, _P, C.c_int, C.POINTER(C.c_int)]),
+    "sgmse_b200_ode_sample": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Ode), _P, _P, C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int * 4), _P]),
+    "sgmse_b200_rk45_host": (C.c_int, [ODE_RHS, _P, C.c_double, C.c_double, _P, C.c_longlong, C.c_double, C.c_double,
+                                       C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int * 4)]),
     "sgmse_b200_padded_frames": (C.c_int, [_P, C.c_int]),
     "sgmse_b200_analysis": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "sgmse_b200_synthesis": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),

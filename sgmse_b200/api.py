@@ -9,6 +9,8 @@
 * ``model.enhance(y, sampler_type, predictor, corrector, N, corrector_steps, snr, timeit, **kw)``
   (model.py:426-465) -> ``np.ndarray [T]`` or ``(x_hat, nfe, rtf)``,
 * ``model.forward(x_t, y, t)`` (legacy branch, model.py:307-310),
+* ``model.get_ode_sampler(y, N=None, minibatch=None, **kw)`` (model.py:370-390; OUVE SDE, score backbones) -> callable
+  returning ``(sample, nfe)`` -- the probability-flow ODE with scipy's RK45 restated on the device,
 
 to the B200 engine.  ``sgmse/model.py`` itself is untouched; ``uninstall(model)`` restores the
 original bound methods.  The predictor / corrector names are the reference registry names
@@ -131,6 +133,39 @@ def make_pc_sampler(engine: Engine, default_N: int):
     return get_pc_sampler
 
 
+def make_ode_sampler(engine: Engine):
+    def get_ode_sampler(self, y, N=None, minibatch=None, **kwargs):
+        """ScoreModel.get_ode_sampler (model.py:370-390) -> sampling.get_ode_sampler (sampling/__init__.py:72-143).
+        ``N`` only lands in the copied SDE (unused by the ODE solver); ``eps`` defaults to ``t_eps`` (model.py:375).
+        Each minibatch is its own ODE system (own adaptive step sequence), as in the reference."""
+        kw = dict(rtol=kwargs.get("rtol", 1e-5), atol=kwargs.get("atol", 1e-5), eps=kwargs.get("eps", engine.cfg.t_eps),
+                  denoise=kwargs.get("denoise", True), method=kwargs.get("method", "RK45"),
+                  seed=kwargs.get("seed", int(torch.randint(0, 2 ** 62, (1,)).item())))
+        noise = kwargs.get("noise", None)               # c64 [B,1,F,T]: the prior draw
+
+        if minibatch is None:
+            def ode_sampler():
+                with torch.no_grad():
+                    return engine.ode_sample(y, prior_noise=noise, **kw)
+            return ode_sampler
+
+        M = y.shape[0]
+
+        def batched_sampling_fn():
+            samples, ns = [], []
+            for i in range(int(ceil(M / minibatch))):
+                sl = slice(i * minibatch, (i + 1) * minibatch)
+                smp, n = engine.ode_sample(y[sl], prior_noise=noise[sl] if noise is not None else None,
+                                           utt_offset=i * minibatch, **kw)
+                samples.append(smp)
+                ns.append(n)
+            # (the reference returns `sample`, the LAST minibatch only, model.py:388-389 -- a typo for `samples`;
+            #  the concatenation is what its PC twin returns, model.py:365-367)
+            return torch.cat(samples, dim=0), ns
+        return batched_sampling_fn
+    return get_ode_sampler
+
+
 def make_enhance(engine: Engine):
     def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="ald", N=30,
                 corrector_steps=1, snr=0.5, timeit=False, **kwargs):
@@ -145,9 +180,18 @@ def make_enhance(engine: Engine):
                 raise ValueError("Invalid type. Choose 'ode' or 'sde'.")
             x_hat = engine.enhance(yy.detach().cpu().float(), N=self.sde.N, kind="sb_" + st, sb_eps=1e-4, sb_n_steps=50, **common)
             sb_nfe = 50
+        elif getattr(self.sde, "sampler_type", "pc") == "ode":      # model.py:446-447: get_ode_sampler(Y, N=N, **kwargs)
+            wav = yy.detach().float().to(engine.device or "cuda")
+            x_parts = []
+            ode_kw = {k: kwargs[k] for k in ("rtol", "atol", "eps", "method") if k in kwargs}
+            for b in range(wav.shape[0]):                                # enhance() is per file in the reference
+                Y, norm = engine.analysis(wav[b:b + 1], pad_mode=common["pad_mode"])
+                X, sb_nfe = engine.ode_sample(Y, denoise=kwargs.get("denoise", True), seed=common["seed"], utt_offset=b, **ode_kw)
+                x_parts.append(engine.synthesis(X, norm, wav.shape[1]))
+            x_hat = torch.cat(x_parts).cpu()
         else:
             if getattr(self.sde, "sampler_type", "pc") != "pc":
-                raise NotImplementedError("only the PC sampler is accelerated on the OUVE SDE (sde.sampler_type must be 'pc')")
+                raise ValueError("Invalid sampler type for SGMSE sampling: {}".format(sampler_type))   # model.py:448-449
             x_hat = engine.enhance(yy.detach().cpu().float(), N=N, predictor=predictor, corrector=corrector,
                                    corrector_steps=corrector_steps, snr=snr, **common)
             sb_nfe = None
@@ -181,9 +225,11 @@ def install(model, engine: Optional[Engine] = None, rebind_forward: bool = True,
     every ``model.eval()`` (which swaps in the EMA weights) re-snapshots ``model.dnn`` into the engine."""
     if engine is None:
         engine = engine_from_score_model(model, **kw)
-    model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "enhance", "forward", "eval")}
+    model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "get_ode_sampler", "enhance", "forward", "eval")}
     model._sgmse_b200_engine = engine
     model.get_pc_sampler = types.MethodType(make_pc_sampler(engine, default_N=model.sde.N), model)
+    if type(model.sde).__name__ == "OUVESDE" and engine.cfg.backbone != "ncsnpp_v2":
+        model.get_ode_sampler = types.MethodType(make_ode_sampler(engine), model)
     model.enhance = types.MethodType(make_enhance(engine), model)
 
     if rebind_forward:

@@ -18,8 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libsgmse_b200.so"
-SOURCES = ["gn.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_tc4.cu", "conv_tc5.cu", "conv_tc6.cu", "small.cu", "attn.cu", "misc.cu", "engine.cu"]
-HEADERS = ["common.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "sgmse_b200.h")]
+SOURCES = ["gn.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_tc4.cu", "conv_tc5.cu", "conv_tc6.cu", "small.cu", "attn.cu", "misc.cu", "ode.cu", "engine.cu"]
+HEADERS = ["common.cuh", "kernels.h", "engine.h", "rk45.h", os.path.join("..", "..", "include", "sgmse_b200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CUDA_LIB = os.environ.get("CUDA_LIB", "/usr/local/cuda/lib64")

@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "engine.h"
+#include "rk45.h"
 
 #include <math.h>
 #include <string.h>
@@ -214,10 +215,22 @@ void pack_conv(Engine& e, const std::vector<PackSrc>& srcs, int cout, bool out_m
 }
 
 void ensure_lanes(Engine& e, int want);
+void clear_graphs(Engine& e);
+
+void free_ode(Engine& e) {
+  OdeBuffers& o = e.ode;
+  cudaFree(o.y); cudaFree(o.y_new); cudaFree(o.stage); cudaFree(o.partial);
+  for (int i = 0; i < 7; ++i) cudaFree(o.k[i]);
+  if (o.partial_host) cudaFreeHost(o.partial_host);
+  o = OdeBuffers{};
+}
 
 void free_workspace(Engine& e) {
   for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec);
   e.graphs.clear();
+  for (auto& g : e.fwd_graphs) cudaGraphExecDestroy(g.second.exec);
+  e.fwd_graphs.clear();
+  free_ode(e);
   for (auto& p : e.fft_plans) cufftDestroy(p.second);
   e.fft_plans.clear();
   cudaFree(e.arena.base); e.arena = Arena{};
@@ -235,6 +248,7 @@ void free_workspace(Engine& e) {
 void free_weights(Engine& e) {
   if (!e.owns_weights) return;
   if (e.lanes.size() > 1) ensure_lanes(e, 1);   // shadow engines hold pointers into the weights being freed
+  clear_graphs(e);                              // ... and so do the kernel arguments baked into captured graphs
   for (void* p : e.dev_allocs) cudaFree(p);
   e.dev_allocs.clear();
   if (e.blob_dev) { cudaFree(e.blob_dev); e.blob_dev = nullptr; }
@@ -601,6 +615,8 @@ struct Fwd {
 void clear_graphs(Engine& e) {
   for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec);
   e.graphs.clear();
+  for (auto& g : e.fwd_graphs) cudaGraphExecDestroy(g.second.exec);
+  e.fwd_graphs.clear();
   ++e.generation;
 }
 
@@ -628,7 +644,8 @@ void ensure_lanes(Engine& e, int want) {
     l->state = nullptr; l->xmean = nullptr; l->temb_table = nullptr; l->temb_scratch = nullptr; l->t_dev = nullptr;
     l->coef_dev = nullptr; l->rng_dev = nullptr; l->lv_scratch = nullptr; l->dbg_flag = nullptr;
     l->persist_px = 0; l->persist_rows = 0;
-    l->graphs.clear(); l->fft_plans.clear();
+    l->graphs.clear(); l->fwd_graphs.clear(); l->fft_plans.clear();
+    l->ode = OdeBuffers{};
     for (int i = 0; i < 4; ++i) { l->stft_buf[i] = nullptr; l->stft_cap[i] = 0; }
     l->own_stream = nullptr;
     l->lanes.clear(); l->lane_streams.clear(); l->lane_events.clear();
@@ -1107,6 +1124,212 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
 }
 
 // ------------------------------------------------------------------------------------------------
+// probability-flow ODE sampler: sampling/__init__.py:72-143 without the host round trips
+// ------------------------------------------------------------------------------------------------
+__global__ void set_float_kernel(float* dst, float v) { *dst = v; }
+
+void ensure_ode(Engine& e, size_t px) {
+  OdeBuffers& o = e.ode;
+  if (!o.partial) {
+    CUDA_OK(cudaMalloc((void**)&o.partial, kOdeNormBlocks * sizeof(double)));
+    CUDA_OK(cudaHostAlloc((void**)&o.partial_host, kOdeNormBlocks * sizeof(double), cudaHostAllocDefault));
+  }
+  if (px <= o.cap_px) return;
+  if (o.y) {
+    CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(o.y); cudaFree(o.y_new); cudaFree(o.stage);
+    for (int i = 0; i < 7; ++i) { cudaFree(o.k[i]); o.k[i] = nullptr; }
+    o.y = nullptr; o.y_new = nullptr; o.stage = nullptr; o.cap_px = 0;
+  }
+  CUDA_OK(cudaMalloc((void**)&o.y, px * sizeof(double2)));
+  CUDA_OK(cudaMalloc((void**)&o.y_new, px * sizeof(double2)));
+  CUDA_OK(cudaMalloc((void**)&o.stage, px * sizeof(float2)));
+  for (int i = 0; i < 7; ++i) CUDA_OK(cudaMalloc((void**)&o.k[i], px * sizeof(float2)));
+  o.cap_px = px;
+}
+
+// One score-network evaluation on e.state with the time-embedding row e.temb_table[0].  The launch sequence of a
+// shape is captured the first time it runs (that first evaluation itself is eager) and replayed afterwards: an ODE
+// solve is hundreds of evaluations of the same sequence with nothing but t changing, and t lives in device memory
+// (temb row, drift coefficients are kernel arguments of the un-captured drift kernel).
+const float4* forward_on_state(Engine& e, int Bc, int F, int T, cudaStream_t st) {
+  Fwd f{e, st, e.temb_table, 0, false, e.cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
+  const bool graph_ok = e.cfg.use_graphs && !e.time_convs && !e.record_taps && st != nullptr;
+  if (!graph_ok) return f.run(e.state, Bc, F, T);
+  const auto key = std::make_tuple(Bc, F, T);
+  auto it = e.fwd_graphs.find(key);
+  if (it != e.fwd_graphs.end()) {
+    CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+    ++e.graph_launches;
+    e.kernel_launches += it->second.kernel_nodes;
+    e.launches_this_forward = it->second.kernel_nodes;
+    e.tc_convs = it->second.tc_convs; e.direct_convs = it->second.direct_convs;
+    return it->second.out;
+  }
+  const float4* p = f.run(e.state, Bc, F, T);                  // eager: sets function attributes, surfaces launch errors
+  const long long saved = e.kernel_launches;
+  cudaGraph_t g = nullptr;
+  CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const float4* pc = nullptr;
+  try {
+    pc = f.run(e.state, Bc, F, T);
+  } catch (...) {
+    cudaStreamEndCapture(st, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
+  }
+  CUDA_OK(cudaStreamEndCapture(st, &g));
+  cudaGraphExec_t ge = nullptr;
+  const cudaError_t ierr = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  CUDA_OK(ierr);
+  const long long nodes = e.kernel_launches - saved;
+  e.kernel_launches = saved;                                    // recorded, not executed
+  if (pc != p) { cudaGraphExecDestroy(ge); SG_CHECK(false, "internal: workspace replay moved the network output"); }
+  e.fwd_graphs.emplace(key, FwdGraph{ge, p, nodes, e.tc_convs, e.direct_convs});
+  return p;
+}
+
+struct OdeDeviceOps {
+  Engine& e;
+  const float2* Y;
+  int B, F, T;
+  cudaStream_t st;
+  size_t px1, total;
+  double2 *y, *y_new;
+  float2* k[7];
+
+  size_t size() const { return total; }
+  OdeK kk() const { OdeK K; for (int i = 0; i < 7; ++i) K.k[i] = k[i]; return K; }
+  void combine(int s, const double* a, double h, bool to_new) {
+    OdeCoefs c{};
+    for (int j = 0; j < s; ++j) c.a[j] = a[j];
+    launch_ode_combine(st, y, kk(), s, c, h, total, e.ode.stage, to_new ? y_new : nullptr);
+    ++e.kernel_launches;
+  }
+  void eval(double t, int slot) {
+    const sgmse_b200_config& c = e.cfg;
+    const float tf = (float)t;                                  // vec_t = torch.ones(B) * t (sampling/__init__.py:122)
+    set_float_kernel<<<1, 1, 0, st>>>(e.t_dev, tf);
+    CUDA_OK(cudaGetLastError());
+    launch_temb(st, temb_weights(e), e.t_dev, 1, e.temb_scratch, e.temb_table);
+    e.kernel_launches += 3;
+    const double ls = log((double)c.sigma_max / c.sigma_min);
+    const double g = c.sigma_min * pow((double)c.sigma_max / c.sigma_min, (double)tf) * sqrt(2 * ls);   // sdes.py:188-196
+    const float cs = (float)(0.5 * g * g);                      // -g^2 * score * 0.5 with score = -dnn (sdes.py:116-117)
+    const float inv_t = 1.0f / tf;
+    const int mb = std::max(1, c.max_batch);
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int Bc = std::min(mb, B - b0);
+      launch_pack_state(st, e.ode.stage + b0 * px1, Y + b0 * px1, Bc, F, T, e.state); ++e.kernel_launches;
+      const float4* p = forward_on_state(e, Bc, F, T, st);
+      launch_ode_drift(st, e.state, p, Bc, F, T, e.out_layer, inv_t, c.theta, cs, k[slot] + b0 * px1); ++e.kernel_launches;
+    }
+  }
+  double finish_norm() {
+    CUDA_OK(cudaMemcpyAsync(e.ode.partial_host, e.ode.partial, kOdeNormBlocks * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    double s = 0.0;
+    for (int i = 0; i < kOdeNormBlocks; ++i) s += e.ode.partial_host[i];
+    return sqrt(s / (double)total);
+  }
+  double norm_init(int which, double rtol, double atol) {
+    launch_ode_norm(st, which, y, y_new, kk(), OdeCoefs{}, 0.0, rtol, atol, total, e.ode.partial); ++e.kernel_launches;
+    return finish_norm();
+  }
+  double norm_err(const double* E, double h, double rtol, double atol) {
+    OdeCoefs c{};
+    for (int j = 0; j < 7; ++j) c.a[j] = E[j];
+    launch_ode_norm(st, 3, y, y_new, kk(), c, h, rtol, atol, total, e.ode.partial); ++e.kernel_launches;
+    return finish_norm();
+  }
+  void accept() { std::swap(y, y_new); std::swap(k[0], k[6]); }
+};
+
+void ode_sample(Engine& e, const float2* Y, int B, int F, int T, const sgmse_b200_ode& o, const float2* prior_noise,
+                float2* out, int* nfe, int* stats, cudaStream_t st_in) {
+  SG_CHECK(e.loaded, "weights not loaded");
+  SG_CHECK(e.cfg.sde_kind == SGMSE_B200_SDE_OUVE, "the probability-flow ODE sampler is implemented for the 'ouve' SDE");
+  SG_CHECK(!is_v2(e), "the probability-flow ODE sampler is implemented for the score models 'ncsnpp' / 'ncsnpp_48k'");
+  SG_CHECK(o.atol >= 0 && o.rtol >= 0, "`atol` must be positive.");                      // scipy validate_tol
+  SG_CHECK(o.eps > 0 && o.eps <= 1, "eps must lie in (0, T=1]");
+  cudaStream_t st = st_in;
+  if (!st) {                                        // stream capture is illegal on the legacy default stream
+    if (!e.own_stream) CUDA_OK(cudaStreamCreate(&e.own_stream));
+    st = e.own_stream;
+  }
+  struct SyncOnExit { cudaStream_t s; bool on; ~SyncOnExit() { if (on) cudaStreamSynchronize(s); } } sync_guard{st, st_in == nullptr};
+  const int mb = std::max(1, e.cfg.max_batch);
+  const size_t px1 = (size_t)F * T, total = (size_t)B * px1;
+  ensure_arena(e, std::min(B, mb), F, T);
+  ensure_persistent(e, (size_t)std::min(B, mb) * px1, std::max(mb, 64));
+  ensure_ode(e, total);
+  const float std1 = (float)ouve_std(e.cfg, 1.0);
+  for (int b0 = 0; b0 < B; b0 += mb) {              // x(T) = y + z * std(1)  (sdes.py:224-229), fp32 like the reference
+    const int Bc = std::min(mb, B - b0);
+    RngParams rp{o.seed, o.utt_offset + b0, 0};
+    CUDA_OK(cudaMemcpyAsync(e.rng_dev, &rp, sizeof(rp), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    launch_pack_state(st, Y + b0 * px1, Y + b0 * px1, Bc, F, T, e.state);
+    launch_prior(st, e.state, Bc, F, T, std1, prior_noise ? prior_noise + b0 * px1 : nullptr, e.rng_dev, 0);
+    launch_ode_init(st, e.state, (size_t)Bc * px1, e.ode.y + b0 * px1);
+    e.kernel_launches += 3;
+    CUDA_OK(cudaStreamSynchronize(st));             // rng_dev is rewritten by the next chunk
+  }
+  OdeDeviceOps ops{e, Y, B, F, T, st, px1, total, e.ode.y, e.ode.y_new,
+                   {e.ode.k[0], e.ode.k[1], e.ode.k[2], e.ode.k[3], e.ode.k[4], e.ode.k[5], e.ode.k[6]}};
+  const rk45::Result r = rk45::solve(ops, 1.0, o.eps, o.rtol, o.atol, o.max_attempts > 0 ? o.max_attempts : 100000);
+  launch_ode_finish(st, ops.y, total, out); ++e.kernel_launches;
+  if (nfe) *nfe = r.nfev;
+  if (stats) { stats[0] = r.steps; stats[1] = r.rejected; stats[2] = r.status; stats[3] = 0; }
+}
+
+// The same controller on a host callback (test hook: pins rk45.h against scipy without a GPU).
+struct OdeHostOps {
+  sgmse_b200_ode_rhs rhs;
+  void* user;
+  long long n;
+  std::vector<double> y, y_new, stage, k[7];
+  size_t size() const { return (size_t)n; }
+  void combine(int s, const double* a, double h, bool to_new) {
+    for (long long i = 0; i < 2 * n; ++i) {
+      double d = 0.0;
+      for (int j = 0; j < s; ++j) d += a[j] * k[j][i];
+      stage[i] = y[i] + d * h;
+    }
+    if (to_new) y_new = stage;
+  }
+  void eval(double t, int slot) { rhs(t, stage.data(), k[slot].data(), n, user); }
+  double rms(const std::vector<double>& v, const std::vector<double>* other_for_scale, double rtol, double atol) const {
+    double s = 0.0;
+    for (long long i = 0; i < n; ++i) {
+      double ay = hypot(y[2 * i], y[2 * i + 1]);
+      if (other_for_scale) ay = fmax(ay, hypot((*other_for_scale)[2 * i], (*other_for_scale)[2 * i + 1]));
+      const double sc = atol + ay * rtol, a = v[2 * i] / sc, b = v[2 * i + 1] / sc;
+      s += a * a + b * b;
+    }
+    return sqrt(s / (double)n);
+  }
+  double norm_init(int which, double rtol, double atol) {
+    if (which == 0) return rms(y, nullptr, rtol, atol);
+    if (which == 1) return rms(k[0], nullptr, rtol, atol);
+    std::vector<double> d((size_t)2 * n);
+    for (long long i = 0; i < 2 * n; ++i) d[i] = k[1][i] - k[0][i];
+    return rms(d, nullptr, rtol, atol);
+  }
+  double norm_err(const double* E, double h, double rtol, double atol) {
+    std::vector<double> d((size_t)2 * n);
+    for (long long i = 0; i < 2 * n; ++i) {
+      double v = 0.0;
+      for (int j = 0; j < 7; ++j) v += E[j] * k[j][i];
+      d[i] = v * h;
+    }
+    return rms(d, &y_new, rtol, atol);
+  }
+  void accept() { y.swap(y_new); k[0].swap(k[6]); }
+};
+
+// ------------------------------------------------------------------------------------------------
 // STFT front / back end
 // ------------------------------------------------------------------------------------------------
 void ensure_stft_buf(Engine& e, int slot, size_t bytes) {
@@ -1366,6 +1589,31 @@ int sgmse_b200_pc_sample(sgmse_b200_engine* e, const void* y, int B, int F, int 
   const int mb = std::max(1, e->cfg.max_batch);
   ensure_stft_buf(*e, 3, (size_t)std::min(B, mb) * F * T * 8);
   pc_sample(*e, (const float2*)y, B, F, T, *s, (const float2*)noise, (float2*)out, nfe, (cudaStream_t)stream);
+  API_END
+}
+
+int sgmse_b200_ode_sample(sgmse_b200_engine* e, const void* y, int B, int F, int T, const sgmse_b200_ode* o,
+                          const void* prior_noise, void* out, int* nfe, int stats[4], void* stream) {
+  API_BEGIN
+  SG_CHECK(e && y && o && out && B > 0, "bad argument");
+  ode_sample(*e, (const float2*)y, B, F, T, *o, (const float2*)prior_noise, (float2*)out, nfe, stats, (cudaStream_t)stream);
+  API_END
+}
+
+int sgmse_b200_rk45_host(sgmse_b200_ode_rhs rhs, void* user, double t0, double t_bound, double* y, long long n,
+                         double rtol, double atol, int max_attempts, int* nfev, int stats[4]) {
+  API_BEGIN
+  SG_CHECK(rhs && (y || n == 0) && n >= 0, "bad argument");
+  SG_CHECK(atol >= 0, "`atol` must be positive.");
+  OdeHostOps ops{rhs, user, n};
+  ops.y.assign(y, y + 2 * n);
+  ops.y_new.assign((size_t)2 * n, 0.0);
+  ops.stage.assign((size_t)2 * n, 0.0);
+  for (auto& k : ops.k) k.assign((size_t)2 * n, 0.0);
+  const rk45::Result r = rk45::solve(ops, t0, t_bound, rtol, atol, max_attempts > 0 ? max_attempts : 100000);
+  for (long long i = 0; i < 2 * n; ++i) y[i] = ops.y[i];
+  if (nfev) *nfev = r.nfev;
+  if (stats) { stats[0] = r.steps; stats[1] = r.rejected; stats[2] = r.status; stats[3] = 0; }
   API_END
 }
 

@@ -86,6 +86,23 @@ struct GraphEntry {
   long long kernel_nodes;
 };
 
+struct FwdGraph {            // one captured score-network evaluation on e.state (ODE sampler: t changes per evaluation)
+  cudaGraphExec_t exec;
+  const float4* out;         // the network's 4-channel output pyramid (arena address, stable per shape)
+  long long kernel_nodes;
+  long long tc_convs, direct_convs;
+};
+
+struct OdeBuffers {          // state of the probability-flow ODE sampler for one whole batch
+  double2* y = nullptr;      // complex128 like scipy's integrator state
+  double2* y_new = nullptr;
+  float2* k[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // complex64 stage derivatives
+  float2* stage = nullptr;   // complex64 argument of the next evaluation
+  double* partial = nullptr; // [kOdeNormBlocks] device
+  double* partial_host = nullptr;   // pinned
+  size_t cap_px = 0;
+};
+
 }  // namespace sgmse
 
 struct sgmse_b200_engine {
@@ -123,6 +140,8 @@ struct sgmse_b200_engine {
   int persist_rows = 0;                       // capacity of temb_table in rows
 
   std::map<sgmse::GraphKey, sgmse::GraphEntry> graphs;
+  std::map<std::tuple<int, int, int>, sgmse::FwdGraph> fwd_graphs;   // (B, F, T) -> captured single evaluation
+  sgmse::OdeBuffers ode;
   std::map<std::tuple<int, int, int>, size_t> arena_need;   // workspace bytes per (B, F, T)
   cudaStream_t own_stream = nullptr;
   std::map<std::pair<int, int>, cufftHandle> fft_plans;   // (type<<28 | n_fft, batch)

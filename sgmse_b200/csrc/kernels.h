@@ -180,6 +180,22 @@ void launch_langevin_coef(cudaStream_t st, const float4* pyr, int N, int H, int 
                           const float2* noise, const RngParams* rng, int draw, float snr, float* scratch,
                           UpdateCoef* coef_out);
 
+// ---- probability-flow ODE sampler (ode.cu, controller in rk45.h) ----
+struct OdeK { const float2* k[7]; };   // stage derivatives K_0..K_6, complex64 like the reference's drift_fn output
+struct OdeCoefs { double a[7]; };
+constexpr int kOdeNormBlocks = 592;    // 4 x 148 SMs; one fp64 partial per block, summed on the host in block order
+// stage = (complex64)(y + (sum_{j<s} a_j K_j) * h); y_new (nullable) receives the fp64 value
+void launch_ode_combine(cudaStream_t st, const double2* y, const OdeK& K, int s, const OdeCoefs& c, double h, size_t total,
+                        float2* stage, double2* y_new);
+// k_out = theta (y - x) + cs * out_layer(pyr, inv_t)   [= theta (y - x) - 0.5 g^2 score, score = -dnn]; state = (x, y)
+void launch_ode_drift(cudaStream_t st, const float4* state, const float4* pyr, int N, int H, int W, const OutLayer& ol,
+                      float inv_t, float theta, float cs, float2* k_out);
+void launch_ode_init(cudaStream_t st, const float4* state, size_t total, double2* y);     // y = (complex128) state.x
+void launch_ode_finish(cudaStream_t st, const double2* y, size_t total, float2* out);     // out = (complex64) y
+// partial[kOdeNormBlocks]: per-block sums of |v/scale|^2, see ode.cu for the four kinds
+void launch_ode_norm(cudaStream_t st, int kind, const double2* y, const double2* y_new, const OdeK& K, const OdeCoefs& c, double h,
+                     double rtol, double atol, size_t total, double* partial);
+
 // ---- STFT front/back end (cuFFT plans live in the engine) ----
 void launch_absmax(cudaStream_t st, const float* wav, int B, int L, float* norm);
 void launch_frame(cudaStream_t st, const float* wav, const float* norm, int B, int L, int n_fft, int hop, int nT,

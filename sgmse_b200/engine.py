@@ -134,6 +134,30 @@ class EngineConfig:
         return c
 
 
+def rk45_host(fun, t_span, y0, rtol=1e-3, atol=1e-6, max_attempts=0):
+    """``scipy.integrate.solve_ivp(fun, t_span, y0, method='RK45', rtol=rtol, atol=atol)`` on the controller the device
+    ODE sampler runs (csrc/rk45.h) with ``fun`` as a host callback.  Host-only.  ``y0``: complex array [n].
+    Returns ``(y(t_bound) complex128 [n], nfev, {"steps", "rejected", "status"})``."""
+    import numpy as np
+    lib = _lib.load()
+    y = np.ascontiguousarray(np.asarray(y0).astype(np.complex128).reshape(-1))
+    n = y.size
+
+    def rhs(t, yp, dp, nn, _user):
+        if nn == 0:
+            return
+        yy = np.ctypeslib.as_array(yp, shape=(2 * nn,)).view(np.complex128)
+        d = np.ctypeslib.as_array(dp, shape=(2 * nn,)).view(np.complex128)
+        d[:] = np.asarray(fun(t, yy.copy()), dtype=np.complex128)
+
+    cb = _lib.ODE_RHS(rhs)
+    nfev = C.c_int()
+    stats = (C.c_int * 4)()
+    _lib.check(lib.sgmse_b200_rk45_host(cb, None, float(t_span[0]), float(t_span[1]), y.ctypes.data, n, float(rtol),
+                                        float(atol), int(max_attempts), C.byref(nfev), C.byref(stats)))
+    return y, int(nfev.value), {"steps": stats[0], "rejected": stats[1], "status": stats[2]}
+
+
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -315,6 +339,46 @@ class Engine:
         nfe = C.c_int()
         _lib.check(self.lib.sgmse_b200_pc_sample(self._h, y.data_ptr(), B, F, T, C.byref(s), nptr, out.data_ptr(),
                                                  C.byref(nfe), _stream_ptr()))
+        return out, int(nfe.value)
+
+    def ode_sample(self, y: torch.Tensor, prior_noise: Optional[torch.Tensor] = None, rtol: float = 1e-5, atol: float = 1e-5,
+                   eps: Optional[float] = None, denoise: bool = True, method: str = "RK45", seed: int = 0, utt_offset: int = 0,
+                   max_attempts: int = 0, return_stats: bool = False):
+        """sampling.get_ode_sampler(sde, score_fn, y, denoise, rtol, atol, method, eps)() (sampling/__init__.py:72-143):
+        y c64 [B,1,F,T] -> (sample, nfe), the probability-flow ODE integrated from T=1 to ``eps`` (default: ``t_eps``, as
+        ``ScoreModel.get_ode_sampler`` passes it, model.py:375) with scipy's RK45 restated on the device.  The whole
+        batch is one ODE system (one shared adaptive step sequence), as in the reference.
+
+        ``denoise`` defaults to True like the reference -- where that default raises ``TypeError`` (the denoising step
+        calls ``ReverseDiffusionPredictor.update_fn(x, y, t)`` without ``stepsize``, predictors.py:60); same here.
+        ``prior_noise``: optional c64 [B,1,F,T], the draw of ``prior_sampling`` (sdes.py:224-229)."""
+        if method != "RK45":
+            raise NotImplementedError("only scipy's default method 'RK45' is implemented on the device")
+        if denoise:
+            raise TypeError("ReverseDiffusionPredictor.update_fn() missing 1 required positional argument: 'stepsize' "
+                            "(the reference's get_ode_sampler(denoise=True) fails the same way; pass denoise=False)")
+        y = self._c64(y)
+        self._use_device()
+        B, _, F, T = y.shape
+        o = _lib.Ode()
+        o.rtol, o.atol = float(rtol), float(atol)
+        o.eps = float(self.cfg.t_eps if eps is None else eps)
+        o.max_attempts = int(max_attempts)
+        o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        o.utt_offset = int(utt_offset)
+        nptr = None
+        if prior_noise is not None:
+            prior_noise = self._c64(prior_noise)
+            if tuple(prior_noise.shape) != (B, 1, F, T):
+                raise ValueError(f"prior_noise must have shape {(B, 1, F, T)}, got {tuple(prior_noise.shape)}")
+            nptr = prior_noise.data_ptr()
+        out = torch.empty_like(y)
+        nfe = C.c_int()
+        stats = (C.c_int * 4)()
+        _lib.check(self.lib.sgmse_b200_ode_sample(self._h, y.data_ptr(), B, F, T, C.byref(o), nptr, out.data_ptr(),
+                                                  C.byref(nfe), C.byref(stats), _stream_ptr()))
+        if return_stats:
+            return out, int(nfe.value), {"steps": stats[0], "rejected": stats[1], "status": stats[2]}
         return out, int(nfe.value)
 
     # ---- STFT chain ------------------------------------------------------------------------------

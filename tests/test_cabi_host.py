@@ -94,3 +94,70 @@ def test_sb_schedule_matches_oracle(sampler_type, N, eps):
     assert ((rows[:, 0] + rows[:, 2]) - (ref_rows[:, 0] + ref_rows[:, 2])).abs().max().item() < 6e-4 or sampler_type == "sde"   # 2 ulp of 2.8e3
     if sampler_type == "sde":
         assert rows[-1, 2].item() == 0.0          # weight_z of the last step (sampling/__init__.py:176-179)
+
+
+# ---- the RK45 controller of the device ODE sampler, driven by a host callback -----------------
+def _ode_case(n=200, seed=0):
+    rng = np.random.default_rng(seed)
+    M = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) * 0.3 / np.sqrt(n)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+
+    def fun(t, y):                                   # rounded to complex64 like the sampler's drift
+        return (-1.5 * y + M @ np.tanh(y.real) + 1j * np.sin(3 * t) * b).astype(np.complex64)
+
+    y0 = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    return fun, y0
+
+
+@pytest.mark.parametrize("rtol,atol,t_bound", [(1e-5, 1e-5, 0.03), (1e-3, 1e-6, 0.03), (1e-8, 1e-10, 0.5), (1e-5, 1e-5, 2.0),
+                                                (1e-5, 1e-5, 1.0)])
+def test_rk45_controller_equals_scipy(rtol, atol, t_bound):
+    """csrc/rk45.h (what sgmse_b200_ode_sample runs) takes scipy's steps: same nfev, same accepted steps, same state
+    up to the summation order of the stage combinations (np.dot vs a plain loop, amplified by the complex64 rounding
+    of the right-hand side)."""
+    from scipy.integrate import solve_ivp
+    from sgmse_b200.engine import rk45_host
+    fun, y0 = _ode_case()
+    s = solve_ivp(fun, (1.0, t_bound), y0, rtol=rtol, atol=atol, method="RK45")
+    y, nfev, st = rk45_host(fun, (1.0, t_bound), y0, rtol=rtol, atol=atol)
+    assert (nfev, st["status"]) == (s.nfev, s.status)
+    if t_bound != 1.0:
+        assert st["steps"] == len(s.t) - 1
+    assert np.abs(s.y[:, -1] - y).max() <= 1e-6 * np.abs(y).max()
+
+
+def test_rk45_controller_rejected_steps_and_failure_modes():
+    from scipy.integrate import solve_ivp
+    from sgmse_b200.engine import rk45_host
+
+    def stiff(t, y):
+        return -2000.0 * (y - np.cos(t)) + 0j
+
+    s = solve_ivp(stiff, (0, 0.5), np.array([0 + 0j]), rtol=1e-4, atol=1e-7, method="RK45")
+    y, nfev, st = rk45_host(stiff, (0, 0.5), np.array([0 + 0j]), rtol=1e-4, atol=1e-7)
+    assert st["rejected"] > 10 and (nfev, st["steps"], st["status"]) == (s.nfev, len(s.t) - 1, 0)
+    assert abs(s.y[0, -1] - y[0]) < 1e-12
+    # bounded: a budget of step attempts, and a NaN right-hand side stops instead of spinning (scipy never returns there)
+    _, nfev, st = rk45_host(stiff, (0, 0.5), np.array([0 + 0j]), rtol=1e-4, atol=1e-7, max_attempts=7)
+    assert st["status"] == -2 and nfev == 2 + 6 * 7
+    _, nfev, st = rk45_host(lambda t, y: y * np.nan, (0, 1), np.array([1 + 0j]))
+    assert st["status"] == -3 and nfev <= 8
+    # empty system and errors through the C-ABI
+    y, nfev, st = rk45_host(lambda t, y: y, (0, 1), np.zeros(0, dtype=complex))
+    assert y.size == 0 and st["status"] == 0
+    with pytest.raises(RuntimeError, match="atol"):
+        rk45_host(stiff, (0, 0.5), np.array([0 + 0j]), atol=-1.0)
+
+
+def test_ode_sampler_host_mirror_errors():
+    """Engine.ode_sample mirrors get_ode_sampler's argument behaviour before anything touches the GPU: the default
+    denoise=True is the reference's TypeError (predictors.py:60), other integrators are not implemented."""
+    eng = Engine(CASES[2][1])
+    y = torch.zeros(1, 1, 64, 64, dtype=torch.complex64)
+    with pytest.raises(TypeError, match="stepsize"):
+        eng.ode_sample(y)
+    with pytest.raises(NotImplementedError):
+        eng.ode_sample(y, denoise=False, method="RK23")
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        eng.ode_sample(y, denoise=False)
+    eng.close()

@@ -153,24 +153,6 @@ def test_golden_v2_pc_sampler_on_ouve(golden_dir):
     eng.close()
 
 
-def test_batched_service_equals_clip_by_clip_enhancement(golden_dir):
-    """clips of different lengths bucketed by padded frame count and sampled together give, clip by
-    clip, exactly what enhancing each clip alone gives with the same (seed, utterance id)."""
-    from sgmse_b200 import BatchedEnhancer
-    z, sd = load_golden(golden_dir, "ncsnpp_small")
-    eng = small_engine("ncsnpp_small", "fp32", max_batch=2)
-    eng.load_state_dict(sd)
-    g = torch.Generator().manual_seed(31)
-    lengths = [2000, 4200, 1900, 2047, 4100]                 # 63/132/60/64/129 frames -> padded 64 / 192 / 64 / 64 / 192
-    waves = [0.1 * torch.randn(L, generator=g) for L in lengths]
-    kw = dict(N=2, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.5)
-    outs, ids = BatchedEnhancer(eng)(waves, seed=9, **kw)
-    assert sorted(ids) == list(range(5))
-    for w, o, i in zip(waves, outs, ids):
-        alone = eng.enhance(w[None].cuda(), seed=9, utt_offset=i, **kw)[0]
-        assert o.shape == w.shape and torch.isfinite(o).all()
-        assert torch.equal(o, alone)
-    eng.close()
 
 
 def test_golden_stft_ops(golden_dir):
@@ -280,25 +262,6 @@ def test_full_size_forward(full_sd, mode, tol, T):
     eng.close()
 
 
-def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
-    """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM
-    preconditioning -- c_in goes through the mma.sync input conv and the input pyramid, c_skip / c_out / 1/sigma through
-    the update coefficients -- two Schroedinger-bridge ODE steps against the oracle."""
-    pre = dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1)
-    cfg = NetConfig.ncsnpp_v2()
-    eng = Engine(EngineConfig.ncsnpp_v2(mode="fp16_tc", max_batch=1, sde="sbve", sb_k=2.6, sb_c=0.4, **pre))
-    eng.load_state_dict(full_sd)
-    g = torch.Generator().manual_seed(17)
-    y = torch.complex(torch.randn(1, 1, 256, 128, generator=g), torch.randn(1, 1, 256, 128, generator=g)) * 0.3
-    sb = o_sde.SBVE(2.6, 0.4)
-    with torch.no_grad():
-        ref, _ = o_sde.sb_sample(lambda a, b, c: o_net.precond_forward(full_sd, cfg, pre, sb.std, a, b, c), y, sb, N=2,
-                                 sampler_type="ode")
-    got, n = eng.sb_sample(y.cuda(), sampler_type="ode", N=2)
-    err = rel_l2(got, ref)
-    print(f"full-size v2 SB-ODE (fp16_tc, edm preconditioning): rel-L2 {err:.3e}")
-    assert n == 50 and eng.counter("tc_convs_last_forward") > 0 and err < 3e-2
-    eng.close()
 
 
 def test_full_size_48k_forward():

@@ -1,0 +1,157 @@
+"""GPU parity tests of the rows SURVEY.md §8(f) marks "next" that were written after the last GPU session of round 1
+(the probability-flow ODE sampler was built with no GPU minutes left: its CUDA path is compiled, its controller and
+oracle are pinned on the CPU, and these tests are its first contact with the device).  The file name sorts after
+test_gpu_parity.py so that `pytest -x -m gpu` reports the core path first.  Run on the B200 box: ``pytest -m gpu``.
+
+Tolerances: fp32 mode rel-L2 <= 1e-3 against the reference fixture after a full adaptive ODE solve; fp16_tc <= 3e-2.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ncsnpp as o_net, sde as o_sde, ode as o_ode, weights as o_w
+from oracle.arch import NetConfig
+from sgmse_b200 import Engine, EngineConfig
+
+pytestmark = pytest.mark.gpu
+
+SMALL_E = dict(nf=16, ch_mult=(1, 2, 2), image_size=64, num_res_blocks=2, n_fft=126, hop_length=32)
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).cpu(), torch.as_tensor(b).cpu()
+    return (torch.linalg.vector_norm((a - b).reshape(-1)) / torch.linalg.vector_norm(b.reshape(-1))).item()
+
+
+def load_golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w/")}
+    return z, sd
+
+
+def small_engine(kind, mode, **kw):
+    if kind == "ncsnpp_small":
+        return Engine(EngineConfig(attn_resolutions=(16,), mode=mode, **SMALL_E, **kw))
+    return Engine(EngineConfig.ncsnpp_48k(mode=mode, theta=1.5, sigma_min=0.05, sigma_max=0.5, spec_factor=0.15,
+                                          spec_abs_exponent=0.5, **SMALL_E, **kw))
+
+
+@pytest.fixture(scope="module")
+def full_sd():
+    return o_w.make_state_dict(NetConfig.ncsnpp(), seed=0)
+
+
+# ---- written late in round 1 (SURVEY.md §8f-1 at full size, §8f-2) ---------------------------------------------------
+def test_batched_service_equals_clip_by_clip_enhancement(golden_dir):
+    """clips of different lengths bucketed by padded frame count and sampled together give, clip by
+    clip, exactly what enhancing each clip alone gives with the same (seed, utterance id)."""
+    from sgmse_b200 import BatchedEnhancer
+    z, sd = load_golden(golden_dir, "ncsnpp_small")
+    eng = small_engine("ncsnpp_small", "fp32", max_batch=2)
+    eng.load_state_dict(sd)
+    g = torch.Generator().manual_seed(31)
+    lengths = [2000, 4200, 1900, 2047, 4100]                 # 63/132/60/64/129 frames -> padded 64 / 192 / 64 / 64 / 192
+    waves = [0.1 * torch.randn(L, generator=g) for L in lengths]
+    kw = dict(N=2, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.5)
+    outs, ids = BatchedEnhancer(eng)(waves, seed=9, **kw)
+    assert sorted(ids) == list(range(5))
+    for w, o, i in zip(waves, outs, ids):
+        alone = eng.enhance(w[None].cuda(), seed=9, utt_offset=i, **kw)[0]
+        assert o.shape == w.shape and torch.isfinite(o).all()
+        assert torch.equal(o, alone)
+    eng.close()
+
+
+def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
+    """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM
+    preconditioning -- c_in goes through the mma.sync input conv and the input pyramid, c_skip / c_out / 1/sigma through
+    the update coefficients -- two Schroedinger-bridge ODE steps against the oracle."""
+    pre = dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1)
+    cfg = NetConfig.ncsnpp_v2()
+    eng = Engine(EngineConfig.ncsnpp_v2(mode="fp16_tc", max_batch=1, sde="sbve", sb_k=2.6, sb_c=0.4, **pre))
+    eng.load_state_dict(full_sd)
+    g = torch.Generator().manual_seed(17)
+    y = torch.complex(torch.randn(1, 1, 256, 128, generator=g), torch.randn(1, 1, 256, 128, generator=g)) * 0.3
+    sb = o_sde.SBVE(2.6, 0.4)
+    with torch.no_grad():
+        ref, _ = o_sde.sb_sample(lambda a, b, c: o_net.precond_forward(full_sd, cfg, pre, sb.std, a, b, c), y, sb, N=2,
+                                 sampler_type="ode")
+    got, n = eng.sb_sample(y.cuda(), sampler_type="ode", N=2)
+    err = rel_l2(got, ref)
+    print(f"full-size v2 SB-ODE (fp16_tc, edm preconditioning): rel-L2 {err:.3e}")
+    assert n == 50 and eng.counter("tc_convs_last_forward") > 0 and err < 3e-2
+    eng.close()
+
+
+# ---- probability-flow ODE sampler ---------------------------------------------------------------
+@pytest.mark.parametrize("name,src", [("ode_small", "ncsnpp_small"), ("ode48k_small", "ncsnpp48k_small")])
+@pytest.mark.parametrize("graphs", [False, True])
+def test_golden_ode_sampler(golden_dir, name, src, graphs):
+    """get_ode_sampler(denoise=False) of the unmodified reference (scipy RK45 over host numpy) against the device solve:
+    same adaptive step sequence (nfe within one rejected step), same state.  Eager launches first, then the captured
+    per-evaluation graph."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    _, sd = load_golden(golden_dir, src)
+    eng = small_engine(src, "fp32", max_batch=2, use_graphs=graphs)
+    eng.load_state_dict(sd)
+    y = torch.from_numpy(z["y"]).cuda()
+    prior = o_sde.make_noise(tuple(y.shape), 1, seed=int(z["prior_seed"]))[0].cuda()
+    tol = float(z["tol_loose"])
+    x, nfe, st = eng.ode_sample(y, prior_noise=prior, rtol=tol, atol=tol, eps=0.03, denoise=False, return_stats=True)
+    err = rel_l2(x, z["x_loose"])
+    print(f"{name} graphs={graphs}: nfe {nfe} (reference {int(z['nfe_loose'])}), steps {st}, rel-L2 {err:.3e}")
+    assert st["status"] == 0 and abs(nfe - int(z["nfe_loose"])) <= 6
+    assert err < 1e-3
+    if graphs:
+        assert eng.counter("graph_launches") >= nfe - 1
+    eng.close()
+
+
+def test_ode_sampler_properties(golden_dir):
+    """The whole batch is ONE ode system (shared step sequence, as in the reference) evaluated in micro-batches of any
+    size; Philox prior draws are keyed by global utterance id; the default denoise=True is the reference's TypeError."""
+    _, sd = load_golden(golden_dir, "ncsnpp_small")
+    z = np.load(os.path.join(golden_dir, "ode_small.npz"))
+    y = torch.from_numpy(z["y"]).cuda()
+    prior = o_sde.make_noise(tuple(y.shape), 1, seed=int(z["prior_seed"]))[0].cuda()
+    outs = []
+    for mb in (1, 2):
+        eng = small_engine("ncsnpp_small", "fp32", max_batch=mb)
+        eng.load_state_dict(sd)
+        outs.append(eng.ode_sample(y, prior_noise=prior, rtol=1e-3, atol=1e-3, denoise=False))
+        if mb == 2:
+            a = eng.ode_sample(y, rtol=1e-2, atol=1e-2, denoise=False, seed=5)
+            b = eng.ode_sample(y, rtol=1e-2, atol=1e-2, denoise=False, seed=5)
+            c = eng.ode_sample(y, rtol=1e-2, atol=1e-2, denoise=False, seed=6)
+            assert torch.equal(a[0], b[0]) and a[1] == b[1] and not torch.equal(a[0], c[0])
+            assert torch.isfinite(torch.view_as_real(a[0])).all()
+            with pytest.raises(TypeError, match="stepsize"):
+                eng.ode_sample(y)
+            # a budget of step attempts ends the solve early and says so
+            _, nfe, st = eng.ode_sample(y, prior_noise=prior, rtol=1e-3, atol=1e-3, denoise=False, max_attempts=2, return_stats=True)
+            assert st["status"] == -2 and nfe == 2 + 12
+        eng.close()
+    assert outs[0][1] == outs[1][1] and torch.equal(outs[0][0], outs[1][0])
+
+
+def test_full_size_ode_on_the_product_path(full_sd):
+    """Full-size NCSN++ (65.6 M parameters) in the product mode against the oracle: same tolerance-driven solve at
+    rtol = atol = 5e-2 (a handful of steps: the CPU oracle needs ~10 s per evaluation at this size)."""
+    cfg = NetConfig.ncsnpp()
+    eng = Engine(EngineConfig(mode="fp16_tc", max_batch=1))
+    eng.load_state_dict(full_sd)
+    g = torch.Generator().manual_seed(29)
+    y = torch.complex(torch.randn(1, 1, 256, 64, generator=g), torch.randn(1, 1, 256, 64, generator=g)) * 0.3
+    prior = o_sde.make_noise(tuple(y.shape), 1, seed=31)[0]
+    with torch.no_grad():
+        ref, nfe_ref = o_ode.ode_sample(lambda a, b, c: o_net.score(full_sd, cfg, a, b, c), y, o_sde.OUVE(), eps=0.03,
+                                        rtol=5e-2, atol=5e-2, prior_noise=prior)
+    got, nfe, st = eng.ode_sample(y.cuda(), prior_noise=prior.cuda(), rtol=5e-2, atol=5e-2, eps=0.03, denoise=False,
+                                  return_stats=True)
+    err = rel_l2(got, ref)
+    print(f"full-size ODE (fp16_tc): nfe {nfe} (oracle {nfe_ref}), {st}, rel-L2 {err:.3e}")
+    assert st["status"] == 0 and abs(nfe - nfe_ref) <= 12 and err < 3e-2
+    assert eng.counter("tc_convs_last_forward") > 0
+    eng.close()

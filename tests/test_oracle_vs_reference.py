@@ -165,3 +165,46 @@ def test_install_for_in_training_evaluation(model16k):
         model16k.eval()
     assert "eval" not in model16k.__dict__ and "enhance" not in model16k.__dict__
     eng.close()
+
+
+def test_install_rebinds_the_ode_sampler(model16k):
+    """SURVEY.md §8f-4: install() routes ScoreModel.get_ode_sampler (model.py:370-390) to the engine for the OUVE SDE;
+    the default call fails with the reference's own TypeError (denoise=True, predictors.py:60) before any GPU work, on
+    the reference and on the engine alike."""
+    import sgmse_b200
+    from sgmse_b200 import config_from_score_model, Engine
+    y = torch.zeros(1, 1, 256, 64, dtype=torch.complex64)
+    with pytest.raises(TypeError, match="stepsize"):
+        model16k.get_ode_sampler(y, device="cpu", rtol=1e-1, atol=1e-1)()          # the unmodified reference
+    eng = Engine(config_from_score_model(model16k))
+    sgmse_b200.install(model16k, engine=eng)
+    try:
+        assert model16k.get_ode_sampler.__func__.__name__ == "get_ode_sampler" and "get_ode_sampler" in model16k.__dict__
+        with pytest.raises(TypeError, match="stepsize"):
+            model16k.get_ode_sampler(y)()
+        with pytest.raises(RuntimeError, match="CUDA tensor"):                      # no CPU path behind the boundary
+            model16k.get_ode_sampler(y, denoise=False, minibatch=1)()
+    finally:
+        sgmse_b200.uninstall(model16k)
+    assert "get_ode_sampler" not in model16k.__dict__
+    eng.close()
+
+
+def test_ode_oracle_matches_reference_live():
+    """oracle/ode.py against the unmodified get_ode_sampler, live, on a config the fixtures do not hold (48 kHz SDE
+    parameters, eps = 0.05, batch of 2 = one coupled ODE system)."""
+    from oracle import ode as o_ode
+    SMALL = dict(nf=16, ch_mult=(1, 2, 2), image_size=64, num_res_blocks=2)
+    m = refshim.make_score_model("ncsnpp_48k", seed=5, n_fft=126, hop_length=32, theta=2.0, sigma_min=0.1, sigma_max=1.0, **SMALL)
+    cfg = NetConfig.ncsnpp_48k(**SMALL)
+    sd = m.dnn.state_dict()
+    g = torch.Generator().manual_seed(3)
+    y = torch.complex(torch.randn(2, 1, 64, 64, generator=g), torch.randn(2, 1, 64, 64, generator=g)) * 0.3
+    draws = o_sde.make_noise(tuple(y.shape), 1, seed=23)
+    with refshim.injected_noise(draws):
+        ref, nfe_ref = m.get_ode_sampler(y, denoise=False, device="cpu", rtol=1e-3, atol=1e-3, eps=0.05)()
+    sde = o_sde.OUVE(theta=2.0, sigma_min=0.1, sigma_max=1.0)
+    got, nfe = o_ode.ode_sample(lambda a, b, c: o_net.score(sd, cfg, a, b, c), y, sde, eps=0.05, rtol=1e-3, atol=1e-3,
+                                prior_noise=draws[0])
+    assert nfe == nfe_ref
+    assert ((ref - got).abs().max() / ref.abs().max()).item() < 1e-6
