@@ -232,7 +232,8 @@ class Engine:
             _lib.check(self.lib.sgmse_b200_load_weights(self._h, blob.data_ptr(), blob.numel()))
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], on_device: bool = False):
-        """``on_device``: flatten where the parameters live (no host round trip; used when weights are refreshed between
+        """``on_device``: flatten where the parameters live (one D2H copy of the flat blob instead of one per tensor; the
+        packing itself runs on the host -- sgmse_b200_load_weights_device; used when weights are refreshed between
         training epochs)."""
         dev = next(iter(sd.values())).device if on_device else "cpu"
         self.load_blob(self.flatten_state_dict(sd, device=dev))

@@ -1,6 +1,6 @@
-"""GPU parity tests of the rows SURVEY.md §8(f) marks "next" that were written after the last GPU session of round 1
-(the probability-flow ODE sampler was built with no GPU minutes left: its CUDA path is compiled, its controller and
-oracle are pinned on the CPU, and these tests are its first contact with the device).  The file name sorts after
+"""GPU parity tests of the rows SURVEY.md §8(f) marks "next" that were written at the very end of round 1.  The
+small-config ODE tests and the batched-service test passed on a B200 in the round's last GPU call
+(profiles/r01_ode_first_contact.txt); the two full-size tests had no GPU minutes left.  The file name sorts after
 test_gpu_parity.py so that `pytest -x -m gpu` reports the core path first.  Run on the B200 box: ``pytest -m gpu``.
 
 Tolerances: fp32 mode rel-L2 <= 1e-3 against the reference fixture after a full adaptive ODE solve; fp16_tc <= 3e-2.
