@@ -1,0 +1,119 @@
+"""Host logic of the drop-in layer (sgmse_b200/api.py) with stand-in model and engine objects: which engine call each
+rebound ScoreModel method makes, with which arguments, and which reference error it reproduces.  No GPU, no reference
+checkout (the live-reference variants are in tests/test_oracle_vs_reference.py)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import sgmse_b200
+from sgmse_b200 import api
+
+
+class OUVESDE:                       # the class NAME is what the drop-in layer dispatches on (model.py:441,450)
+    def __init__(self, sampler_type="pc", N=30):
+        self.sampler_type, self.N = sampler_type, N
+
+
+class SBVESDE:
+    def __init__(self, sampler_type="ode", N=50):
+        self.sampler_type, self.N = sampler_type, N
+
+
+class FakeEngine:
+    def __init__(self, backbone="ncsnpp"):
+        self.cfg = types.SimpleNamespace(backbone=backbone, t_eps=0.03, sr=16000)
+        self.device = "cpu"
+        self.calls = []
+
+    def enhance(self, wav, **kw):
+        self.calls.append(("enhance", tuple(wav.shape), kw))
+        return wav * 2
+
+    def analysis(self, wav, pad_mode="zero_pad"):
+        self.calls.append(("analysis", tuple(wav.shape), pad_mode))
+        return torch.zeros(wav.shape[0], 1, 4, 64, dtype=torch.complex64), wav.abs().amax(dim=1)
+
+    def synthesis(self, X, norm, length):
+        self.calls.append(("synthesis", tuple(X.shape), length))
+        return torch.ones(X.shape[0], length) * norm[:, None]
+
+    def ode_sample(self, y, prior_noise=None, denoise=True, **kw):
+        self.calls.append(("ode_sample", tuple(y.shape), denoise, prior_noise is not None, kw))
+        if denoise:
+            raise TypeError("ReverseDiffusionPredictor.update_fn() missing 1 required positional argument: 'stepsize'")
+        return y + 1, 38
+
+    def pc_sample(self, y, noise=None, **kw):
+        self.calls.append(("pc_sample", tuple(y.shape), kw))
+        return y, kw["N"] * 2
+
+
+def make_model(sde):
+    m = types.SimpleNamespace(sde=sde, sr=16000)
+    m.__dict__["_orig"] = True
+    return m
+
+
+def test_install_binds_the_ode_sampler_only_where_the_engine_has_it():
+    m = make_model(OUVESDE())
+    eng = FakeEngine()
+    sgmse_b200.install(m, engine=eng, rebind_forward=False)
+    assert {"get_pc_sampler", "get_ode_sampler", "get_sb_sampler", "enhance"} <= set(m.__dict__)
+    sgmse_b200.uninstall(m)
+    assert "get_ode_sampler" not in m.__dict__ and "enhance" not in m.__dict__
+    m2 = make_model(SBVESDE())
+    sgmse_b200.install(m2, engine=FakeEngine("ncsnpp_v2"), rebind_forward=False)
+    assert "get_ode_sampler" not in m2.__dict__          # the reference's own torch path stays in place
+    sgmse_b200.uninstall(m2)
+
+
+def test_get_ode_sampler_arguments_and_minibatch_loop():
+    m = make_model(OUVESDE())
+    eng = FakeEngine()
+    sgmse_b200.install(m, engine=eng, rebind_forward=False)
+    y = torch.zeros(5, 1, 4, 64, dtype=torch.complex64)
+    with pytest.raises(TypeError, match="stepsize"):     # the reference's default (denoise=True) fails the same way
+        m.get_ode_sampler(y)()
+    x, nfe = m.get_ode_sampler(y, denoise=False, rtol=1e-3, seed=11)()
+    name, shape, denoise, has_noise, kw = eng.calls[-1]
+    assert (name, shape, denoise, has_noise) == ("ode_sample", (5, 1, 4, 64), False, False)
+    assert kw["rtol"] == 1e-3 and kw["atol"] == 1e-5 and kw["eps"] == 0.03 and kw["method"] == "RK45" and kw["seed"] == 11
+    assert nfe == 38 and torch.equal(x, y + 1)
+    # minibatch: one ODE system per slice, noise ids continue across slices, nfe is a list (model.py:380-390)
+    noise = torch.zeros_like(y)
+    eng.calls.clear()
+    x, ns = m.get_ode_sampler(y, minibatch=2, denoise=False, noise=noise, seed=3)()
+    assert ns == [38, 38, 38] and x.shape == y.shape
+    assert [c[1][0] for c in eng.calls] == [2, 2, 1] and [c[4]["utt_offset"] for c in eng.calls] == [0, 2, 4]
+    assert all(c[3] for c in eng.calls)
+    sgmse_b200.uninstall(m)
+
+
+def test_enhance_dispatch_follows_model_py():
+    """model.py:441-454: OUVESDE + 'pc' -> PC sampler, OUVESDE + 'ode' -> ODE sampler, anything else -> ValueError."""
+    wav = 0.5 * torch.ones(1, 1000)
+    eng = FakeEngine()
+    m = make_model(OUVESDE("pc"))
+    sgmse_b200.install(m, engine=eng, rebind_forward=False)
+    out = m.enhance(wav, N=7, corrector_steps=2, snr=0.33, seed=1)
+    assert isinstance(out, np.ndarray) and out.shape == (1000,)
+    name, shape, kw = eng.calls[-1]
+    assert name == "enhance" and kw["N"] == 7 and kw["corrector_steps"] == 2 and kw["snr"] == 0.33
+    xh, nfe, rtf = m.enhance(wav, N=7, corrector_steps=2, timeit=True)
+    assert nfe == 7 * 3 and rtf > 0
+
+    m.sde.sampler_type = "ode"
+    eng.calls.clear()
+    with pytest.raises(TypeError, match="stepsize"):     # enhance() forwards kwargs only: denoise stays True (model.py:447)
+        m.enhance(wav)
+    xh, nfe, rtf = m.enhance(wav, denoise=False, rtol=1e-2, timeit=True, seed=4)
+    names = [c[0] for c in eng.calls]
+    assert names[-3:] == ["analysis", "ode_sample", "synthesis"] and nfe == 38 and xh.shape == (1000,)
+    assert eng.calls[-2][4]["rtol"] == 1e-2 and eng.calls[-2][4]["seed"] == 4 and eng.calls[-1][2] == 1000
+
+    m.sde.sampler_type = "bogus"
+    with pytest.raises(ValueError, match="Invalid sampler type"):
+        m.enhance(wav)
+    sgmse_b200.uninstall(m)

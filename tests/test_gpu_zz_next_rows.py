@@ -64,25 +64,6 @@ def test_batched_service_equals_clip_by_clip_enhancement(golden_dir):
     eng.close()
 
 
-def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
-    """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM
-    preconditioning -- c_in goes through the mma.sync input conv and the input pyramid, c_skip / c_out / 1/sigma through
-    the update coefficients -- two Schroedinger-bridge ODE steps against the oracle."""
-    pre = dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1)
-    cfg = NetConfig.ncsnpp_v2()
-    eng = Engine(EngineConfig.ncsnpp_v2(mode="fp16_tc", max_batch=1, sde="sbve", sb_k=2.6, sb_c=0.4, **pre))
-    eng.load_state_dict(full_sd)
-    g = torch.Generator().manual_seed(17)
-    y = torch.complex(torch.randn(1, 1, 256, 128, generator=g), torch.randn(1, 1, 256, 128, generator=g)) * 0.3
-    sb = o_sde.SBVE(2.6, 0.4)
-    with torch.no_grad():
-        ref, _ = o_sde.sb_sample(lambda a, b, c: o_net.precond_forward(full_sd, cfg, pre, sb.std, a, b, c), y, sb, N=2,
-                                 sampler_type="ode")
-    got, n = eng.sb_sample(y.cuda(), sampler_type="ode", N=2)
-    err = rel_l2(got, ref)
-    print(f"full-size v2 SB-ODE (fp16_tc, edm preconditioning): rel-L2 {err:.3e}")
-    assert n == 50 and eng.counter("tc_convs_last_forward") > 0 and err < 3e-2
-    eng.close()
 
 
 # ---- SURVEY.md §8f-4: probability-flow ODE sampler ---------------------------------------------------------------
@@ -134,6 +115,28 @@ def test_ode_sampler_properties(golden_dir):
             assert st["status"] == -2 and nfe == 2 + 12
         eng.close()
     assert outs[0][1] == outs[1][1] and torch.equal(outs[0][0], outs[1][0])
+
+
+# ---- full size, product mode (not yet run on a GPU) ----
+def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
+    """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM
+    preconditioning -- c_in goes through the mma.sync input conv and the input pyramid, c_skip / c_out / 1/sigma through
+    the update coefficients -- two Schroedinger-bridge ODE steps against the oracle."""
+    pre = dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1)
+    cfg = NetConfig.ncsnpp_v2()
+    eng = Engine(EngineConfig.ncsnpp_v2(mode="fp16_tc", max_batch=1, sde="sbve", sb_k=2.6, sb_c=0.4, **pre))
+    eng.load_state_dict(full_sd)
+    g = torch.Generator().manual_seed(17)
+    y = torch.complex(torch.randn(1, 1, 256, 128, generator=g), torch.randn(1, 1, 256, 128, generator=g)) * 0.3
+    sb = o_sde.SBVE(2.6, 0.4)
+    with torch.no_grad():
+        ref, _ = o_sde.sb_sample(lambda a, b, c: o_net.precond_forward(full_sd, cfg, pre, sb.std, a, b, c), y, sb, N=2,
+                                 sampler_type="ode")
+    got, n = eng.sb_sample(y.cuda(), sampler_type="ode", N=2)
+    err = rel_l2(got, ref)
+    print(f"full-size v2 SB-ODE (fp16_tc, edm preconditioning): rel-L2 {err:.3e}")
+    assert n == 50 and eng.counter("tc_convs_last_forward") > 0 and err < 3e-2
+    eng.close()
 
 
 def test_full_size_ode_on_the_product_path(full_sd):
