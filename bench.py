@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--N", type=int, default=30)
     ap.add_argument("--mode", default="fp16_tc")
     ap.add_argument("--lanes", type=int, default=1, help="concurrent launch sequences inside the sampler graph")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json configs[i-1]: 2 = the metric's workload (default, the only one the driver runs); "
+                         "3 = ncsnpp_48k 48 kHz batch 8; 4 = dereverb settings N=50 snr=0.33 batch 32 (parity-test cases, "
+                         "measurable here for the record; no CPU baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
@@ -185,9 +189,10 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": f"SGMSE+ NCSN++ (VoiceBank-DEMAND config, 65.6 M params, random init), 16 kHz, 4-s clips, "
-                        f"batch {args.batch} per GPU, PC sampler reverse_diffusion+ald N={args.N} snr 0.5 "
-                        f"({2 * args.N} network evaluations), STFT 510/128",
+    return {"workload": f"{args.workload_name}, 4-s clips, "
+                        f"batch {args.batch} per GPU, PC sampler reverse_diffusion+ald N={args.N} snr {args.snr} "
+                        f"({2 * args.N} network evaluations), STFT {args.stft}",
+            "baseline_config": args.config,
             "global_batch": args.batch * args.gpus, "per_gpu_batch": args.batch, "micro_batch": args.micro_batch, "lanes": args.lanes,
             "parallelism": f"dp{args.gpus} (batch sharded, no data-path collective)",
             "l2": "working set per step (>10 GB of activations per micro-batch) exceeds the 126 MB L2; no flush needed"}
@@ -211,7 +216,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    eng = Engine(EngineConfig(mode=args.mode, max_batch=args.micro_batch, use_graphs=True), device=dev)
+    ecfg = (EngineConfig.ncsnpp_48k if args.config == 3 else EngineConfig)(mode=args.mode, max_batch=args.micro_batch, use_graphs=True)
+    eng = Engine(ecfg, device=dev)
     eng.set_option("lanes", args.lanes)
     # weights: rank 0 creates them, NCCL broadcast over NVLink, packed per rank
     n = eng.weights_numel()
@@ -229,7 +235,7 @@ def run_b200(args):
     wav_dev = wav_host.to(dev)
     out_dev = torch.empty_like(wav_dev)
     out_host = torch.empty_like(wav_host).pin_memory()
-    kw = dict(N=args.N, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.5)
+    kw = dict(N=args.N, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=args.snr)
 
     def barrier():
         if world > 1:
@@ -303,7 +309,8 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": "utterances/sec (4 s, 16 kHz, N=30 PC)", "value": round(value, 4), "unit": "utterances/s",
+            "metric": "utterances/sec (4 s, 16 kHz, N=30 PC)" if args.config == 2 else
+                      f"utterances/sec (4 s, {SR // 1000} kHz, N={args.N} PC)", "value": round(value, 4), "unit": "utterances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 (fp32 accumulate)" if args.mode != "fp32" else "f32", "data": "synthetic",
@@ -319,8 +326,34 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+WORKLOADS = {
+    # name, sampling rate, GFLOP per forward per utterance, per-GPU batch, micro-batch, N, snr
+    2: dict(name="SGMSE+ NCSN++ (VoiceBank-DEMAND config, 65.6 M params, random init), 16 kHz", sr=16000, gflop=1064.7,
+            batch=16, micro=16, N=30, snr=0.5, stft="510/128"),
+    3: dict(name="NCSN++ 48 kHz (EARS-WHAM config: backbone ncsnpp_48k, 64.7 M params, random init), 48 kHz", sr=48000,
+            gflop=3187.6, batch=8, micro=8, N=30, snr=0.5, stft="1534/384"),
+    4: dict(name="SGMSE+ NCSN++ (WSJ0-REVERB dereverberation settings, random init), 16 kHz", sr=16000, gflop=1064.7,
+            batch=32, micro=16, N=50, snr=0.33, stft="510/128"),
+}
+
+
+def apply_workload(args):
+    """--config 3 / 4 replace the defaults of --batch / --micro-batch / --N (explicit flags still win is NOT attempted:
+    a named config means its published settings)."""
+    global SR, GFLOP_PER_FORWARD
+    w = WORKLOADS[args.config]
+    args.snr = w["snr"]
+    args.workload_name = w["name"]
+    args.stft = w["stft"]
+    if args.config != 2:
+        args.batch, args.micro_batch, args.N = w["batch"], w["micro"], w["N"]
+        args.no_cpu_baseline = True
+        SR, GFLOP_PER_FORWARD = w["sr"], w["gflop"]
+
+
 def main():
     args = parse()
+    apply_workload(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -117,6 +117,52 @@ def test_ode_sampler_properties(golden_dir):
     assert outs[0][1] == outs[1][1] and torch.equal(outs[0][0], outs[1][0])
 
 
+# ---- size-independent properties at the BASELINE.json shapes (configs 2 and 3) ------------------------------------------
+@pytest.mark.parametrize("kind,B,L", [("16k", 16, 64000), ("48k", 8, 192000)])
+def test_full_size_stft_round_trip(kind, B, L):
+    """analysis -> synthesis is the identity away from the clip's end (normalise, STFT, compress, pad | decompress, iSTFT,
+    renormalise: model.py:435-438,457-458).  The last n_fft samples are excluded: frames beyond the clip are padding and
+    the reference's own round trip deviates there by ~0.05 (oracle: 1.2e-7 in the interior, 4.4e-2 in the tail)."""
+    cfg = EngineConfig(max_batch=B) if kind == "16k" else EngineConfig.ncsnpp_48k(max_batch=B)
+    eng = Engine(cfg)                                  # the STFT chain needs no weights
+    g = torch.Generator().manual_seed(41)
+    wav = (0.1 * torch.randn(B, L, generator=g)).cuda()
+    for pad_mode in ("zero_pad", "reflection"):
+        Y, norm = eng.analysis(wav, pad_mode=pad_mode)
+        assert tuple(Y.shape) == (B, 1, cfg.n_fft // 2 + 1, 512) and torch.allclose(norm, wav.abs().amax(dim=1))
+        back = eng.synthesis(Y, norm, L)
+        err = (back - wav)[:, : L - cfg.n_fft].abs().max().item()
+        print(f"{kind} {pad_mode}: interior round-trip error {err:.2e}")
+        assert err < 2e-5
+    eng.close()
+
+
+def test_full_size_prior_draw_statistics(full_sd):
+    """prior_sampling (sdes.py:224-229) at the benchmark shape through the sampler with predictor = corrector = 'none':
+    x = y + std(1) z with z ~ CN(0, 1) from the in-kernel Philox generator -- real and imaginary variance 1/2 each,
+    utterances uncorrelated, and utterance b of a batch at offset o is utterance 0 of a batch at offset o + b."""
+    eng = Engine(EngineConfig(mode="fp16_tc", max_batch=4))
+    eng.load_state_dict(full_sd)
+    B, F, T = 4, 256, 512
+    y = torch.zeros(B, 1, F, T, dtype=torch.complex64).cuda()
+    x, nfe = eng.pc_sample(y, N=1, predictor="none", corrector="none", seed=77, utt_offset=10)
+    std1 = 0.38898                                            # SURVEY.md §8a: OUVESDE._std(1) for the 16 kHz SDE
+    z = torch.view_as_real(x[:, 0]) / std1                    # [B, F, T, 2]
+    n = F * T
+    assert nfe == 1
+    for b in range(B):
+        re, im = z[b, ..., 0].flatten(), z[b, ..., 1].flatten()
+        assert abs(re.mean().item()) < 5 / (2 * n) ** 0.5 and abs(im.mean().item()) < 5 / (2 * n) ** 0.5       # 5 sigma
+        assert abs(re.var().item() - 0.5) < 0.01 and abs(im.var().item() - 0.5) < 0.01
+        assert abs((re * im).mean().item()) < 0.01
+    assert abs((z[0].flatten() * z[1].flatten()).mean().item()) < 0.01          # different utterance ids: independent
+    x2, _ = eng.pc_sample(y[:1], N=1, predictor="none", corrector="none", seed=77, utt_offset=12)
+    assert torch.equal(x2[0], x[2])
+    x3, _ = eng.pc_sample(y[:1], N=1, predictor="none", corrector="none", seed=78, utt_offset=12)
+    assert not torch.equal(x3[0], x[2])
+    eng.close()
+
+
 # ---- full size, product mode (not yet run on a GPU) ----
 def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
     """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM
