@@ -180,6 +180,37 @@ def golden_ode(name, src_name, backbone, cfg: NetConfig, seed):
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), y=_np(y), prior_seed=np.int64(17), **out)
 
 
+def golden_full_n30(name="full_n30"):
+    """BASELINE.json configs[0] through the UNMODIFIED reference: one 4-s 16 kHz clip, full-size NCSN++ (65.6 M
+    parameters), OUVE SDE, predictor-corrector sampler reverse_diffusion + ald, N = 30, snr = 0.5 -- the sequence of
+    model.enhance (model.py:433-459) / enhancement.py:75-96 on CPU, ~5 minutes on 8 cores.  The weights are the oracle's
+    seeded init (oracle/weights.py, seed 0) loaded into the reference model, the clip is bench.py's synthetic utterance 0
+    and the 61 noise draws come from seeds -- all three are regenerated on the GPU box, only the reference's OUTPUT is
+    stored (enhanced waveform + final spectrogram, 1.3 MB)."""
+    import time
+    from . import weights as o_w
+    from sgmse_b200.synth import synthetic_speech
+    cfg = NetConfig.ncsnpp()
+    model = refshim.make_score_model("ncsnpp", seed=0)
+    from sgmse.util.other import pad_spec
+    model.dnn.load_state_dict(o_w.make_state_dict(cfg, seed=0))
+    L, N = 64000, 30
+    wav = synthetic_speech(1, L)                                   # 0.1 * randn, torch.manual_seed(1000)
+    t0 = time.time()
+    norm = wav.abs().max()
+    Y = torch.unsqueeze(model._forward_transform(model._stft(wav / norm)), 0)
+    Y = pad_spec(Y)
+    draws = sde_mod.make_noise(tuple(Y.shape), sde_mod.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=2000)
+    with refshim.injected_noise(draws), torch.no_grad():
+        sample, nfe = model.get_pc_sampler("reverse_diffusion", "ald", Y, N=N, corrector_steps=1, snr=0.5)()
+    x_hat = model.to_audio(sample.squeeze(), L) * norm
+    print(name, "reference CPU run", round(time.time() - t0, 1), "s, nfe", nfe, "threads", torch.get_num_threads())
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), enh=_np(x_hat.reshape(-1)), sample=_np(sample[0, 0]),
+                        nfe=np.int64(nfe), N=np.int64(N), L=np.int64(L), wav_seed=np.int64(1000), weight_seed=np.int64(0),
+                        noise_seed=np.int64(2000), snr=np.float64(0.5), cpu_seconds=np.float64(time.time() - t0),
+                        cpu_threads=np.int64(torch.get_num_threads()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     golden_ops()
@@ -187,6 +218,7 @@ def main():
     golden_network("ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
     golden_v2("ncsnpp_v2_small", NetConfig.ncsnpp_v2(attn_resolutions=(16,), **SMALL), seed=3)
     golden_ode("ode_small", "ncsnpp_small", "ncsnpp", NetConfig.ncsnpp(attn_resolutions=(16,), **SMALL), seed=1)
+    golden_full_n30()
     golden_ode("ode48k_small", "ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
 
 

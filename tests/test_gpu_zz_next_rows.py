@@ -185,6 +185,40 @@ def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
     eng.close()
 
 
+# Bounds of the N = 30 run.  Emulating the product mode's storage precision on the CPU oracle (conv operands and results
+# rounded to fp16, fp32 accumulation; 0.5-s clip, same 60 evaluations) moves the enhanced waveform by rel-L2 8.9e-3 =
+# 41 dB SI-SDR against the fp32 run: the sampler amplifies a per-evaluation error of a few 1e-3 about threefold.  The
+# product-mode bound leaves room for what the emulation lacks (tanh.approx SiLU, fp16 FIR arithmetic).
+FULL_N30_FP32_SDR, FULL_N30_FP32_REL = 45.0, 6e-3
+FULL_N30_TC_SDR, FULL_N30_TC_REL = 25.0, 6e-2
+
+
+def test_full_size_n30_against_the_reference_run(golden_dir):
+    """BASELINE.json configs[0] end to end: the UNMODIFIED reference enhanced one 4-s 16 kHz clip on CPU (full-size
+    NCSN++, reverse_diffusion + ald, N = 30, snr 0.5, 60 network evaluations; tests/golden/full_n30.npz, generated by
+    oracle/make_golden.py: golden_full_n30) -- the engine repeats it on the same weights, clip and 61 noise draws (all
+    regenerated from seeds) through sgmse_b200_enhance.  Waveform-level agreement: SI-SDR(reference, engine) as defined in
+    util/other.py:64-68 and rel-L2; PESQ is not installable offline."""
+    from oracle import pipeline as o_pipe
+    from sgmse_b200.synth import synthetic_speech
+    z = np.load(os.path.join(golden_dir, "full_n30.npz"))
+    L, N = int(z["L"]), int(z["N"])
+    sd = o_w.make_state_dict(NetConfig.ncsnpp(), seed=int(z["weight_seed"]))
+    wav = synthetic_speech(1, L, seed=int(z["wav_seed"]))
+    draws = o_sde.make_noise((1, 1, 256, 512), o_sde.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=int(z["noise_seed"]))
+    noise = torch.stack(draws).cuda()
+    ref = z["enh"]
+    for mode, min_sdr, max_rel in (("fp32", FULL_N30_FP32_SDR, FULL_N30_FP32_REL), ("fp16_tc", FULL_N30_TC_SDR, FULL_N30_TC_REL)):
+        eng = Engine(EngineConfig(mode=mode, max_batch=1))
+        eng.load_state_dict(sd)
+        got = eng.enhance(wav.cuda(), noise=noise, N=N, predictor="reverse_diffusion", corrector="ald", corrector_steps=1,
+                          snr=float(z["snr"]))[0].cpu().numpy()
+        sdr, rel = o_pipe.si_sdr(ref, got), float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        print(f"full-size N=30 vs the reference's CPU run ({float(z['cpu_seconds']):.0f} s there): {mode} SI-SDR {sdr:.1f} dB, rel-L2 {rel:.2e}")
+        assert np.isfinite(got).all() and sdr > min_sdr and rel < max_rel
+        eng.close()
+
+
 def test_full_size_ode_on_the_product_path(full_sd):
     """Full-size NCSN++ (65.6 M parameters) in the product mode against the oracle: same tolerance-driven solve at
     rtol = atol = 5e-2 (a handful of steps: the CPU oracle needs ~10 s per evaluation at this size)."""

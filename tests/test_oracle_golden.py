@@ -187,3 +187,20 @@ def test_ode_sampler(golden_dir, name, src):
     assert int(z["denoise_default_raises"]) == 1        # the reference's default denoise=True is a TypeError
     with pytest.raises(TypeError):
         ode.ode_sample(lambda a, b, c: None, y, sde_mod.OUVE(), prior_noise=prior, denoise=True)
+
+
+@pytest.mark.slow
+@pytest.mark.skipif(not os.environ.get("SGMSE_B200_SLOW"), reason="~3 minutes of CPU: set SGMSE_B200_SLOW=1")
+def test_full_size_n30_oracle_equals_reference_run(golden_dir):
+    """BASELINE.json configs[0]: the oracle repeats the unmodified reference's full-size N = 30 enhancement of one 4-s clip
+    (tests/golden/full_n30.npz) from the same seeds."""
+    from oracle import weights as o_w
+    from sgmse_b200.synth import synthetic_speech
+    z = np.load(os.path.join(golden_dir, "full_n30.npz"))
+    cfg = NetConfig.ncsnpp()
+    sd = o_w.make_state_dict(cfg, seed=int(z["weight_seed"]))
+    wav = synthetic_speech(1, int(z["L"]), seed=int(z["wav_seed"]))
+    N = int(z["N"])
+    draws = sde_mod.make_noise((1, 1, 256, 512), sde_mod.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=int(z["noise_seed"]))
+    x_hat, X, _ = pipeline.enhance(sd, cfg, spec_mod.SpecConfig(), sde_mod.OUVE(), wav, draws, N=N, snr=float(z["snr"]), return_spec=True)
+    assert _rel(X[0, 0], z["sample"]) < 1e-4 and _rel(x_hat[0], z["enh"]) < 1e-4
