@@ -1605,7 +1605,7 @@ int sgmse_b200_rk45_host(sgmse_b200_ode_rhs rhs, void* user, double t0, double t
   API_BEGIN
   SG_CHECK(rhs && (y || n == 0) && n >= 0, "bad argument");
   SG_CHECK(atol >= 0, "`atol` must be positive.");
-  OdeHostOps ops{rhs, user, n};
+  OdeHostOps ops{rhs, user, n, {}, {}, {}, {}};
   ops.y.assign(y, y + 2 * n);
   ops.y_new.assign((size_t)2 * n, 0.0);
   ops.stage.assign((size_t)2 * n, 0.0);
