@@ -216,13 +216,16 @@ def refresh(model):
     return eng
 
 
-def install(model, engine: Optional[Engine] = None, rebind_forward: bool = True, refresh_on_eval: bool = False, **kw) -> Engine:
+def install(model, engine: Optional[Engine] = None, rebind_forward=True, refresh_on_eval: bool = False, **kw) -> Engine:
     """Route ``model.get_pc_sampler`` / ``model.get_sb_sampler`` / ``model.enhance`` (and ``model.forward``) through the engine.
 
     In-training evaluation (SURVEY.md §8f-3: ``validation_step`` calls ``self.enhance`` per file, model.py:205-257;
     ``evaluate_model`` calls ``model.get_pc_sampler``, util/inference.py:16-63): install with
     ``rebind_forward=False`` -- training steps keep the differentiable torch forward -- and ``refresh_on_eval=True`` --
-    every ``model.eval()`` (which swaps in the EMA weights) re-snapshots ``model.dnn`` into the engine."""
+    every ``model.eval()`` (which swaps in the EMA weights) re-snapshots ``model.dnn`` into the engine.
+    ``rebind_forward="no_grad"`` additionally sends every forward that runs with gradients disabled to the engine: the
+    validation loss (``validation_step`` -> ``_step`` -> ``self(x_t, y, t)``, model.py:189-198,257-258) while
+    ``training_step`` stays on autograd."""
     if engine is None:
         engine = engine_from_score_model(model, **kw)
     model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "get_ode_sampler", "enhance", "forward", "eval")}
@@ -232,7 +235,17 @@ def install(model, engine: Optional[Engine] = None, rebind_forward: bool = True,
         model.get_ode_sampler = types.MethodType(make_ode_sampler(engine), model)
     model.enhance = types.MethodType(make_enhance(engine), model)
 
-    if rebind_forward:
+    if rebind_forward == "no_grad":
+        # training keeps the differentiable torch forward; whatever runs under torch.no_grad() -- the `_step` of
+        # validation_step (model.py:189-198,257-258: x_t = mean + std z -> self(x_t, y, t) -> loss) -- goes to the engine
+        torch_forward = model.forward                 # bound method of the class (or whatever was installed before)
+
+        def forward(self, x_t, y, t):
+            if torch.is_grad_enabled():
+                return torch_forward(x_t, y, t)
+            return engine.model_forward(x_t, y, t)
+        model.forward = types.MethodType(forward, model)
+    elif rebind_forward:
         def forward(self, x_t, y, t):
             return engine.model_forward(x_t, y, t)    # legacy: score; 'ncsnpp_v2': model.py:283-304
         model.forward = types.MethodType(forward, model)

@@ -117,3 +117,30 @@ def test_enhance_dispatch_follows_model_py():
     with pytest.raises(ValueError, match="Invalid sampler type"):
         m.enhance(wav)
     sgmse_b200.uninstall(m)
+
+
+def test_forward_under_no_grad_goes_to_the_engine():
+    """install(rebind_forward="no_grad"): training_step keeps autograd, the `_step` of validation_step (model.py:189-198,
+    257-258, run by Lightning under torch.no_grad()) evaluates the network on the engine."""
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(()))
+            self.sde = OUVESDE()
+
+        def forward(self, x_t, y, t):
+            return self.w * x_t
+
+    eng = FakeEngine()
+    eng.model_forward = lambda x_t, y, t: (eng.calls.append(("model_forward", tuple(x_t.shape))), x_t * 3)[1]
+    m = M()
+    sgmse_b200.install(m, engine=eng, rebind_forward="no_grad")
+    x = torch.ones(2, 1, 4, 4)
+    out = m(x, x, torch.ones(2))
+    assert out.requires_grad and torch.equal(out, x) and not eng.calls          # autograd path untouched
+    with torch.no_grad():
+        out = m(x, x, torch.ones(2))
+    assert torch.equal(out, 3 * x) and eng.calls == [("model_forward", (2, 1, 4, 4))]
+    sgmse_b200.uninstall(m)
+    with torch.no_grad():
+        assert torch.equal(m(x, x, torch.ones(2)), x)
