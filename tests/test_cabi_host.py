@@ -161,3 +161,22 @@ def test_ode_sampler_host_mirror_errors():
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         eng.ode_sample(y, denoise=False)
     eng.close()
+
+
+def test_plain_c_client(tmp_path):
+    """include/sgmse_b200.h is C: a gcc -std=c99 program (tests/c/cabi_host.c) links libsgmse_b200.so and drives the
+    host-only entry points -- manifest, schedule, RK45 controller with a C callback -- with no Python or C++ around it."""
+    import shutil
+    import subprocess
+    from sgmse_b200 import build
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.load()
+    lib = build.lib_path()
+    exe = str(tmp_path / "cabi_host")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "cabi_host.c"), "-o", exe, lib, "-lm", "-Wl,-rpath," + os.path.dirname(lib)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "cabi_host ok" in r.stdout, r.stdout + r.stderr
