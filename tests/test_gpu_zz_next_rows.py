@@ -163,6 +163,27 @@ def test_full_size_prior_draw_statistics(full_sd):
     eng.close()
 
 
+def test_plain_c_client_on_the_product_path(tmp_path):
+    """tests/c/cabi_gpu.c: a C99 program (no Python, no C++, no CUDA call of its own) enhances two clips through
+    sgmse_b200_enhance with host buffers on the fp16 tcgen05 path and checks finiteness, seed determinism and graph replay."""
+    import shutil
+    import subprocess
+    from sgmse_b200 import _lib, build
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.load()
+    lib = build.lib_path()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cabi_gpu")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "c", "cabi_gpu.c"), "-o", exe, lib, "-lm",
+                        "-Wl,-rpath," + os.path.dirname(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout.strip())
+    assert r.returncode == 0 and "cabi_gpu ok" in r.stdout, r.stdout + r.stderr
+
+
 # ---- full size, product mode (not yet run on a GPU) ----
 def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
     """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM
