@@ -159,8 +159,8 @@ def make_ode_sampler(engine: Engine):
                                            utt_offset=i * minibatch, **kw)
                 samples.append(smp)
                 ns.append(n)
-            # (the reference returns `sample`, the LAST minibatch only, model.py:388-389 -- a typo for `samples`;
-            #  the concatenation is what its PC twin returns, model.py:365-367)
+            # (the reference returns `sample`, the LAST minibatch only, model.py:389 -- a typo for `samples`;
+            #  the concatenation is what its PC twin returns, model.py:367)
             return torch.cat(samples, dim=0), ns
         return batched_sampling_fn
     return get_ode_sampler
