@@ -206,6 +206,33 @@ def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
     eng.close()
 
 
+def test_full_size_48k_sampler_properties():
+    """BASELINE.json configs[2] shape (ncsnpp_48k defaults, F = 768, T = 512, 48 kHz SDE theta 2 / sigma 0.1-1): one
+    predictor-corrector step on two utterances -- finite, graph replay == eager launch sequence (bitwise), utterance 1
+    alone at offset 1 == utterance 1 of the pair, and the host-buffer enhance path at 48 kHz (192 000-sample clips)."""
+    cfg = NetConfig.ncsnpp_48k()
+    sd = o_w.make_state_dict(cfg, seed=4)
+    eng = Engine(EngineConfig.ncsnpp_48k(mode="fp16_tc", max_batch=2))
+    eng.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    y = (torch.complex(torch.randn(2, 1, 768, 512, generator=g), torch.randn(2, 1, 768, 512, generator=g)) * 0.1).cuda()
+    a, nfe = eng.pc_sample(y, N=1, seed=3)
+    assert nfe == 2 and torch.isfinite(torch.view_as_real(a)).all()
+    b, _ = eng.pc_sample(y, N=1, seed=3)
+    assert torch.equal(a, b)
+    eng.set_option("use_graphs", 0)
+    c, _ = eng.pc_sample(y, N=1, seed=3)
+    assert torch.equal(a, c)
+    d, _ = eng.pc_sample(y[1:2], N=1, seed=3, utt_offset=1)
+    assert torch.equal(a[1:2], d)
+    eng.set_option("use_graphs", 1)
+    wav = 0.1 * torch.randn(2, 192000, generator=g)
+    out = eng.enhance(wav.pin_memory(), N=1, seed=3, pad_mode="reflection")
+    assert out.shape == wav.shape and not out.is_cuda and torch.isfinite(out).all()
+    assert eng.counter("tc_convs_last_forward") > 0
+    eng.close()
+
+
 # Bounds of the N = 30 run.  Emulating the product mode's storage precision on the CPU oracle (conv operands and results
 # rounded to fp16, fp32 accumulation; 0.5-s clip, same 60 evaluations) moves the enhanced waveform by rel-L2 8.9e-3 =
 # 41 dB SI-SDR against the fp32 run: the sampler amplifies a per-evaluation error of a few 1e-3 about threefold.  The
