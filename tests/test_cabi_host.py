@@ -180,3 +180,31 @@ def test_plain_c_client(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "cabi_host ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_shape_contract_is_enforced_on_the_host():
+    """The reference's shape contract: F and T multiples of 2^(levels-1) (6 down-samplings: 64), and for
+    'ncsnpp' F == image_size, or the build-time attention placement disagrees with the run-time trigger (ncsnpp.py:84,308)
+    -- checked by the host-side walk of the launch sequence, no GPU involved."""
+    eng = Engine(CASES[0][1])                                    # full-size 16 kHz NCSN++
+    assert eng.workspace_bytes(1, 256, 512) > 1 << 30
+    assert eng.workspace_bytes(2, 256, 512) > 1.9 * eng.workspace_bytes(1, 256, 512)
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        eng.workspace_bytes(1, 256, 500)                         # pad_spec (util/other.py:76-90) exists for this
+    with pytest.raises(RuntimeError, match="image_size"):
+        eng.workspace_bytes(1, 128, 512)
+    with pytest.raises(RuntimeError, match="bad argument"):
+        eng.workspace_bytes(0, 256, 512)                         # empty batch
+    assert eng.padded_frames(64000) == 512 and eng.padded_frames(63 * 128) == 64 and eng.padded_frames(64 * 128) == 128
+    eng.close()
+    eng48 = Engine(CASES[1][1])                                  # ncsnpp_48k: attention only in the bottleneck, any F % 64 == 0
+    assert eng48.workspace_bytes(1, 768, 512) > eng48.workspace_bytes(1, 256, 512) > 0
+    eng48.close()
+    # sampler settings the reference's registries reject
+    lib = _lib.load()
+    s = Engine(CASES[2][1]).sampler_struct()
+    s.predictor = 7
+    import ctypes as C
+    assert lib.sgmse_b200_noise_draws(C.byref(s)) >= 0           # counting draws is host-only
+    with pytest.raises(ValueError, match="Corrector with name 'x' unknown."):
+        Engine(CASES[2][1]).sampler_struct(corrector="x")
