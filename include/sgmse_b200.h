@@ -206,9 +206,11 @@ long long sgmse_b200_workspace_bytes(sgmse_b200_engine* e, int B, int F, int T);
 /* copy a recorded intermediate activation (see sgmse_b200_set_option "record_taps") as fp32 NCHW to host */
 int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, long long cap, int shape[4]);
 /* options: "record_taps" (0/1), "use_graphs" (0/1), "tc_mask" (bit i set = conv class i may use tcgen05),
- * "time_convs" (0/1: bracket every convolution launch with CUDA events; disables graph replay) */
+ * "time_convs" (0/1: bracket every convolution launch with CUDA events; disables graph replay),
+ * "lanes" (1..8 concurrent launch sequences inside a captured sampler graph), "max_graphs" (captured sampler graphs kept,
+ * least recently used evicted; default 16) */
 int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value);
-/* counters: "kernel_launches" (since creation), "graph_launches", "workspace_bytes", "weights_bytes",
+/* counters: "kernel_launches" (since creation), "graph_launches", "cached_graphs", "workspace_bytes", "weights_bytes",
  * "tc_convs_last_forward", "direct_convs_last_forward", "launches_last_forward",
  * "timed_conv_tc_us" / "timed_conv_tc_mflop" / "timed_conv_tc_kbytes" / "timed_conv_tc_count" /
  * "timed_conv_direct_us" (sums over the launches timed since "time_convs" was switched on) */

@@ -1111,8 +1111,16 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
       cudaGraphDestroy(g);
       long long after = 0;
       for (int i = 0; i < L; ++i) { after += e.lanes[i]->kernel_launches; e.lanes[i]->kernel_launches = saved[i]; }
-      it = e.graphs.emplace(key, GraphEntry{ge, after - before}).first;   // kernels recorded, not executed
+      if ((int)e.graphs.size() >= std::max(1, e.max_graphs)) {           // evict the least recently launched executable
+        auto victim = e.graphs.begin();
+        for (auto g2 = e.graphs.begin(); g2 != e.graphs.end(); ++g2)
+          if (g2->second.last_used < victim->second.last_used) victim = g2;
+        cudaGraphExecDestroy(victim->second.exec);                        // deferred by the runtime if still in flight
+        e.graphs.erase(victim);
+      }
+      it = e.graphs.emplace(key, GraphEntry{ge, after - before, 0}).first;   // kernels recorded, not executed
     }
+    it->second.last_used = ++e.graph_clock;
     CUDA_OK(cudaGraphLaunch(it->second.exec, st));
     ++e.graph_launches;
     e.kernel_launches += it->second.kernel_nodes;
@@ -1721,6 +1729,10 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
     e->arena_need.clear();
     clear_graphs(*e);
   }
+  else if (k == "max_graphs") {
+    SG_CHECK(value >= 1 && value <= 1024, "max_graphs must be in 1..1024");
+    e->max_graphs = (int)value;
+  }
   else if (k == "lanes") {
     SG_CHECK(value >= 1 && value <= 8, "lanes must be in 1..8");
     e->num_lanes = (int)value;
@@ -1741,6 +1753,7 @@ long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key) {
   const std::string k = key;
   if (k == "kernel_launches") return e->kernel_launches;
   if (k == "graph_launches") return e->graph_launches;
+  if (k == "cached_graphs") return (long long)e->graphs.size();
   if (k == "workspace_bytes") return (long long)e->arena.cap;
   if (k == "weights_bytes") return (long long)e->weights_bytes;
   if (k == "tc_convs_last_forward") return e->tc_convs;

@@ -84,6 +84,7 @@ struct ConvTiming {
 struct GraphEntry {
   cudaGraphExec_t exec;
   long long kernel_nodes;
+  long long last_used = 0;   // engine.graph_clock at the last launch (least-recently-used eviction)
 };
 
 struct FwdGraph {            // one captured score-network evaluation on e.state (ODE sampler: t changes per evaluation)
@@ -140,6 +141,8 @@ struct sgmse_b200_engine {
   int persist_rows = 0;                       // capacity of temb_table in rows
 
   std::map<sgmse::GraphKey, sgmse::GraphEntry> graphs;
+  long long graph_clock = 0;
+  int max_graphs = 16;                        // a long-running service sees many (B, T, sampler) keys: keep the 16 most recent
   std::map<std::tuple<int, int, int>, sgmse::FwdGraph> fwd_graphs;   // (B, F, T) -> captured single evaluation
   sgmse::OdeBuffers ode;
   std::map<std::tuple<int, int, int>, size_t> arena_need;   // workspace bytes per (B, F, T)

@@ -117,6 +117,25 @@ def test_ode_sampler_properties(golden_dir):
     assert outs[0][1] == outs[1][1] and torch.equal(outs[0][0], outs[1][0])
 
 
+def test_graph_cache_is_bounded(golden_dir):
+    """A service sees many (batch, frames, sampler) keys: the engine keeps the `max_graphs` most recently used captured
+    sampler graphs and re-captures an evicted one on demand -- results unchanged."""
+    z, sd = load_golden(golden_dir, "ncsnpp_small")
+    eng = small_engine("ncsnpp_small", "fp32", max_batch=2)
+    eng.load_state_dict(sd)
+    eng.set_option("max_graphs", 1)
+    y = torch.from_numpy(z["y"]).cuda()
+    a1, _ = eng.pc_sample(y, N=1, seed=1)
+    a2, _ = eng.pc_sample(y, N=2, seed=1)                      # a second key: evicts the first executable
+    assert eng.counter("cached_graphs") == 1
+    b1, _ = eng.pc_sample(y, N=1, seed=1)                      # captured again
+    assert torch.equal(a1, b1) and eng.counter("cached_graphs") == 1
+    eng.set_option("use_graphs", 0)
+    c2, _ = eng.pc_sample(y, N=2, seed=1)
+    assert torch.equal(a2, c2) and not torch.equal(a1, a2)
+    eng.close()
+
+
 # ---- size-independent properties at the BASELINE.json shapes (configs 2 and 3) ------------------------------------------
 @pytest.mark.parametrize("kind,B,L", [("16k", 16, 64000), ("48k", 8, 192000)])
 def test_full_size_stft_round_trip(kind, B, L):
