@@ -208,7 +208,8 @@ int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, 
 /* options: "record_taps" (0/1), "use_graphs" (0/1), "tc_mask" (bit i set = conv class i may use tcgen05),
  * "time_convs" (0/1: bracket every convolution launch with CUDA events; disables graph replay),
  * "lanes" (1..8 concurrent launch sequences inside a captured sampler graph), "max_graphs" (captured sampler graphs kept,
- * least recently used evicted; default 16) */
+ * least recently used evicted; default 16).  The kernel A/B switches the tools use ("tc_variant", "attn_variant",
+ * "fir_variant", "inconv_variant", "outconv_variant", "tc6_*") select code paths PROCESS-WIDE, not per engine. */
 int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value);
 /* counters: "kernel_launches" (since creation), "graph_launches", "cached_graphs", "workspace_bytes", "weights_bytes",
  * "tc_convs_last_forward", "direct_convs_last_forward", "launches_last_forward",
