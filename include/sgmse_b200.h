@@ -154,7 +154,8 @@ int sgmse_b200_model_forward(sgmse_b200_engine* e, const void* x_t, const void* 
  * dx/dt = theta (y - x) - 0.5 g(t)^2 score(x, y, t) from t = 1 to t = eps with scipy's RK45 (Dormand-Prince 5(4), rtol /
  * atol error control, RMS norm over ALL bins of the batch: the utterances of one call share one adaptive step sequence,
  * as in the reference).  The integrator state is complex128 and stays in HBM; one double per norm crosses to the host.
- * OUVE SDE and the 'ncsnpp' / 'ncsnpp_48k' backbones. */
+ * OUVE SDE; backbones 'ncsnpp' / 'ncsnpp_48k', and 'ncsnpp_v2' with loss_type score_matching / denoiser (the drift calls
+ * ScoreModel.forward, model.py:283-304). */
 typedef struct sgmse_b200_ode {
   double rtol, atol;         /* 1e-5, 1e-5 (sampling/__init__.py:74) */
   double eps;                /* end time; ScoreModel.get_ode_sampler passes t_eps = 0.03 (model.py:375) */

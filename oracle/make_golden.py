@@ -211,6 +211,35 @@ def golden_full_n30(name="full_n30"):
                         cpu_threads=np.int64(torch.get_num_threads()))
 
 
+V2_ODE_PRECOND = {
+    "score": dict(loss_type="score_matching", network_scaling=None, c_in="1", c_out="1/sigma", c_skip="0", sigma_data=0.1),
+    "denoiser_edm_in": dict(loss_type="denoiser", network_scaling="1/t", c_in="edm", c_out="1", c_skip="0", sigma_data=0.1),
+}
+
+
+def golden_ode_v2(name="ode_v2_small"):
+    """The probability-flow ODE sampler on preconditioned 'ncsnpp_v2' score models with the OUVE SDE (get_ode_sampler calls
+    ScoreModel.forward(x, y, t), i.e. model.py:283-304): the weights of ncsnpp_v2_small.npz under two ScoreModel wrappers --
+    a plain score-matching model, and a 'denoiser' model with c_in = 'edm' and 1/t network scaling (every evaluation
+    rescales the network input)."""
+    cfg = NetConfig.ncsnpp_v2(attn_resolutions=(16,), **SMALL)
+    kw = dict(nf=cfg.nf, ch_mult=cfg.ch_mult, image_size=cfg.image_size, attn_resolutions=cfg.attn_resolutions,
+              n_fft=126, hop_length=32)
+    z = np.load(os.path.join(OUT, "ncsnpp_v2_small.npz"))
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w/")}
+    y = torch.from_numpy(z["y"])
+    out = {}
+    for tag, pre in V2_ODE_PRECOND.items():
+        m = refshim.make_score_model(backbone="ncsnpp_v2", seed=3, **kw, **pre)
+        m.dnn.load_state_dict(sd)
+        with refshim.injected_noise(sde_mod.make_noise(tuple(y.shape), 1, seed=19)):
+            smp, nfe = m.get_ode_sampler(y, denoise=False, device="cpu", rtol=1e-3, atol=1e-3)()
+        out[f"x_{tag}"] = _np(smp)
+        out[f"nfe_{tag}"] = np.int64(nfe)
+        print(name, tag, "nfe", nfe, "finite", bool(torch.isfinite(torch.view_as_real(smp)).all()))
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), y=_np(y), prior_seed=np.int64(19), tol=np.float64(1e-3), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     golden_ops()
@@ -218,6 +247,7 @@ def main():
     golden_network("ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
     golden_v2("ncsnpp_v2_small", NetConfig.ncsnpp_v2(attn_resolutions=(16,), **SMALL), seed=3)
     golden_ode("ode_small", "ncsnpp_small", "ncsnpp", NetConfig.ncsnpp(attn_resolutions=(16,), **SMALL), seed=1)
+    golden_ode_v2()
     golden_full_n30()
     golden_ode("ode48k_small", "ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
 

@@ -36,6 +36,12 @@ class OUVE:
         th, ls, smin = self.theta, self.logsig, self.sigma_min
         return math.sqrt(smin ** 2 * math.exp(-2 * th * t) * (math.exp(2 * (th + ls) * t) - 1) * ls / (th + ls))
 
+    def std_tensor(self, t: torch.Tensor) -> torch.Tensor:
+        # sdes.py:206-219 on an fp32 tensor, operation by operation (what ScoreModel.forward's v2 branch calls, model.py:284)
+        sigma_min, theta, logsig = self.sigma_min, self.theta, self.logsig
+        return torch.sqrt((sigma_min ** 2 * torch.exp(-2 * theta * t) * (torch.exp(2 * (theta + logsig) * t) - 1) * logsig)
+                          / (theta + logsig))
+
 
 def timesteps(N: int, eps: float, T: float = 1.0):
     """torch.linspace(T, eps, N) evaluated in fp32 like the reference (sampling/__init__.py:56)."""

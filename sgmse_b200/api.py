@@ -231,8 +231,9 @@ def install(model, engine: Optional[Engine] = None, rebind_forward=True, refresh
     model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "get_ode_sampler", "enhance", "forward", "eval")}
     model._sgmse_b200_engine = engine
     model.get_pc_sampler = types.MethodType(make_pc_sampler(engine, default_N=model.sde.N), model)
-    if type(model.sde).__name__ == "OUVESDE" and engine.cfg.backbone != "ncsnpp_v2":
-        model.get_ode_sampler = types.MethodType(make_ode_sampler(engine), model)
+    if type(model.sde).__name__ == "OUVESDE" and not (engine.cfg.backbone == "ncsnpp_v2" and
+                                                      getattr(engine.cfg, "loss_type", "score_matching") == "data_prediction"):
+        model.get_ode_sampler = types.MethodType(make_ode_sampler(engine), model)    # needs a score model
     model.enhance = types.MethodType(make_enhance(engine), model)
 
     if rebind_forward == "no_grad":

@@ -1160,9 +1160,10 @@ void ensure_ode(Engine& e, size_t px) {
 // shape is captured the first time it runs (that first evaluation itself is eager) and replayed afterwards: an ODE
 // solve is hundreds of evaluations of the same sequence with nothing but t changing, and t lives in device memory
 // (temb row, drift coefficients are kernel arguments of the un-captured drift kernel).
-const float4* forward_on_state(Engine& e, int Bc, int F, int T, cudaStream_t st) {
+const float4* forward_on_state(Engine& e, int Bc, int F, int T, cudaStream_t st, float in_scale = 1.f) {
   Fwd f{e, st, e.temb_table, 0, false, e.cfg.mode == SGMSE_B200_MODE_FP32 ? DT_F32 : DT_F16};
-  const bool graph_ok = e.cfg.use_graphs && !e.time_convs && !e.record_taps && st != nullptr;
+  f.in_scale = in_scale;                                       // c_in(t) of a preconditioned model: a kernel argument, so
+  const bool graph_ok = e.cfg.use_graphs && !e.time_convs && !e.record_taps && st != nullptr && in_scale == 1.f;   // not graphed
   if (!graph_ok) return f.run(e.state, Bc, F, T);
   const auto key = std::make_tuple(Bc, F, T);
   auto it = e.fwd_graphs.find(key);
@@ -1226,12 +1227,19 @@ struct OdeDeviceOps {
     const double g = c.sigma_min * pow((double)c.sigma_max / c.sigma_min, (double)tf) * sqrt(2 * ls);   // sdes.py:188-196
     const float cs = (float)(0.5 * g * g);                      // -g^2 * score * 0.5 with score = -dnn (sdes.py:116-117)
     const float inv_t = 1.0f / tf;
+    const bool v2 = is_v2(e);
+    const Precond pc = v2 ? precond(c, (double)tf) : Precond{1.0, 0.0, 0.0};   // score = a x + b F(c_in x, c_in y, t)
     const int mb = std::max(1, c.max_batch);
     for (int b0 = 0; b0 < B; b0 += mb) {
       const int Bc = std::min(mb, B - b0);
       launch_pack_state(st, e.ode.stage + b0 * px1, Y + b0 * px1, Bc, F, T, e.state); ++e.kernel_launches;
-      const float4* p = forward_on_state(e, Bc, F, T, st);
-      launch_ode_drift(st, e.state, p, Bc, F, T, e.out_layer, inv_t, c.theta, cs, k[slot] + b0 * px1); ++e.kernel_launches;
+      const float4* p = forward_on_state(e, Bc, F, T, st, (float)pc.c_in);
+      if (v2)
+        launch_ode_drift_affine(st, e.state, p, Bc, F, T, e.out_layer, (float)(-(double)c.theta - 0.5 * g * g * pc.a), c.theta,
+                                (float)(-0.5 * g * g * pc.b), k[slot] + b0 * px1);
+      else
+        launch_ode_drift(st, e.state, p, Bc, F, T, e.out_layer, inv_t, c.theta, cs, k[slot] + b0 * px1);
+      ++e.kernel_launches;
     }
   }
   double finish_norm() {
@@ -1258,7 +1266,8 @@ void ode_sample(Engine& e, const float2* Y, int B, int F, int T, const sgmse_b20
                 float2* out, int* nfe, int* stats, cudaStream_t st_in) {
   SG_CHECK(e.loaded, "weights not loaded");
   SG_CHECK(e.cfg.sde_kind == SGMSE_B200_SDE_OUVE, "the probability-flow ODE sampler is implemented for the 'ouve' SDE");
-  SG_CHECK(!is_v2(e), "the probability-flow ODE sampler is implemented for the score models 'ncsnpp' / 'ncsnpp_48k'");
+  SG_CHECK(!is_v2(e) || e.cfg.loss_type != SGMSE_B200_LOSS_DATA_PREDICTION,
+           "the probability-flow ODE sampler needs a score model (loss_type 'score_matching' or 'denoiser')");
   SG_CHECK(o.atol >= 0 && o.rtol >= 0, "`atol` must be positive.");                      // scipy validate_tol
   SG_CHECK(o.eps > 0 && o.eps <= 1, "eps must lie in (0, T=1]");
   cudaStream_t st = st_in;

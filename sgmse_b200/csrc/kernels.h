@@ -190,6 +190,9 @@ void launch_ode_combine(cudaStream_t st, const double2* y, const OdeK& K, int s,
 // k_out = theta (y - x) + cs * out_layer(pyr, inv_t)   [= theta (y - x) - 0.5 g^2 score, score = -dnn]; state = (x, y)
 void launch_ode_drift(cudaStream_t st, const float4* state, const float4* pyr, int N, int H, int W, const OutLayer& ol,
                       float inv_t, float theta, float cs, float2* k_out);
+// k_out = cx x + cy y + cF * output_layer(pyr)   (score of a preconditioned 'ncsnpp_v2' model folded in, see ode.cu)
+void launch_ode_drift_affine(cudaStream_t st, const float4* state, const float4* pyr, int N, int H, int W, const OutLayer& ol,
+                             float cx, float cy, float cF, float2* k_out);
 void launch_ode_init(cudaStream_t st, const float4* state, size_t total, double2* y);     // y = (complex128) state.x
 void launch_ode_finish(cudaStream_t st, const double2* y, size_t total, float2* out);     // out = (complex64) y
 // partial[kOdeNormBlocks]: per-block sums of |v/scale|^2, see ode.cu for the four kinds

@@ -65,6 +65,18 @@ __global__ void ode_drift_kernel(const float4* __restrict__ state, const float4*
   k_out[i] = make_float2(theta * (s.z - s.x) + cs * d.x, theta * (s.w - s.y) + cs * d.y);
 }
 
+// The same drift with the score of a preconditioned 'ncsnpp_v2' model, score = a x + b F, F = output_layer(pyr) of the
+// network evaluated on c_in (x, y) (model.py:283-304):  k = cx x + cy y + cF F  with the host-folded coefficients
+// cx = -theta - 0.5 g^2 a,  cy = theta,  cF = -0.5 g^2 b.
+__global__ void ode_drift_affine_kernel(const float4* __restrict__ state, const float4* __restrict__ pyr, size_t total, OutLayer ol,
+                                        float cx, float cy, float cF, float2* __restrict__ k_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float4 s = state[i];
+  const float2 d = out_layer_ode(ol, pyr[i], 1.0f);
+  k_out[i] = make_float2(cx * s.x + cy * s.z + cF * d.x, cx * s.y + cy * s.w + cF * d.y);
+}
+
 __global__ void ode_init_kernel(const float4* __restrict__ state, size_t total, double2* __restrict__ y) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -127,6 +139,12 @@ void launch_ode_drift(cudaStream_t st, const float4* state, const float4* pyr, i
                       float inv_t, float theta, float cs, float2* k_out) {
   const size_t total = (size_t)N * H * W;
   ode_drift_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(state, pyr, total, ol, inv_t, theta, cs, k_out);
+  CUDA_OK(cudaGetLastError());
+}
+void launch_ode_drift_affine(cudaStream_t st, const float4* state, const float4* pyr, int N, int H, int W, const OutLayer& ol,
+                             float cx, float cy, float cF, float2* k_out) {
+  const size_t total = (size_t)N * H * W;
+  ode_drift_affine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(state, pyr, total, ol, cx, cy, cF, k_out);
   CUDA_OK(cudaGetLastError());
 }
 void launch_ode_init(cudaStream_t st, const float4* state, size_t total, double2* y) {

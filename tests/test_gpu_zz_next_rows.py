@@ -203,6 +203,31 @@ def test_plain_c_client_on_the_product_path(tmp_path):
     assert r.returncode == 0 and "cabi_gpu ok" in r.stdout, r.stdout + r.stderr
 
 
+V2_ODE_PRECOND = {
+    "score": dict(loss_type="score_matching", network_scaling=None, c_in="1", c_out="1/sigma", c_skip="0", sigma_data=0.1),
+    "denoiser_edm_in": dict(loss_type="denoiser", network_scaling="1/t", c_in="edm", c_out="1", c_skip="0", sigma_data=0.1),
+}
+
+
+@pytest.mark.parametrize("tag", list(V2_ODE_PRECOND))
+def test_golden_ode_sampler_on_v2_score_models(golden_dir, tag):
+    """The ODE sampler driven by ScoreModel.forward of preconditioned 'ncsnpp_v2' score models (OUVE SDE): the score
+    a x + b F(c_in x, c_in y) is folded into the drift kernel's coefficients, c_in(t) scales the network input per
+    evaluation ('denoiser_edm_in': not graph-replayed).  Fixture: get_ode_sampler of the unmodified reference."""
+    z = np.load(os.path.join(golden_dir, "ode_v2_small.npz"))
+    _, sd = load_golden(golden_dir, "ncsnpp_v2_small")
+    eng = Engine(EngineConfig.ncsnpp_v2(attn_resolutions=(16,), mode="fp32", sde="ouve", max_batch=2, **SMALL_E, **V2_ODE_PRECOND[tag]))
+    eng.load_state_dict(sd)
+    y = torch.from_numpy(z["y"]).cuda()
+    prior = o_sde.make_noise(tuple(y.shape), 1, seed=int(z["prior_seed"]))[0].cuda()
+    tol = float(z["tol"])
+    x, nfe, st = eng.ode_sample(y, prior_noise=prior, rtol=tol, atol=tol, eps=0.03, denoise=False, return_stats=True)
+    err = rel_l2(x, z[f"x_{tag}"])
+    print(f"v2 ODE {tag}: nfe {nfe} (reference {int(z[f'nfe_{tag}'])}), {st}, rel-L2 {err:.3e}")
+    assert st["status"] == 0 and abs(nfe - int(z[f"nfe_{tag}"])) <= 12 and err < 2e-3
+    eng.close()
+
+
 # ---- full size, product mode (not yet run on a GPU) ----
 def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
     """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM

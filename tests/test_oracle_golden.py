@@ -204,3 +204,27 @@ def test_full_size_n30_oracle_equals_reference_run(golden_dir):
     draws = sde_mod.make_noise((1, 1, 256, 512), sde_mod.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=int(z["noise_seed"]))
     x_hat, X, _ = pipeline.enhance(sd, cfg, spec_mod.SpecConfig(), sde_mod.OUVE(), wav, draws, N=N, snr=float(z["snr"]), return_spec=True)
     assert _rel(X[0, 0], z["sample"]) < 1e-4 and _rel(x_hat[0], z["enh"]) < 1e-4
+
+
+V2_ODE_PRECOND = {
+    "score": dict(loss_type="score_matching", network_scaling=None, c_in="1", c_out="1/sigma", c_skip="0", sigma_data=0.1),
+    "denoiser_edm_in": dict(loss_type="denoiser", network_scaling="1/t", c_in="edm", c_out="1", c_skip="0", sigma_data=0.1),
+}
+
+
+@pytest.mark.parametrize("tag", list(V2_ODE_PRECOND))
+def test_ode_sampler_on_v2_score_models(golden_dir, tag):
+    """get_ode_sampler on preconditioned 'ncsnpp_v2' score models with the OUVE SDE (the drift calls ScoreModel.forward,
+    model.py:283-304) against the unmodified reference: same number of evaluations, same state."""
+    from oracle import ode
+    z = np.load(os.path.join(golden_dir, "ode_v2_small.npz"))
+    _, sd = _load(golden_dir, "ncsnpp_v2_small")
+    y = torch.from_numpy(z["y"])
+    prior = sde_mod.make_noise(tuple(y.shape), 1, seed=int(z["prior_seed"]))[0]
+    ou = sde_mod.OUVE()
+    pre = V2_ODE_PRECOND[tag]
+    tol = float(z["tol"])
+    x, nfe = ode.ode_sample(lambda a, b, c: ncsnpp.precond_forward(sd, V2_CFG, pre, ou.std_tensor, a, b, c), y, ou, eps=0.03,
+                            rtol=tol, atol=tol, prior_noise=prior)
+    assert nfe == int(z[f"nfe_{tag}"])
+    assert _rel(x, z[f"x_{tag}"]) < 1e-5
