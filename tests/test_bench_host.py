@@ -1,0 +1,54 @@
+"""Host-side pieces of bench.py (no GPU): workload description per BASELINE.json config, peak lookup, parsing of the
+nvidia-smi clock samples that end up in the JSON line's "clocks" object."""
+import importlib
+import sys
+
+import pytest
+
+
+@pytest.fixture()
+def bench(monkeypatch):
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    import bench as b
+    return importlib.reload(b)
+
+
+def test_default_workload_is_baseline_config_2(bench, monkeypatch):
+    a = bench.parse()
+    bench.apply_workload(a)
+    cfg = bench.workload_config(a)
+    assert (a.batch, a.micro_batch, a.N, a.snr, a.steps, a.warmup) == (16, 16, 30, 0.5, 3, 3)
+    assert "VoiceBank" in cfg["workload"] and "N=30" in cfg["workload"] and cfg["baseline_config"] == 2
+    assert cfg["global_batch"] == 16 and "no data-path collective" in cfg["parallelism"] and "L2" in cfg["l2"]
+    assert "model" not in cfg                                   # this tier's config names a workload, not a model
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--config", "3"])
+    a = bench.parse()
+    bench.apply_workload(a)
+    assert (a.batch, a.N, bench.SR, bench.GFLOP_PER_FORWARD, a.no_cpu_baseline) == (8, 30, 48000, 3187.6, True)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--config", "4", "--gpus", "2"])
+    a = bench.parse()
+    bench.apply_workload(a)
+    cfg = bench.workload_config(a)
+    assert (a.batch, a.N, a.snr) == (32, 50, 0.33) and cfg["global_batch"] == 64 and "100 network evaluations" in cfg["workload"]
+
+
+def test_peaks_come_from_the_driver_file_or_the_stated_fallback(bench):
+    p = bench.peaks()
+    assert p["source"].startswith("MEASURED_PEAKS.json") or p["source"].startswith("fallback")
+    assert 3000 < p["hbm_gbs"] < 9000 and 800 < p["tflops_sustained"] <= p["tflops_burst"] < 2500
+
+
+def test_clock_samples_are_reduced_to_median_max_and_reasons(bench):
+    cs = bench.ClockSampler(0)
+    cs.rows = [
+        ["0", "1755", "1965", "980.1", "Not Active", "Not Active", "Not Active", "Active"],
+        ["0", "1650", "1965", "995.0", "Not Active", "Not Active", "Not Active", "Active"],
+        ["0", "1800", "1965", "700.2", "Not Active", "Not Active", "Not Active", "Not Active"],
+        ["garbage"],
+        ["0", "[N/A]", "1965", "1.0", "Not Active", "Not Active", "Not Active", "Not Active"],
+    ]
+    out = cs.stop()
+    assert out == {"sm_mhz": 1755.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3}
+    cs.rows = [["0", "600", "1965", "100", "Active", "Active", "Not Active", "Not Active"]]
+    assert cs.stop()["reasons"] == ["hw_slowdown", "hw_thermal_slowdown"]
+    assert bench.ClockSampler(0).stop() == {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
