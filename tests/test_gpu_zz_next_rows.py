@@ -64,8 +64,6 @@ def test_batched_service_equals_clip_by_clip_enhancement(golden_dir):
     eng.close()
 
 
-
-
 # ---- probability-flow ODE sampler ---------------------------------------------------------------
 @pytest.mark.parametrize("name,src", [("ode_small", "ncsnpp_small"), ("ode48k_small", "ncsnpp48k_small")])
 @pytest.mark.parametrize("graphs", [False, True])
@@ -117,25 +115,6 @@ def test_ode_sampler_properties(golden_dir):
     assert outs[0][1] == outs[1][1] and torch.equal(outs[0][0], outs[1][0])
 
 
-def test_graph_cache_is_bounded(golden_dir):
-    """A service sees many (batch, frames, sampler) keys: the engine keeps the `max_graphs` most recently used captured
-    sampler graphs and re-captures an evicted one on demand -- results unchanged."""
-    z, sd = load_golden(golden_dir, "ncsnpp_small")
-    eng = small_engine("ncsnpp_small", "fp32", max_batch=2)
-    eng.load_state_dict(sd)
-    eng.set_option("max_graphs", 1)
-    y = torch.from_numpy(z["y"]).cuda()
-    a1, _ = eng.pc_sample(y, N=1, seed=1)
-    a2, _ = eng.pc_sample(y, N=2, seed=1)                      # a second key: evicts the first executable
-    assert eng.counter("cached_graphs") == 1
-    b1, _ = eng.pc_sample(y, N=1, seed=1)                      # captured again
-    assert torch.equal(a1, b1) and eng.counter("cached_graphs") == 1
-    eng.set_option("use_graphs", 0)
-    c2, _ = eng.pc_sample(y, N=2, seed=1)
-    assert torch.equal(a2, c2) and not torch.equal(a1, a2)
-    eng.close()
-
-
 # ---- size-independent properties at the BASELINE.json shapes (configs 2 and 3) ------------------------------------------
 @pytest.mark.parametrize("kind,B,L", [("16k", 16, 64000), ("48k", 8, 192000)])
 def test_full_size_stft_round_trip(kind, B, L):
@@ -182,101 +161,6 @@ def test_full_size_prior_draw_statistics(full_sd):
     eng.close()
 
 
-def test_plain_c_client_on_the_product_path(tmp_path):
-    """tests/c/cabi_gpu.c: a C99 program (no Python, no C++, no CUDA call of its own) enhances two clips through
-    sgmse_b200_enhance with host buffers on the fp16 tcgen05 path and checks finiteness, seed determinism and graph replay."""
-    import shutil
-    import subprocess
-    from sgmse_b200 import _lib, build
-    if shutil.which("gcc") is None:
-        pytest.skip("no gcc")
-    _lib.load()
-    lib = build.lib_path()
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = str(tmp_path / "cabi_gpu")
-    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
-                        os.path.join(root, "tests", "c", "cabi_gpu.c"), "-o", exe, lib, "-lm",
-                        "-Wl,-rpath," + os.path.dirname(lib)], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    print(r.stdout.strip())
-    assert r.returncode == 0 and "cabi_gpu ok" in r.stdout, r.stdout + r.stderr
-
-
-V2_ODE_PRECOND = {
-    "score": dict(loss_type="score_matching", network_scaling=None, c_in="1", c_out="1/sigma", c_skip="0", sigma_data=0.1),
-    "denoiser_edm_in": dict(loss_type="denoiser", network_scaling="1/t", c_in="edm", c_out="1", c_skip="0", sigma_data=0.1),
-}
-
-
-@pytest.mark.parametrize("tag", list(V2_ODE_PRECOND))
-def test_golden_ode_sampler_on_v2_score_models(golden_dir, tag):
-    """The ODE sampler driven by ScoreModel.forward of preconditioned 'ncsnpp_v2' score models (OUVE SDE): the score
-    a x + b F(c_in x, c_in y) is folded into the drift kernel's coefficients, c_in(t) scales the network input per
-    evaluation ('denoiser_edm_in': not graph-replayed).  Fixture: get_ode_sampler of the unmodified reference."""
-    z = np.load(os.path.join(golden_dir, "ode_v2_small.npz"))
-    _, sd = load_golden(golden_dir, "ncsnpp_v2_small")
-    eng = Engine(EngineConfig.ncsnpp_v2(attn_resolutions=(16,), mode="fp32", sde="ouve", max_batch=2, **SMALL_E, **V2_ODE_PRECOND[tag]))
-    eng.load_state_dict(sd)
-    y = torch.from_numpy(z["y"]).cuda()
-    prior = o_sde.make_noise(tuple(y.shape), 1, seed=int(z["prior_seed"]))[0].cuda()
-    tol = float(z["tol"])
-    x, nfe, st = eng.ode_sample(y, prior_noise=prior, rtol=tol, atol=tol, eps=0.03, denoise=False, return_stats=True)
-    err = rel_l2(x, z[f"x_{tag}"])
-    print(f"v2 ODE {tag}: nfe {nfe} (reference {int(z[f'nfe_{tag}'])}), {st}, rel-L2 {err:.3e}")
-    assert st["status"] == 0 and abs(nfe - int(z[f"nfe_{tag}"])) <= 12 and err < 2e-3
-    eng.close()
-
-
-# ---- full size, product mode (not yet run on a GPU) ----
-def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
-    """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM
-    preconditioning -- c_in goes through the mma.sync input conv and the input pyramid, c_skip / c_out / 1/sigma through
-    the update coefficients -- two Schroedinger-bridge ODE steps against the oracle."""
-    pre = dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1)
-    cfg = NetConfig.ncsnpp_v2()
-    eng = Engine(EngineConfig.ncsnpp_v2(mode="fp16_tc", max_batch=1, sde="sbve", sb_k=2.6, sb_c=0.4, **pre))
-    eng.load_state_dict(full_sd)
-    g = torch.Generator().manual_seed(17)
-    y = torch.complex(torch.randn(1, 1, 256, 128, generator=g), torch.randn(1, 1, 256, 128, generator=g)) * 0.3
-    sb = o_sde.SBVE(2.6, 0.4)
-    with torch.no_grad():
-        ref, _ = o_sde.sb_sample(lambda a, b, c: o_net.precond_forward(full_sd, cfg, pre, sb.std, a, b, c), y, sb, N=2,
-                                 sampler_type="ode")
-    got, n = eng.sb_sample(y.cuda(), sampler_type="ode", N=2)
-    err = rel_l2(got, ref)
-    print(f"full-size v2 SB-ODE (fp16_tc, edm preconditioning): rel-L2 {err:.3e}")
-    assert n == 50 and eng.counter("tc_convs_last_forward") > 0 and err < 3e-2
-    eng.close()
-
-
-def test_full_size_48k_sampler_properties():
-    """BASELINE.json configs[2] shape (ncsnpp_48k defaults, F = 768, T = 512, 48 kHz SDE theta 2 / sigma 0.1-1): one
-    predictor-corrector step on two utterances -- finite, graph replay == eager launch sequence (bitwise), utterance 1
-    alone at offset 1 == utterance 1 of the pair, and the host-buffer enhance path at 48 kHz (192 000-sample clips)."""
-    cfg = NetConfig.ncsnpp_48k()
-    sd = o_w.make_state_dict(cfg, seed=4)
-    eng = Engine(EngineConfig.ncsnpp_48k(mode="fp16_tc", max_batch=2))
-    eng.load_state_dict(sd)
-    g = torch.Generator().manual_seed(5)
-    y = (torch.complex(torch.randn(2, 1, 768, 512, generator=g), torch.randn(2, 1, 768, 512, generator=g)) * 0.1).cuda()
-    a, nfe = eng.pc_sample(y, N=1, seed=3)
-    assert nfe == 2 and torch.isfinite(torch.view_as_real(a)).all()
-    b, _ = eng.pc_sample(y, N=1, seed=3)
-    assert torch.equal(a, b)
-    eng.set_option("use_graphs", 0)
-    c, _ = eng.pc_sample(y, N=1, seed=3)
-    assert torch.equal(a, c)
-    d, _ = eng.pc_sample(y[1:2], N=1, seed=3, utt_offset=1)
-    assert torch.equal(a[1:2], d)
-    eng.set_option("use_graphs", 1)
-    wav = 0.1 * torch.randn(2, 192000, generator=g)
-    out = eng.enhance(wav.pin_memory(), N=1, seed=3, pad_mode="reflection")
-    assert out.shape == wav.shape and not out.is_cuda and torch.isfinite(out).all()
-    assert eng.counter("tc_convs_last_forward") > 0
-    eng.close()
-
-
 # Bounds of the N = 30 run.  Emulating the product mode's storage precision on the CPU oracle (conv operands and results
 # rounded to fp16, fp32 accumulation; 0.5-s clip, same 60 evaluations) moves the enhanced waveform by rel-L2 8.9e-3 =
 # 41 dB SI-SDR against the fp32 run: the sampler amplifies a per-evaluation error of a few 1e-3 about threefold.  The
@@ -311,6 +195,28 @@ def test_full_size_n30_against_the_reference_run(golden_dir):
         eng.close()
 
 
+# ---- full size, product mode (not yet run on a GPU) ----
+def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
+    """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM
+    preconditioning -- c_in goes through the mma.sync input conv and the input pyramid, c_skip / c_out / 1/sigma through
+    the update coefficients -- two Schroedinger-bridge ODE steps against the oracle."""
+    pre = dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1)
+    cfg = NetConfig.ncsnpp_v2()
+    eng = Engine(EngineConfig.ncsnpp_v2(mode="fp16_tc", max_batch=1, sde="sbve", sb_k=2.6, sb_c=0.4, **pre))
+    eng.load_state_dict(full_sd)
+    g = torch.Generator().manual_seed(17)
+    y = torch.complex(torch.randn(1, 1, 256, 128, generator=g), torch.randn(1, 1, 256, 128, generator=g)) * 0.3
+    sb = o_sde.SBVE(2.6, 0.4)
+    with torch.no_grad():
+        ref, _ = o_sde.sb_sample(lambda a, b, c: o_net.precond_forward(full_sd, cfg, pre, sb.std, a, b, c), y, sb, N=2,
+                                 sampler_type="ode")
+    got, n = eng.sb_sample(y.cuda(), sampler_type="ode", N=2)
+    err = rel_l2(got, ref)
+    print(f"full-size v2 SB-ODE (fp16_tc, edm preconditioning): rel-L2 {err:.3e}")
+    assert n == 50 and eng.counter("tc_convs_last_forward") > 0 and err < 3e-2
+    eng.close()
+
+
 def test_full_size_ode_on_the_product_path(full_sd):
     """Full-size NCSN++ (65.6 M parameters) in the product mode against the oracle: same tolerance-driven solve at
     rtol = atol = 5e-2 (a handful of steps; T = 128 as in test_full_size_forward)."""
@@ -330,3 +236,95 @@ def test_full_size_ode_on_the_product_path(full_sd):
     assert st["status"] == 0 and abs(nfe - nfe_ref) <= 12 and err < 3e-2
     assert eng.counter("tc_convs_last_forward") > 0
     eng.close()
+
+
+def test_full_size_48k_sampler_properties():
+    """BASELINE.json configs[2] shape (ncsnpp_48k defaults, F = 768, T = 512, 48 kHz SDE theta 2 / sigma 0.1-1): one
+    predictor-corrector step on two utterances -- finite, graph replay == eager launch sequence (bitwise), utterance 1
+    alone at offset 1 == utterance 1 of the pair, and the host-buffer enhance path at 48 kHz (192 000-sample clips)."""
+    cfg = NetConfig.ncsnpp_48k()
+    sd = o_w.make_state_dict(cfg, seed=4)
+    eng = Engine(EngineConfig.ncsnpp_48k(mode="fp16_tc", max_batch=2))
+    eng.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    y = (torch.complex(torch.randn(2, 1, 768, 512, generator=g), torch.randn(2, 1, 768, 512, generator=g)) * 0.1).cuda()
+    a, nfe = eng.pc_sample(y, N=1, seed=3)
+    assert nfe == 2 and torch.isfinite(torch.view_as_real(a)).all()
+    b, _ = eng.pc_sample(y, N=1, seed=3)
+    assert torch.equal(a, b)
+    eng.set_option("use_graphs", 0)
+    c, _ = eng.pc_sample(y, N=1, seed=3)
+    assert torch.equal(a, c)
+    d, _ = eng.pc_sample(y[1:2], N=1, seed=3, utt_offset=1)
+    assert torch.equal(a[1:2], d)
+    eng.set_option("use_graphs", 1)
+    wav = 0.1 * torch.randn(2, 192000, generator=g)
+    out = eng.enhance(wav.pin_memory(), N=1, seed=3, pad_mode="reflection")
+    assert out.shape == wav.shape and not out.is_cuda and torch.isfinite(out).all()
+    assert eng.counter("tc_convs_last_forward") > 0
+    eng.close()
+
+
+V2_ODE_PRECOND = {
+    "score": dict(loss_type="score_matching", network_scaling=None, c_in="1", c_out="1/sigma", c_skip="0", sigma_data=0.1),
+    "denoiser_edm_in": dict(loss_type="denoiser", network_scaling="1/t", c_in="edm", c_out="1", c_skip="0", sigma_data=0.1),
+}
+
+
+@pytest.mark.parametrize("tag", list(V2_ODE_PRECOND))
+def test_golden_ode_sampler_on_v2_score_models(golden_dir, tag):
+    """The ODE sampler driven by ScoreModel.forward of preconditioned 'ncsnpp_v2' score models (OUVE SDE): the score
+    a x + b F(c_in x, c_in y) is folded into the drift kernel's coefficients, c_in(t) scales the network input per
+    evaluation ('denoiser_edm_in': not graph-replayed).  Fixture: get_ode_sampler of the unmodified reference."""
+    z = np.load(os.path.join(golden_dir, "ode_v2_small.npz"))
+    _, sd = load_golden(golden_dir, "ncsnpp_v2_small")
+    eng = Engine(EngineConfig.ncsnpp_v2(attn_resolutions=(16,), mode="fp32", sde="ouve", max_batch=2, **SMALL_E, **V2_ODE_PRECOND[tag]))
+    eng.load_state_dict(sd)
+    y = torch.from_numpy(z["y"]).cuda()
+    prior = o_sde.make_noise(tuple(y.shape), 1, seed=int(z["prior_seed"]))[0].cuda()
+    tol = float(z["tol"])
+    x, nfe, st = eng.ode_sample(y, prior_noise=prior, rtol=tol, atol=tol, eps=0.03, denoise=False, return_stats=True)
+    err = rel_l2(x, z[f"x_{tag}"])
+    print(f"v2 ODE {tag}: nfe {nfe} (reference {int(z[f'nfe_{tag}'])}), {st}, rel-L2 {err:.3e}")
+    assert st["status"] == 0 and abs(nfe - int(z[f"nfe_{tag}"])) <= 12 and err < 2e-3
+    eng.close()
+
+
+def test_graph_cache_is_bounded(golden_dir):
+    """A service sees many (batch, frames, sampler) keys: the engine keeps the `max_graphs` most recently used captured
+    sampler graphs and re-captures an evicted one on demand -- results unchanged."""
+    z, sd = load_golden(golden_dir, "ncsnpp_small")
+    eng = small_engine("ncsnpp_small", "fp32", max_batch=2)
+    eng.load_state_dict(sd)
+    eng.set_option("max_graphs", 1)
+    y = torch.from_numpy(z["y"]).cuda()
+    a1, _ = eng.pc_sample(y, N=1, seed=1)
+    a2, _ = eng.pc_sample(y, N=2, seed=1)                      # a second key: evicts the first executable
+    assert eng.counter("cached_graphs") == 1
+    b1, _ = eng.pc_sample(y, N=1, seed=1)                      # captured again
+    assert torch.equal(a1, b1) and eng.counter("cached_graphs") == 1
+    eng.set_option("use_graphs", 0)
+    c2, _ = eng.pc_sample(y, N=2, seed=1)
+    assert torch.equal(a2, c2) and not torch.equal(a1, a2)
+    eng.close()
+
+
+def test_plain_c_client_on_the_product_path(tmp_path):
+    """tests/c/cabi_gpu.c: a C99 program (no Python, no C++, no CUDA call of its own) enhances two clips through
+    sgmse_b200_enhance with host buffers on the fp16 tcgen05 path and checks finiteness, seed determinism and graph replay."""
+    import shutil
+    import subprocess
+    from sgmse_b200 import _lib, build
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.load()
+    lib = build.lib_path()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cabi_gpu")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "c", "cabi_gpu.c"), "-o", exe, lib, "-lm",
+                        "-Wl,-rpath," + os.path.dirname(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout.strip())
+    assert r.returncode == 0 and "cabi_gpu ok" in r.stdout, r.stdout + r.stderr
