@@ -247,9 +247,9 @@ def main():
     golden_network("ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
     golden_v2("ncsnpp_v2_small", NetConfig.ncsnpp_v2(attn_resolutions=(16,), **SMALL), seed=3)
     golden_ode("ode_small", "ncsnpp_small", "ncsnpp", NetConfig.ncsnpp(attn_resolutions=(16,), **SMALL), seed=1)
-    golden_ode_v2()
-    golden_full_n30()
     golden_ode("ode48k_small", "ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
+    golden_ode_v2()
+    golden_full_n30()            # ~2.5 minutes: the full-size reference run
 
 
 if __name__ == "__main__":
