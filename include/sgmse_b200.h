@@ -34,6 +34,7 @@
  *                                    model.py:411-412,457-458
  *   sgmse_b200_enhance               ScoreModel.enhance                    sgmse/model.py:426-465
  *                                    (= enhancement.py:75-96 per file)
+ *   sgmse_b200_enhance_ode           ScoreModel.enhance, sde.sampler_type == 'ode'   sgmse/model.py:446-447
  *   sgmse_b200_load_weights          model.dnn.state_dict() after eval()   sgmse/model.py:111-125 (EMA swap)
  *
  * Threading: one engine per (device, caller); an engine is not thread-safe.  All work is enqueued on the
@@ -200,6 +201,12 @@ int sgmse_b200_synthesis(sgmse_b200_engine* e, const void* X, const float* norm,
  * recommended); the H2D / D2H copies are part of the call and it returns after the result is in `out`. */
 int sgmse_b200_enhance(sgmse_b200_engine* e, const float* wav, int B, int L, const sgmse_b200_sampler* s,
                        const void* noise, float* out, int host_buffers, void* stream);
+
+/* The same with the probability-flow ODE sampler (ScoreModel.enhance with sde.sampler_type == 'ode', model.py:446-447):
+ * every utterance is its own ODE system (the reference calls enhance() per file); nfe (nullable) receives B counts.
+ * prior_noise: NULL or device c64 [B,1,F,Tpad]. */
+int sgmse_b200_enhance_ode(sgmse_b200_engine* e, const float* wav, int B, int L, const sgmse_b200_ode* o, int pad_mode,
+                           const void* prior_noise, float* out, int host_buffers, int* nfe, void* stream);
 
 /* Introspection / debugging */
 /* bytes of activation workspace one forward pass of (B, F, T) needs; host-only (no CUDA call); -1 on error */

@@ -181,14 +181,9 @@ def make_enhance(engine: Engine):
             x_hat = engine.enhance(yy.detach().cpu().float(), N=self.sde.N, kind="sb_" + st, sb_eps=1e-4, sb_n_steps=50, **common)
             sb_nfe = 50
         elif getattr(self.sde, "sampler_type", "pc") == "ode":      # model.py:446-447: get_ode_sampler(Y, N=N, **kwargs)
-            wav = yy.detach().float().to(engine.device or "cuda")
-            x_parts = []
             ode_kw = {k: kwargs[k] for k in ("rtol", "atol", "eps", "method") if k in kwargs}
-            for b in range(wav.shape[0]):                                # enhance() is per file in the reference
-                Y, norm = engine.analysis(wav[b:b + 1], pad_mode=common["pad_mode"])
-                X, sb_nfe = engine.ode_sample(Y, denoise=kwargs.get("denoise", True), seed=common["seed"], utt_offset=b, **ode_kw)
-                x_parts.append(engine.synthesis(X, norm, wav.shape[1]))
-            x_hat = torch.cat(x_parts).cpu()
+            x_hat, nfes = engine.enhance_ode(yy.detach().cpu().float(), denoise=kwargs.get("denoise", True), **ode_kw, **common)
+            sb_nfe = nfes[-1]                                            # one ODE system per clip, as enhance() is per file
         else:
             if getattr(self.sde, "sampler_type", "pc") != "pc":
                 raise ValueError("Invalid sampler type for SGMSE sampling: {}".format(sampler_type))   # model.py:448-449

@@ -1430,6 +1430,37 @@ void enhance(Engine& e, const float* wav, int B, int L, const sgmse_b200_sampler
   }
 }
 
+// ScoreModel.enhance with sde.sampler_type == 'ode' (model.py:446-447): every utterance is its own ODE system, as
+// enhance() is called per file in the reference.
+void enhance_ode(Engine& e, const float* wav, int B, int L, const sgmse_b200_ode& o, int pad_mode, const float2* prior_noise,
+                 float* out, bool host, int* nfe, cudaStream_t st) {
+  const int Tpad = padded_frames(e, L), F = e.cfg.n_fft / 2 + 1;
+  const size_t px1 = (size_t)F * Tpad, px = (size_t)B * px1;
+  const size_t wav_bytes = ((size_t)B * L * 4 + 255) & ~(size_t)255;
+  ensure_stft_buf(e, 2, 2 * wav_bytes + 256 + ((size_t)B * 4 + 255) / 256 * 256 + 2 * px * 8);
+  uint8_t* base = (uint8_t*)e.stft_buf[2];
+  float* wav_d = (float*)base;
+  float* out_d = (float*)(base + wav_bytes);
+  float* norm = (float*)(base + 2 * wav_bytes);
+  float2* Y = (float2*)(base + 2 * wav_bytes + ((size_t)B * 4 + 255) / 256 * 256);
+  float2* X = Y + px;
+  const float* wsrc = wav;
+  if (host) { CUDA_OK(cudaMemcpyAsync(wav_d, wav, (size_t)B * L * 4, cudaMemcpyHostToDevice, st)); wsrc = wav_d; }
+  analysis(e, wsrc, B, L, pad_mode, Y, norm, st);
+  for (int b = 0; b < B; ++b) {
+    sgmse_b200_ode ob = o;
+    ob.utt_offset = o.utt_offset + b;
+    ode_sample(e, Y + b * px1, 1, F, Tpad, ob, prior_noise ? prior_noise + b * px1 : nullptr, X + b * px1, nfe ? nfe + b : nullptr,
+               nullptr, st);
+  }
+  float* odst = host ? out_d : out;
+  synthesis(e, X, norm, B, Tpad, L, odst, st);
+  if (host) {
+    CUDA_OK(cudaMemcpyAsync(out, out_d, (size_t)B * L * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1653,6 +1684,14 @@ int sgmse_b200_enhance(sgmse_b200_engine* e, const float* wav, int B, int L, con
   API_BEGIN
   SG_CHECK(e && wav && s && out && B > 0 && L > 0, "bad argument");
   enhance(*e, wav, B, L, *s, (const float2*)noise, out, host_buffers != 0, (cudaStream_t)stream);
+  API_END
+}
+
+int sgmse_b200_enhance_ode(sgmse_b200_engine* e, const float* wav, int B, int L, const sgmse_b200_ode* o, int pad_mode,
+                           const void* prior_noise, float* out, int host_buffers, int* nfe, void* stream) {
+  API_BEGIN
+  SG_CHECK(e && wav && o && out && B > 0 && L > 0, "bad argument");
+  enhance_ode(*e, wav, B, L, *o, pad_mode, (const float2*)prior_noise, out, host_buffers != 0, nfe, (cudaStream_t)stream);
   API_END
 }
 

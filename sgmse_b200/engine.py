@@ -425,6 +425,38 @@ class Engine:
                                                _stream_ptr()))
         return out
 
+    def enhance_ode(self, wav: torch.Tensor, prior_noise: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                    rtol: float = 1e-5, atol: float = 1e-5, eps: Optional[float] = None, denoise: bool = True,
+                    method: str = "RK45", seed: int = 0, utt_offset: int = 0, pad_mode: str = "zero_pad", max_attempts: int = 0):
+        """``ScoreModel.enhance`` with ``sde.sampler_type == 'ode'`` (model.py:446-447) in one call
+        (sgmse_b200_enhance_ode): wav f32 [B,L] (host or device) -> (enhanced wav [B,L] on the same side, nfe list).
+        Every utterance is its own ODE system.  ``denoise`` as in :meth:`ode_sample` (the reference default raises)."""
+        if method != "RK45":
+            raise NotImplementedError("only scipy's default method 'RK45' is implemented on the device")
+        if denoise:
+            raise TypeError("ReverseDiffusionPredictor.update_fn() missing 1 required positional argument: 'stepsize' "
+                            "(the reference's get_ode_sampler(denoise=True) fails the same way; pass denoise=False)")
+        self._use_device()
+        wav = wav.to(torch.float32).contiguous()
+        B, L = wav.shape
+        host = not wav.is_cuda
+        if out is None:
+            out = torch.empty_like(wav, pin_memory=True) if host else torch.empty_like(wav)
+        o = _lib.Ode()
+        o.rtol, o.atol = float(rtol), float(atol)
+        o.eps = float(self.cfg.t_eps if eps is None else eps)
+        o.max_attempts = int(max_attempts)
+        o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        o.utt_offset = int(utt_offset)
+        nptr = None
+        if prior_noise is not None:
+            prior_noise = self._c64(prior_noise)
+            nptr = prior_noise.data_ptr()
+        nfe = (C.c_int * B)()
+        _lib.check(self.lib.sgmse_b200_enhance_ode(self._h, wav.data_ptr(), B, L, C.byref(o), _lookup(PAD_MODES, pad_mode, "Pad mode"),
+                                                   nptr, out.data_ptr(), int(host), nfe, _stream_ptr()))
+        return out, [int(v) for v in nfe]
+
     # ---- introspection ---------------------------------------------------------------------------
     def set_option(self, key: str, value: int):
         _lib.check(self.lib.sgmse_b200_set_option(self._h, key.encode(), int(value)))

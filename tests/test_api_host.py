@@ -39,6 +39,12 @@ class FakeEngine:
         self.calls.append(("synthesis", tuple(X.shape), length))
         return torch.ones(X.shape[0], length) * norm[:, None]
 
+    def enhance_ode(self, wav, denoise=True, **kw):
+        self.calls.append(("enhance_ode", tuple(wav.shape), denoise, kw))
+        if denoise:
+            raise TypeError("ReverseDiffusionPredictor.update_fn() missing 1 required positional argument: 'stepsize'")
+        return wav * 2, [38] * wav.shape[0]
+
     def ode_sample(self, y, prior_noise=None, denoise=True, **kw):
         self.calls.append(("ode_sample", tuple(y.shape), denoise, prior_noise is not None, kw))
         if denoise:
@@ -109,9 +115,9 @@ def test_enhance_dispatch_follows_model_py():
     with pytest.raises(TypeError, match="stepsize"):     # enhance() forwards kwargs only: denoise stays True (model.py:447)
         m.enhance(wav)
     xh, nfe, rtf = m.enhance(wav, denoise=False, rtol=1e-2, timeit=True, seed=4)
-    names = [c[0] for c in eng.calls]
-    assert names[-3:] == ["analysis", "ode_sample", "synthesis"] and nfe == 38 and xh.shape == (1000,)
-    assert eng.calls[-2][4]["rtol"] == 1e-2 and eng.calls[-2][4]["seed"] == 4 and eng.calls[-1][2] == 1000
+    name, shape, denoise, kw = eng.calls[-1]
+    assert (name, shape, denoise) == ("enhance_ode", (1, 1000), False) and nfe == 38 and xh.shape == (1000,)
+    assert kw["rtol"] == 1e-2 and kw["seed"] == 4 and kw["pad_mode"] == "zero_pad"
 
     m.sde.sampler_type = "bogus"
     with pytest.raises(ValueError, match="Invalid sampler type"):

@@ -290,6 +290,26 @@ def test_golden_ode_sampler_on_v2_score_models(golden_dir, tag):
     eng.close()
 
 
+def test_enhance_ode_equals_its_parts(golden_dir):
+    """sgmse_b200_enhance_ode (ScoreModel.enhance with sde.sampler_type == 'ode', model.py:446-447: host waveform in, host
+    waveform out) is analysis -> one ODE system per clip -> synthesis, bit for bit."""
+    _, sd = load_golden(golden_dir, "ncsnpp_small")
+    eng = small_engine("ncsnpp_small", "fp32", max_batch=2)
+    eng.load_state_dict(sd)
+    g = torch.Generator().manual_seed(51)
+    wav = 0.1 * torch.randn(2, 2000, generator=g)
+    kw = dict(rtol=1e-2, atol=1e-2, denoise=False, seed=6)
+    out, nfes = eng.enhance_ode(wav, utt_offset=3, **kw)
+    assert not out.is_cuda and out.shape == wav.shape and len(nfes) == 2 and min(nfes) >= 8
+    for b in range(2):
+        Y, norm = eng.analysis(wav[b:b + 1].cuda())
+        X, nfe = eng.ode_sample(Y, utt_offset=3 + b, **kw)
+        assert nfe == nfes[b] and torch.equal(eng.synthesis(X, norm, 2000).cpu(), out[b:b + 1])
+    with pytest.raises(TypeError, match="stepsize"):
+        eng.enhance_ode(wav)
+    eng.close()
+
+
 def test_graph_cache_is_bounded(golden_dir):
     """A service sees many (batch, frames, sampler) keys: the engine keeps the `max_graphs` most recently used captured
     sampler graphs and re-captures an evicted one on demand -- results unchanged."""
