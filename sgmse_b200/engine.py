@@ -420,6 +420,9 @@ class Engine:
         nptr = None
         if noise is not None:
             noise = self._c64(noise)
+            need = (int(self.lib.sgmse_b200_noise_draws(C.byref(s))), B, 1, self.F, self.padded_frames(L))
+            if tuple(noise.shape) != need:
+                raise ValueError(f"noise must have shape {need}, got {tuple(noise.shape)}")
             nptr = noise.data_ptr()
         _lib.check(self.lib.sgmse_b200_enhance(self._h, wav.data_ptr(), B, L, C.byref(s), nptr, out.data_ptr(), int(host),
                                                _stream_ptr()))
