@@ -1032,6 +1032,10 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
   SG_CHECK(s.corrector >= 0 && s.corrector <= 2, "Corrector with id %d unknown.", s.corrector);
   const int mb = std::max(1, e.cfg.max_batch);
   const int csteps = s.corrector != SGMSE_B200_CORR_NONE ? s.corrector_steps : 0;
+  const bool coupled = s.kind == SGMSE_B200_SAMPLER_PC && s.corrector == SGMSE_B200_CORR_LANGEVIN && csteps > 0;
+  SG_CHECK(!coupled || B <= mb,
+           "the Langevin corrector couples the utterances of a batch through batch-mean norms (correctors.py:50-52): B=%d "
+           "must not exceed max_batch=%d (it would be sampled in independent micro-batches)", B, mb);
   ensure_arena(e, std::min(B, mb), F, T);
   ensure_persistent(e, (size_t)std::min(B, mb) * F * T, std::max({mb, 64, s.N * (csteps + 1) + 1}));
   prepare_tables(e, s, st);
@@ -1049,7 +1053,8 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
     }
     // graph path: the micro-batch is split over concurrent lanes; every lane's launch sequence works on
     // lane-owned staging (pointer-stable), forked from / joined into the caller's stream inside ONE graph.
-    const int L = std::max(1, std::min(e.num_lanes, Bc));
+    // the Langevin corrector couples the utterances of a batch (batch-mean norms, correctors.py:50-52): one launch sequence
+    const int L = coupled ? 1 : std::max(1, std::min(e.num_lanes, Bc));
     ensure_lanes(e, std::max(L, (int)e.lanes.size()));
     const int per = (Bc + L - 1) / L;
     int lb[16], ln[16];

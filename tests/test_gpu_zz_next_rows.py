@@ -310,6 +310,26 @@ def test_enhance_ode_equals_its_parts(golden_dir):
     eng.close()
 
 
+def test_langevin_corrector_keeps_the_batch_coupled(golden_dir):
+    """LangevinCorrector's step size is a batch mean (correctors.py:50-52): the captured-graph path must not split a batch
+    over concurrent lanes (it did before this test existed), and a batch larger than max_batch is refused instead of being
+    sampled as independent micro-batches."""
+    z, sd = load_golden(golden_dir, "ncsnpp_small")
+    eng = small_engine("ncsnpp_small", "fp32", max_batch=2)
+    eng.load_state_dict(sd)
+    y = torch.from_numpy(z["y"]).cuda()                       # B = 2
+    kw = dict(N=2, predictor="reverse_diffusion", corrector="langevin", corrector_steps=1, snr=0.5, seed=21)
+    a, _ = eng.pc_sample(y, **kw)                             # graph path
+    eng.set_option("use_graphs", 0)
+    b, _ = eng.pc_sample(y, **kw)                             # one eager launch sequence over the whole batch
+    assert torch.equal(a, b)
+    alone, _ = eng.pc_sample(y[:1], **kw)
+    assert not torch.equal(alone, a[:1])                      # the coupling is real: utterance 0 alone differs
+    with pytest.raises(RuntimeError, match="couples the utterances"):
+        eng.pc_sample(torch.cat([y, y]), **kw)
+    eng.close()
+
+
 def test_graph_cache_is_bounded(golden_dir):
     """A service sees many (batch, frames, sampler) keys: the engine keeps the `max_graphs` most recently used captured
     sampler graphs and re-captures an evicted one on demand -- results unchanged."""
