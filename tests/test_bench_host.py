@@ -52,3 +52,14 @@ def test_clock_samples_are_reduced_to_median_max_and_reasons(bench):
     cs.rows = [["0", "600", "1965", "100", "Active", "Active", "Not Active", "Not Active"]]
     assert cs.stop()["reasons"] == ["hw_slowdown", "hw_thermal_slowdown"]
     assert bench.ClockSampler(0).stop() == {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+
+
+def test_reference_arm_runs_on_rank_0_only():
+    """Under torchrun (N > 1) only rank 0 times the CPU reference; the other ranks exit 0 without work or output."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
