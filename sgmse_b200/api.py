@@ -221,6 +221,8 @@ def install(model, engine: Optional[Engine] = None, rebind_forward=True, refresh
     ``rebind_forward="no_grad"`` additionally sends every forward that runs with gradients disabled to the engine: the
     validation loss (``validation_step`` -> ``_step`` -> ``self(x_t, y, t)``, model.py:189-198,257-258) while
     ``training_step`` stays on autograd."""
+    if getattr(model, "_sgmse_b200_saved", None) is not None:
+        uninstall(model)                              # re-installing: start again from the model's own methods
     if engine is None:
         engine = engine_from_score_model(model, **kw)
     model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "get_ode_sampler", "enhance", "forward", "eval")}

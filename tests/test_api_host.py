@@ -150,3 +150,16 @@ def test_forward_under_no_grad_goes_to_the_engine():
     sgmse_b200.uninstall(m)
     with torch.no_grad():
         assert torch.equal(m(x, x, torch.ones(2)), x)
+
+
+def test_installing_twice_starts_from_the_models_own_methods():
+    m = make_model(OUVESDE())
+    e1, e2 = FakeEngine(), FakeEngine()
+    sgmse_b200.install(m, engine=e1, rebind_forward=False)
+    sgmse_b200.install(m, engine=e2, rebind_forward=False)
+    assert m._sgmse_b200_engine is e2
+    m.get_ode_sampler(torch.zeros(1, 1, 4, 64, dtype=torch.complex64), denoise=False)()
+    assert e2.calls and not e1.calls
+    sgmse_b200.uninstall(m)
+    assert not any(k in m.__dict__ for k in ("get_pc_sampler", "get_ode_sampler", "get_sb_sampler", "enhance", "_sgmse_b200_engine"))
+    sgmse_b200.uninstall(m)                              # idempotent
