@@ -285,6 +285,7 @@ def run_b200(args):
         us = eng.counter("timed_conv_tc_us")
         mflop = eng.counter("timed_conv_tc_mflop")
         cnt = eng.counter("timed_conv_tc_count")
+        kbytes = eng.counter("timed_conv_tc_kbytes")    # algorithmic bytes of the same launches (inputs once + output once)
         eng.set_option("time_convs", 0)
         pk = peaks()
         ach = mflop / max(us, 1)            # MFLOP/us = TFLOP/s
@@ -302,6 +303,9 @@ def run_b200(args):
                 "launches_timed": cnt, "avg_launch_us": round(us / max(cnt, 1), 1),
                 "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
                 "share_of_step": round(us * 1e-3 / (ms / args.steps), 3),
+                # the same launches against the other roof: algorithmic HBM bytes / time (KB/us = GB/s)
+                "algorithmic_hbm_gbs": round(kbytes / max(us, 1), 1), "hbm_peak_gbs": pk["hbm_gbs"],
+                "hbm_frac": round(kbytes / max(us, 1) / pk["hbm_gbs"], 4),
                 "algorithmic_gflop_per_step": round(mflop * 1e-3, 1)}
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
