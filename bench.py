@@ -50,6 +50,8 @@ def parse():
                     help="BASELINE.json configs[i-1]: 2 = the metric's workload (default, the only one the driver runs); "
                          "3 = ncsnpp_48k 48 kHz batch 8; 4 = dereverb settings N=50 snr=0.33 batch 32 (parity-test cases, "
                          "measurable here for the record; no CPU baseline)")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="engine A/B option (Engine.set_option), e.g. --opt pdl=1 with SGMSE_B200_PDL=1; recorded in config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
@@ -195,6 +197,7 @@ def workload_config(args):
             "baseline_config": args.config,
             "global_batch": args.batch * args.gpus, "per_gpu_batch": args.batch, "micro_batch": args.micro_batch, "lanes": args.lanes,
             "parallelism": f"dp{args.gpus} (batch sharded, no data-path collective)",
+            **({"options": list(args.opt)} if getattr(args, "opt", None) else {}),
             "l2": "working set per step (>10 GB of activations per micro-batch) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -219,6 +222,9 @@ def run_b200(args):
     ecfg = (EngineConfig.ncsnpp_48k if args.config == 3 else EngineConfig)(mode=args.mode, max_batch=args.micro_batch, use_graphs=True)
     eng = Engine(ecfg, device=dev)
     eng.set_option("lanes", args.lanes)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     # weights: rank 0 creates them, NCCL broadcast over NVLink, packed per rank
     n = eng.weights_numel()
     if rank == 0:

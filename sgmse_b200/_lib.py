@@ -88,9 +88,10 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.lib_path()
+    pdl = os.environ.get("SGMSE_B200_PDL", "0") not in ("", "0")     # A/B twin with programmatic dependent launch compiled in
+    path = _build.lib_path(pdl)
     if not os.path.exists(path) or os.environ.get("SGMSE_B200_REBUILD"):
-        path = _build.build()
+        path = _build.build(pdl=pdl)
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the library does not export it

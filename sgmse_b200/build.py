@@ -1,6 +1,6 @@
 """In-tree build of libsgmse_b200.so (nvcc, sm_100a only).
 
-    python -m sgmse_b200.build [--force]
+    python -m sgmse_b200.build [--force] [--pdl]
 
 The shared library lands in ``sgmse_b200/lib/`` (git-ignored, but it travels to the GPU box with the
 gpurun snapshot).  CUDA runtime is linked statically; cuFFT dynamically (``libcufft.so.11`` from the
@@ -28,12 +28,16 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "--expt-relaxed-constexpr", "-diag-suppress", "177"]
 
 
-def lib_path() -> str:
-    return os.path.join(LIBDIR, LIBNAME)
+PDL_LIBNAME = "libsgmse_b200_pdl.so"   # same sources with -DSGMSE_B200_PDL (programmatic dependent launch, common.cuh)
 
 
-def _digest() -> str:
+def lib_path(pdl: bool = False) -> str:
+    return os.path.join(LIBDIR, PDL_LIBNAME if pdl else LIBNAME)
+
+
+def _digest(extra: str = "") -> str:
     h = hashlib.sha256()
+    h.update(extra.encode())
     for f in SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
@@ -41,18 +45,22 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, pdl: bool = False) -> str:
+    """Default library: no PDL instruction in its SASS.  pdl=True builds the A/B twin libsgmse_b200_pdl.so
+    (select it at run time with SGMSE_B200_PDL=1, then ``Engine.set_option("pdl", 1)``)."""
     os.makedirs(LIBDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, "build.stamp")
-    dig = _digest()
-    if not force and os.path.exists(lib_path()) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return lib_path()
-    objdir = os.path.join(LIBDIR, "obj")
+    stamp = os.path.join(LIBDIR, "build_pdl.stamp" if pdl else "build.stamp")
+    dig = _digest("pdl" if pdl else "")
+    out = lib_path(pdl)
+    defs = ["-DSGMSE_B200_PDL"] if pdl else []
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return out
+    objdir = os.path.join(LIBDIR, "obj_pdl" if pdl else "obj")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC, *ARCH, *CFLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *ARCH, *CFLAGS, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -62,15 +70,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, *ARCH, "-shared", "-cudart", "static", "-o", lib_path(), *objs,
+    cmd = [NVCC, *ARCH, "-shared", "-cudart", "static", "-o", out, *objs,
            "-L" + CUDA_LIB, "-lcufft", "-Xlinker", "-rpath," + CUDA_LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as fh:
         fh.write(dig)
-    return lib_path()
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, pdl="--pdl" in sys.argv))

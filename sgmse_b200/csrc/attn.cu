@@ -171,6 +171,7 @@ namespace {
 template <int C>
 __global__ void __launch_bounds__(128) attention_tc_kernel(const __half* __restrict__ qkv, int S, float scale_log2e,
                                                            __half* __restrict__ out) {
+  pdl_trigger(); pdl_wait();
   constexpr int LD = C + 8;                       // padded row (halfs): 16-byte aligned rows, conflict-free fragments
   extern __shared__ __align__(16) __half smh[];
   __half* Qs = smh;                               // [64][LD]
@@ -273,7 +274,7 @@ void run_tc(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int S) {
   auto kern = attention_tc_kernel<C>;
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(S, 64), qkv.N);
-  kern<<<grid, 128, smem, st>>>((const __half*)qkv.p, S, 1.4426950408889634f / sqrtf((float)C), (__half*)out.p);
+  launch_k(kern, grid, dim3(128), smem, st, (const __half*)qkv.p, S, 1.4426950408889634f / sqrtf((float)C), (__half*)out.p);
   CUDA_OK(cudaGetLastError());
 }
 }  // namespace

@@ -45,6 +45,49 @@ extern volatile int* g_wait_code_host;
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Compiled in only with -DSGMSE_B200_PDL (sgmse_b200/build.py --pdl builds a
+// second library, libsgmse_b200_pdl.so): the default library's SASS carries none of these instructions.  Contract of
+// a PDL-aware kernel: pdl_trigger() first (the next kernel of the stream may start its prologue as soon as every CTA
+// of this grid is resident), then pdl_wait() in EVERY thread before the first access to global memory that an
+// earlier kernel of the stream writes or reads (only weights -- constant after load_weights -- may be touched
+// before it), and never an exit without it (a grid whose CTAs all left early would "complete" before its
+// predecessor and break the chain for the kernel after it).
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() {
+#ifdef SGMSE_B200_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#ifdef SGMSE_B200_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+#endif
+extern int g_pdl;              // runtime switch (option "pdl"); refused unless the library was built with SGMSE_B200_PDL
+bool pdl_compiled();
+
+#ifdef __CUDACC__
+// Launch of a PDL-aware kernel: plain <<<>>> unless g_pdl, else cudaLaunchKernelEx with the programmatic stream
+// serialization attribute (captured into a CUDA graph as a programmatic dependency edge).
+template <typename... P, typename... A>
+inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  if (!g_pdl) {
+    kern<<<grid, block, smem, st>>>(static_cast<P>(args)...);
+    return;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...));
+}
+#endif
+
+// ----------------------------------------------------------------------------------------------
 // activation element types: float (exact mode) or __half (fast modes)
 // ----------------------------------------------------------------------------------------------
 template <typename T> struct Act;

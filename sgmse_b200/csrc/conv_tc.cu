@@ -110,6 +110,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -127,6 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                    // everything above is on-chip set-up; global memory is first touched below
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -433,7 +435,7 @@ void launch_impl(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) 
     attr_set = true;
   }
   const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
-  kern<<<grid, NUM_THREADS, L::DYN_BYTES, st>>>(ma[0], ma[1], ma[2], mb, md, mr, P);
+  launch_k(kern, dim3(grid), dim3(NUM_THREADS), (size_t)L::DYN_BYTES, st, ma[0], ma[1], ma[2], mb, md, mr, P);
   CUDA_OK(cudaGetLastError());
 }
 

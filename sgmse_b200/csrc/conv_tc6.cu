@@ -237,6 +237,7 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_d);
@@ -254,6 +255,7 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                    // everything above is on-chip set-up; global memory is first touched below
   const uint32_t tmem_base = *tmem_ptr;
   const int tiles_per_utt = P.tiles_w * P.tiles_h;
 
@@ -751,7 +753,7 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
     attr_set = true;
   }
   const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
-  kern<<<grid, NUM_THREADS, L::DYN_BYTES, st>>>(ma[0], ma[1], ma[2], ma[3], mcat, mw, md, P);
+  launch_k(kern, dim3(grid), dim3(NUM_THREADS), (size_t)L::DYN_BYTES, st, ma[0], ma[1], ma[2], ma[3], mcat, mw, md, P);
   CUDA_OK(cudaGetLastError());
 }
 

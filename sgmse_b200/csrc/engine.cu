@@ -1782,6 +1782,13 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
     e->arena_need.clear();
     clear_graphs(*e);
   }
+  else if (k == "pdl") {
+    // programmatic dependent launch between the kernels of the launch sequence (process-wide, like the other A/B switches)
+    SG_CHECK(value == 0 || sgmse::pdl_compiled(),
+             "option 'pdl' needs the library built with -DSGMSE_B200_PDL (python -m sgmse_b200.build --pdl, SGMSE_B200_LIB=...)");
+    sgmse::g_pdl = value != 0;
+    clear_graphs(*e);
+  }
   else if (k == "max_graphs") {
     SG_CHECK(value >= 1 && value <= 1024, "max_graphs must be in 1..1024");
     e->max_graphs = (int)value;
@@ -1807,6 +1814,8 @@ long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key) {
   if (k == "kernel_launches") return e->kernel_launches;
   if (k == "graph_launches") return e->graph_launches;
   if (k == "cached_graphs") return (long long)e->graphs.size();
+  if (k == "pdl_compiled") return sgmse::pdl_compiled() ? 1 : 0;
+  if (k == "pdl") return sgmse::g_pdl;
   if (k == "workspace_bytes") return (long long)e->arena.cap;
   if (k == "weights_bytes") return (long long)e->weights_bytes;
   if (k == "tc_convs_last_forward") return e->tc_convs;

@@ -17,6 +17,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int sl
                                    const float* __restrict__ st1, int C1, int slots1,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    int cpg, double inv_count, float2* __restrict__ ab, uint4* __restrict__ ab16) {
+  pdl_trigger(); pdl_wait();
   const int g = blockIdx.x, n = blockIdx.y;
   const int Ct = C0 + C1;
   const int max_slots = slots0 > slots1 ? slots0 : slots1;
@@ -94,7 +95,7 @@ void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc*
   SG_CHECK(!ab16 || cpg % 2 == 0, "GroupNorm: the half2 coefficient table needs an even number of channels per group");
   const double inv_count = 1.0 / ((double)s0.H * s0.W * cpg);
   dim3 grid(groups, s0.N);
-  gn_finalize_kernel<<<grid, 256, 0, st>>>(s0.stats, s0.C, s0.slots, s1 ? s1->stats : nullptr, C1,
+  launch_k(gn_finalize_kernel, grid, dim3(256), 0, st, s0.stats, s0.C, s0.slots, s1 ? s1->stats : nullptr, C1,
                                            s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab, ab16);
   CUDA_OK(cudaGetLastError());
 }
@@ -105,6 +106,7 @@ void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc*
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void channel_stats_kernel(const T* __restrict__ x, int HW, int C, float* __restrict__ stats) {
+  pdl_trigger(); pdl_wait();
   const int c = blockIdx.x * 32 + threadIdx.x, n = blockIdx.y;
   float s = 0.f, q = 0.f;
   if (c < C)
@@ -121,8 +123,8 @@ void launch_channel_stats(cudaStream_t st, TensorDesc& t) {
   SG_CHECK(t.stats != nullptr, "channel_stats: tensor has no statistics buffer");
   t.slots = 1;
   dim3 grid(cdiv(t.C, 32), t.N), block(32, 8);
-  if (t.dt == DT_F16) channel_stats_kernel<__half><<<grid, block, 0, st>>>((const __half*)t.p, t.H * t.W, t.C, t.stats);
-  else channel_stats_kernel<float><<<grid, block, 0, st>>>((const float*)t.p, t.H * t.W, t.C, t.stats);
+  if (t.dt == DT_F16) launch_k(channel_stats_kernel<__half>, grid, block, 0, st, (const __half*)t.p, t.H * t.W, t.C, t.stats);
+  else launch_k(channel_stats_kernel<float>, grid, block, 0, st, (const float*)t.p, t.H * t.W, t.C, t.stats);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -135,6 +137,7 @@ template <typename T, bool SILU>
 __global__ void __launch_bounds__(256)
 gn_apply_plain_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1, int C1,
                       const float2* __restrict__ ab, int HW, T* __restrict__ out) {
+  pdl_trigger(); pdl_wait();
   const int Ct = C0 + C1, cvpp = Ct >> 3;
   const int ppb = blockDim.x / cvpp;
   const int cv = threadIdx.x % cvpp, pl = threadIdx.x / cvpp;
@@ -195,6 +198,7 @@ template <typename T, int RS>
 __global__ void __launch_bounds__(256)
 gn_apply_fir_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ ab, int Hi, int Wi,
                     T* __restrict__ out0, T* __restrict__ out1) {
+  pdl_trigger(); pdl_wait();
   const int cvpp = C >> 3;
   const int Ho = RS == RS_DOWN ? Hi / 2 : Hi * 2;
   const int Wo = RS == RS_DOWN ? Wi / 2 : Wi * 2;
@@ -273,6 +277,7 @@ template <typename T, int RS, int TIN, int CV, bool FAST>   // TIN: input tile e
 __global__ void __launch_bounds__(256)
 gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ ab, int Hi, int Wi,
                           T* __restrict__ out0, T* __restrict__ out1) {
+  pdl_trigger(); pdl_wait();
   constexpr int TOUT = RS == RS_UP ? (TIN - 2) * 2 : (TIN - 2) / 2;   // output tile edge
   __shared__ __align__(16) __half hs[TIN * TIN][CV * 8];
   __shared__ __align__(16) __half xs[TIN * TIN][CV * 8];
@@ -407,8 +412,8 @@ static void gn_apply_dispatch(cudaStream_t st, const TensorDesc& x0, const Tenso
     int gx = cdiv(HW, ppb * 4);
     if (gx < 1) gx = 1;
     dim3 grid(gx, x0.N);
-    if (silu) gn_apply_plain_kernel<T, true><<<grid, block, 0, st>>>(p0, x0.C, p1, C1, ab, HW, o0);
-    else gn_apply_plain_kernel<T, false><<<grid, block, 0, st>>>(p0, x0.C, p1, C1, ab, HW, o0);
+    if (silu) launch_k(gn_apply_plain_kernel<T, true>, grid, dim3(block), 0, st, p0, x0.C, p1, C1, ab, HW, o0);
+    else launch_k(gn_apply_plain_kernel<T, false>, grid, dim3(block), 0, st, p0, x0.C, p1, C1, ab, HW, o0);
   } else {
     SG_CHECK(silu && out1 && !x1, "resampling gn_apply expects silu, a raw output and a single source");
     const size_t total = (size_t)out0.H * out0.W * cvpp;
@@ -417,15 +422,15 @@ static void gn_apply_dispatch(cudaStream_t st, const TensorDesc& x0, const Tenso
     T* o1 = (T*)out1->p;
     if (std::is_same<T, __half>::value && rs == RS_UP && x0.H % 8 == 0 && x0.W % 8 == 0 && x0.C % 64 == 0) {
       dim3 g(x0.W / 8, x0.H / 8, x0.N * (x0.C / 64));
-      if (g_fir_variant == 0) gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, true><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
-      else gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, false><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      if (g_fir_variant == 0) launch_k(gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, true>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      else launch_k(gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, false>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
     } else if (std::is_same<T, __half>::value && rs == RS_DOWN && out0.H % 8 == 0 && out0.W % 8 == 0 && x0.C % 32 == 0) {
       dim3 g(out0.W / 8, out0.H / 8, x0.N * (x0.C / 32));
-      if (g_fir_variant == 0) gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, true><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
-      else gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, false><<<g, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      if (g_fir_variant == 0) launch_k(gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, true>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      else launch_k(gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, false>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
     } else
-    if (rs == RS_DOWN) gn_apply_fir_kernel<T, RS_DOWN><<<grid, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
-    else gn_apply_fir_kernel<T, RS_UP><<<grid, 256, 0, st>>>(p0, x0.C, ab, x0.H, x0.W, o0, o1);
+    if (rs == RS_DOWN) launch_k(gn_apply_fir_kernel<T, RS_DOWN>, grid, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
+    else launch_k(gn_apply_fir_kernel<T, RS_UP>, grid, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
   }
   CUDA_OK(cudaGetLastError());
 }

@@ -8,6 +8,15 @@
 
 namespace sgmse {
 
+int g_pdl = 0;                 // see common.cuh
+bool pdl_compiled() {
+#ifdef SGMSE_B200_PDL
+  return true;
+#else
+  return false;
+#endif
+}
+
 // ================================================================================================
 // time embedding
 // ================================================================================================
@@ -113,6 +122,7 @@ __global__ void pc_update_kernel(float4* __restrict__ state, const float4* __res
                                  OutLayer ol, const float* __restrict__ inv_t_dev, float inv_t_scalar,
                                  const UpdateCoef* __restrict__ coef_dev, const float2* __restrict__ noise,
                                  const RngParams* rng, int draw, float2* __restrict__ x_mean_out) {
+  pdl_trigger(); pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int n = (int)(idx / HW);
@@ -134,7 +144,7 @@ void launch_pc_update(cudaStream_t st, float4* state, const float4* pyr, int N, 
                       const float* inv_t, float inv_t_scalar, const UpdateCoef* coef_dev, const float2* noise,
                       const RngParams* rng, int draw, float2* x_mean_out) {
   const size_t total = (size_t)N * H * W;
-  pc_update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(state, pyr, H * W, total, ol, inv_t, inv_t_scalar,
+  launch_k(pc_update_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, state, pyr, H * W, total, ol, inv_t, inv_t_scalar,
                                                                     coef_dev, noise, rng, draw, x_mean_out);
   CUDA_OK(cudaGetLastError());
 }
@@ -142,6 +152,7 @@ void launch_pc_update(cudaStream_t st, float4* state, const float4* pyr, int N, 
 __global__ void affine_update_kernel(float4* __restrict__ state, const float4* __restrict__ pyr, int HW, size_t total,
                                      OutLayer ol, const AffineCoef* __restrict__ coef_dev, const float2* __restrict__ noise,
                                      const RngParams* rng, int draw, int use_noise, float2* __restrict__ x_mean_out) {
+  pdl_trigger(); pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int n = (int)(idx / HW);
@@ -161,7 +172,7 @@ void launch_affine_update(cudaStream_t st, float4* state, const float4* pyr, int
                           const AffineCoef* coef_dev, const float2* noise, const RngParams* rng, int draw, bool use_noise,
                           float2* x_mean_out) {
   const size_t total = (size_t)N * H * W;
-  affine_update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(state, pyr, H * W, total, ol, coef_dev, noise, rng,
+  launch_k(affine_update_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, state, pyr, H * W, total, ol, coef_dev, noise, rng,
                                                                         draw, use_noise ? 1 : 0, x_mean_out);
   CUDA_OK(cudaGetLastError());
 }

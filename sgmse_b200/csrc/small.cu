@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(128) input_conv_mma_kernel(const float4* __res
                                                              int num_tiles, float in_scale) {
   constexpr int C = NT * 8;
   constexpr int PITCH = C + 8;                       // halfs per staged row: conflict-free 32-bit writes, 16-B aligned rows
+  pdl_trigger();                                     // weights / bias are constant: staged before pdl_wait()
   extern __shared__ __align__(16) uint8_t ic_smem[];
   uint2* wfrag = reinterpret_cast<uint2*>(ic_smem);                                   // [3][NT][32]
   __half* stage = reinterpret_cast<__half*>(ic_smem + (size_t)3 * NT * 32 * sizeof(uint2));   // [4 warps][32][PITCH]
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(128) input_conv_mma_kernel(const float4* __res
 #pragma unroll
   for (int j = 0; j < NT; ++j) { bia[j][0] = bias[j * 8 + 2 * t]; bia[j][1] = bias[j * 8 + 2 * t + 1]; }
   __syncthreads();
+  pdl_wait();
   const int HW = H * W;
   __half* wstage = stage + (size_t)warp * 32 * PITCH;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -198,7 +200,7 @@ static void input_conv_mma_launch(cudaStream_t st, const float4* state, int N, i
   auto k = input_conv_mma_kernel<NT>;
   CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(num_tiles, 148 * 4);
-  k<<<grid, 128, smem, st>>>(state, H, W, w, bias, (__half*)out.p, out.stats, out.slots, num_tiles, in_scale);
+  launch_k(k, dim3(grid), dim3(128), smem, st, state, H, W, w, bias, (__half*)out.p, out.stats, out.slots, num_tiles, in_scale);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -230,6 +232,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) combine_kernel(const float4* __restrict__ pyr, const float* __restrict__ w,
                                                       const float* __restrict__ bias, const T* __restrict__ h, int HW, int M,
                                                       int C, T* __restrict__ out, float* __restrict__ stats, int slots) {
+  pdl_trigger(); pdl_wait();
   __shared__ float4 pin[32];
   const int m0 = blockIdx.x * 32;
   const int n = m0 / HW, r0 = m0 - n * HW;
@@ -262,9 +265,9 @@ void launch_combine(cudaStream_t st, const float4* pyr, const float* w, const fl
   float* stp = tile_stats ? out.stats : nullptr;
   const int grid = cdiv(M, 32);
   if (h.dt == DT_F16)
-    combine_kernel<__half><<<grid, 128, 0, st>>>(pyr, w, bias, (const __half*)h.p, HW, M, h.C, (__half*)out.p, stp, out.slots);
+    launch_k(combine_kernel<__half>, dim3(grid), dim3(128), 0, st, pyr, w, bias, (const __half*)h.p, HW, M, h.C, (__half*)out.p, stp, out.slots);
   else
-    combine_kernel<float><<<grid, 128, 0, st>>>(pyr, w, bias, (const float*)h.p, HW, M, h.C, (float*)out.p, stp, out.slots);
+    launch_k(combine_kernel<float>, dim3(grid), dim3(128), 0, st, pyr, w, bias, (const float*)h.p, HW, M, h.C, (float*)out.p, stp, out.slots);
   CUDA_OK(cudaGetLastError());
   if (out.stats && !tile_stats) launch_channel_stats(st, out);
 }
@@ -278,6 +281,7 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
 
 template <int RS>
 __global__ void fir4_kernel(const float4* __restrict__ in, int N, int Hi, int Wi, float4* __restrict__ out, float scale) {
+  pdl_trigger(); pdl_wait();
   const int Ho = RS == RS_DOWN ? Hi / 2 : Hi * 2, Wo = RS == RS_DOWN ? Wi / 2 : Wi * 2;
   const size_t total = (size_t)N * Ho * Wo;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,8 +309,8 @@ void launch_fir4(cudaStream_t st, const float4* in, int N, int H, int W, Resampl
   SG_CHECK(rs != RS_NONE, "fir4: nothing to do");
   const size_t total = rs == RS_DOWN ? (size_t)N * (H / 2) * (W / 2) : (size_t)N * H * 2 * W * 2;
   const int grid = (int)((total + 255) / 256);
-  if (rs == RS_DOWN) fir4_kernel<RS_DOWN><<<grid, 256, 0, st>>>(in, N, H, W, out, scale);
-  else fir4_kernel<RS_UP><<<grid, 256, 0, st>>>(in, N, H, W, out, scale);
+  if (rs == RS_DOWN) launch_k(fir4_kernel<RS_DOWN>, dim3(grid), dim3(256), 0, st, in, N, H, W, out, scale);
+  else launch_k(fir4_kernel<RS_UP>, dim3(grid), dim3(256), 0, st, in, N, H, W, out, scale);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -419,6 +423,7 @@ __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restr
                                                            const float2* __restrict__ gn_ab, const uint2* __restrict__ wfrag_g) {
   constexpr int LD = C + 8;            // halfs per staged pixel (16-byte aligned, conflict-free ldmatrix rows)
   constexpr int KS = C / 16;
+  pdl_trigger();                       // weight fragments are constant: staged before pdl_wait()
   extern __shared__ __align__(16) uint8_t oc_smem[];
   __half* tile = reinterpret_cast<__half*>(oc_smem);                       // [18*18][LD]
   uint2* wfrag = reinterpret_cast<uint2*>(oc_smem + (size_t)18 * 18 * LD * 2);   // [9*KS][32] B fragments
@@ -445,6 +450,7 @@ __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restr
   }
   // optional fused GroupNorm-apply + SiLU of the RAW tensor while staging (256 % (C/8) == 0: a thread keeps one
   // 8-channel vector, so its (a, b) live in registers); out-of-image pixels stay zero (padding follows the activation)
+  pdl_wait();
   float ga[8], gb[8];
   if (gn_ab) {
     const float4* q = reinterpret_cast<const float4*>(gn_ab + (size_t)n * C + (tid % (C / 8)) * 8);
@@ -511,7 +517,7 @@ static void out_conv_mma_launch(cudaStream_t st, const TensorDesc& act, const fl
   auto k = out_conv_mma_kernel<C>;
   CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(act.W, 16), cdiv(act.H, 16), act.N);
-  k<<<grid, 256, smem, st>>>((const __half*)act.p, act.H, act.W, w, b, addend, out, gn_ab, wfrag);
+  launch_k(k, grid, dim3(256), smem, st, (const __half*)act.p, act.H, act.W, w, b, addend, out, gn_ab, wfrag);
   CUDA_OK(cudaGetLastError());
 }
 
