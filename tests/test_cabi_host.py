@@ -208,3 +208,28 @@ def test_shape_contract_is_enforced_on_the_host():
     assert lib.sgmse_b200_noise_draws(C.byref(s)) >= 0           # counting draws is host-only
     with pytest.raises(ValueError, match="Corrector with name 'x' unknown."):
         Engine(CASES[2][1]).sampler_struct(corrector="x")
+
+
+def test_pdl_twin_library_is_opt_in():
+    """Programmatic dependent launch is compiled into a SECOND library only (sgmse_b200/build.py --pdl): the
+    default library refuses `pdl=1` (its kernels carry no griddepcontrol.wait, so a PDL launch would race), the twin exports
+    the same C-ABI and accepts it.  Host-only: the option touches no CUDA state on an engine that has captured nothing."""
+    import ctypes as C
+    from sgmse_b200 import build
+    eng = Engine(CASES[2][1])
+    assert eng.counter("pdl_compiled") == 0 and eng.counter("pdl") == 0
+    with pytest.raises(RuntimeError, match="SGMSE_B200_PDL"):
+        eng.set_option("pdl", 1)
+    eng.set_option("pdl", 0)                                  # switching it off is always legal
+    eng.close()
+    twin = C.CDLL(build.build(pdl=True))
+    for name, (res, args) in _lib.SYMBOLS.items():
+        fn = getattr(twin, name)
+        fn.restype, fn.argtypes = res, args
+    cfg = CASES[2][1].to_c()
+    h = C.c_void_p()
+    assert twin.sgmse_b200_create(C.byref(cfg), C.byref(h)) == 0
+    assert twin.sgmse_b200_get_counter(h, b"pdl_compiled") == 1
+    assert twin.sgmse_b200_set_option(h, b"pdl", 1) == 0 and twin.sgmse_b200_get_counter(h, b"pdl") == 1
+    assert twin.sgmse_b200_set_option(h, b"pdl", 0) == 0
+    twin.sgmse_b200_destroy(h)
