@@ -261,7 +261,11 @@ gn_apply_fir_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ 
 // Phase 1 stages h = silu(a*x+b) and the raw x of an input tile (+1 pixel halo) in smem as fp32->half pairs;
 // phase 2 applies the separable [1,3,3,1] FIR from smem and writes both outputs with 128-bit stores.
 // ------------------------------------------------------------------------------------------------
-int g_fir_variant = 0;   // 0: one-MUFU silu (tanh form) + half2 FIR-down arithmetic; 1: expf/divide silu, fp32 FIR
+int g_fir_variant = 0;   // 0: one-MUFU silu (tanh form) + half2 FIR-down arithmetic; 1: expf/divide silu, fp32 FIR;
+                         // 2 (round-2 candidate, not yet run on a GPU): 0 + all global loads of phase 1 in flight at once
+                         //    (the SASS of 0 has ONE LDG.128 per loop trip in front of 8 MUFU: 4-6 serialized memory
+                         //    round trips per thread) + half2 FIR-up over 2x2 output quads (9 instead of 16 LDS.128 and
+                         //    ~50 instead of ~150 instructions per output vector)
 
 // silu(z) = hz*tanh(hz) + hz with hz = z/2: one MUFU instead of two (ex2 + rcp)
 __device__ __forceinline__ float silu_tanh_half_arg(float hz) {
@@ -273,11 +277,12 @@ __device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { uint32_t d;
 __device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
 __device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 
-template <typename T, int RS, int TIN, int CV, bool FAST>   // TIN: input tile edge incl. halo; CV: 8-channel vectors per block
+template <typename T, int RS, int TIN, int CV, int MODE>   // TIN: input tile edge incl. halo; CV: 8-channel vectors per block; MODE = g_fir_variant
 __global__ void __launch_bounds__(256)
 gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ ab, int Hi, int Wi,
                           T* __restrict__ out0, T* __restrict__ out1) {
   pdl_trigger(); pdl_wait();
+  constexpr bool FAST = MODE != 1;
   constexpr int TOUT = RS == RS_UP ? (TIN - 2) * 2 : (TIN - 2) / 2;   // output tile edge
   __shared__ __align__(16) __half hs[TIN * TIN][CV * 8];
   __shared__ __align__(16) __half xs[TIN * TIN][CV * 8];
@@ -300,6 +305,40 @@ gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restr
     }
   }
   const T* src = x0 + (size_t)n * Hi * Wi * C + c;
+  if constexpr (MODE == 2) {
+    // same arithmetic as below, but every load of this thread is issued before the first use
+    constexpr int ITEMS = TIN * TIN * CV, ROUNDS = (ITEMS + 255) / 256;
+    static_assert(256 % CV == 0, "a thread must keep its channel vector across rounds");
+    Vec8<T> v[ROUNDS];
+    bool inside[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int item = threadIdx.x + r * 256;
+      const int px = item / CV;
+      const int y = iy0 + px / TIN, x = ix0 + px % TIN;
+      inside[r] = item < ITEMS && (unsigned)y < (unsigned)Hi && (unsigned)x < (unsigned)Wi;
+      if (inside[r]) v[r].load(src + ((size_t)y * Wi + x) * C);
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int item = threadIdx.x + r * 256;
+      if (item < ITEMS) {
+        const int px = item / CV;
+        float f[8], h[8];
+        if (inside[r]) {
+          v[r].get(f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h[i] = silu_tanh_half_arg(fmaf(a[i], f[i], b[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { f[i] = 0.f; h[i] = 0.f; }
+        }
+        Vec8<__half> o;
+        o.set(h); o.store(&hs[px][cv * 8]);
+        o.set(f); o.store(&xs[px][cv * 8]);
+      }
+    }
+  } else
   for (int item = threadIdx.x; item < TIN * TIN * CV; item += 256) {
     const int px = item / CV;
     const int y = iy0 + px / TIN, x = ix0 + px % TIN;
@@ -363,6 +402,61 @@ gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restr
       *reinterpret_cast<uint4*>(out0 + o) = oh;
       *reinterpret_cast<uint4*>(out1 + o) = oxr;
     }
+  } else if constexpr (MODE == 2 && RS == RS_UP) {
+    // One item = one input pixel (ly, lx) of the tile's interior and its 2x2 output quad.  Separable, in half2:
+    //   e_r = 3/4 h[r][lx] + 1/4 h[r][lx-1],  o_r = 3/4 h[r][lx] + 1/4 h[r][lx+1]            (r = ly-1, ly, ly+1)
+    //   out(2y, 2x) = 3/4 e_ly + 1/4 e_(ly-1)   out(2y, 2x+1) = 3/4 o_ly + 1/4 o_(ly-1)
+    //   out(2y+1, 2x) = 3/4 e_ly + 1/4 e_(ly+1) out(2y+1, 2x+1) = 3/4 o_ly + 1/4 o_(ly+1)
+    // (up_or_down_sampling.py:195-224: zero-insert x2, FIR [1,3,3,1]/4 per axis; x1/4 is exact, so two roundings of
+    // 2^-11 per output on top of the fp16 store)
+    const uint32_t K75 = 0x3A003A00u, K25 = 0x34003400u;   // half2(0.75), half2(0.25)
+    constexpr int TI = TIN - 2;
+    for (int item = threadIdx.x; item < TI * TI * CV; item += 256) {
+      const int ipx = item / CV;
+      const int ly = ipx / TI + 1, lx = ipx % TI + 1;
+      uint4 q[2][4];                                       // [tensor][dy*2+dx]
+#pragma unroll
+      for (int tsr = 0; tsr < 2; ++tsr) {
+        uint4 e[3], o[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int base = (ly - 1 + r) * TIN + lx;
+          const __half* row = tsr == 0 ? &hs[0][0] : &xs[0][0];
+          const uint4 vl = *reinterpret_cast<const uint4*>(row + (size_t)(base - 1) * (CV * 8) + cv * 8);
+          const uint4 vc = *reinterpret_cast<const uint4*>(row + (size_t)base * (CV * 8) + cv * 8);
+          const uint4 vr = *reinterpret_cast<const uint4*>(row + (size_t)(base + 1) * (CV * 8) + cv * 8);
+          const uint32_t* wl = reinterpret_cast<const uint32_t*>(&vl);
+          const uint32_t* wc = reinterpret_cast<const uint32_t*>(&vc);
+          const uint32_t* wr = reinterpret_cast<const uint32_t*>(&vr);
+          uint32_t* we = reinterpret_cast<uint32_t*>(&e[r]);
+          uint32_t* wo = reinterpret_cast<uint32_t*>(&o[r]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            we[k] = h2_fma(K75, wc[k], h2_mul(K25, wl[k]));
+            wo[k] = h2_fma(K75, wc[k], h2_mul(K25, wr[k]));
+          }
+        }
+        const uint32_t* e0 = reinterpret_cast<const uint32_t*>(&e[0]); const uint32_t* e1 = reinterpret_cast<const uint32_t*>(&e[1]);
+        const uint32_t* e2 = reinterpret_cast<const uint32_t*>(&e[2]); const uint32_t* o0 = reinterpret_cast<const uint32_t*>(&o[0]);
+        const uint32_t* o1 = reinterpret_cast<const uint32_t*>(&o[1]); const uint32_t* o2 = reinterpret_cast<const uint32_t*>(&o[2]);
+        uint32_t* q00 = reinterpret_cast<uint32_t*>(&q[tsr][0]); uint32_t* q01 = reinterpret_cast<uint32_t*>(&q[tsr][1]);
+        uint32_t* q10 = reinterpret_cast<uint32_t*>(&q[tsr][2]); uint32_t* q11 = reinterpret_cast<uint32_t*>(&q[tsr][3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          q00[k] = h2_fma(K75, e1[k], h2_mul(K25, e0[k]));
+          q01[k] = h2_fma(K75, o1[k], h2_mul(K25, o0[k]));
+          q10[k] = h2_fma(K75, e1[k], h2_mul(K25, e2[k]));
+          q11[k] = h2_fma(K75, o1[k], h2_mul(K25, o2[k]));
+        }
+      }
+      const int Y = blockIdx.y * TOUT + 2 * (ly - 1), X = blockIdx.x * TOUT + 2 * (lx - 1);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const size_t o = (((size_t)n * Ho + Y + (d >> 1)) * Wo + X + (d & 1)) * C + c;
+        *reinterpret_cast<uint4*>(out0 + o) = q[0][d];
+        *reinterpret_cast<uint4*>(out1 + o) = q[1][d];
+      }
+    }
   } else
   for (int item = threadIdx.x; item < TOUT * TOUT * CV; item += 256) {
     const int opx = item / CV;
@@ -422,12 +516,14 @@ static void gn_apply_dispatch(cudaStream_t st, const TensorDesc& x0, const Tenso
     T* o1 = (T*)out1->p;
     if (std::is_same<T, __half>::value && rs == RS_UP && x0.H % 8 == 0 && x0.W % 8 == 0 && x0.C % 64 == 0) {
       dim3 g(x0.W / 8, x0.H / 8, x0.N * (x0.C / 64));
-      if (g_fir_variant == 0) launch_k(gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, true>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
-      else launch_k(gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, false>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      if (g_fir_variant == 0) launch_k(gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, 0>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      else if (g_fir_variant == 2) launch_k(gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, 2>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      else launch_k(gn_apply_fir_tiled_kernel<T, RS_UP, 10, 8, 1>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
     } else if (std::is_same<T, __half>::value && rs == RS_DOWN && out0.H % 8 == 0 && out0.W % 8 == 0 && x0.C % 32 == 0) {
       dim3 g(out0.W / 8, out0.H / 8, x0.N * (x0.C / 32));
-      if (g_fir_variant == 0) launch_k(gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, true>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
-      else launch_k(gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, false>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      if (g_fir_variant == 0) launch_k(gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, 0>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      else if (g_fir_variant == 2) launch_k(gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, 2>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
+      else launch_k(gn_apply_fir_tiled_kernel<T, RS_DOWN, 18, 4, 1>, g, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
     } else
     if (rs == RS_DOWN) launch_k(gn_apply_fir_kernel<T, RS_DOWN>, grid, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);
     else launch_k(gn_apply_fir_kernel<T, RS_UP>, grid, dim3(256), 0, st, p0, x0.C, ab, x0.H, x0.W, o0, o1);

@@ -35,6 +35,7 @@ void launch_gn_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1
                      Resample rs, TensorDesc& out0, TensorDesc* out1);
 
 extern int g_fir_variant;   // 0: one-MUFU (tanh-form) silu + half2 FIR-down arithmetic in the tiled fp16 kernels; 1: expf silu, fp32 FIR
+                            // 2: 0 + phase-1 loads in flight at once + half2 quad FIR-up (round-2 candidate, see gn.cu)
 
 // ---- convolutions ----
 struct ConvSeg {
