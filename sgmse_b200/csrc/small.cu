@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restric
 //   state float4 of neighbour tap 4s + (t >> 1) [a0/a1] and 4s + 2 + (t >> 1) [a2/a3]: straight from global/L1.
 //   B fragments (k x channels) are built once per block in shared memory; the block then walks tiles of 128 pixels.
 //   Output goes through a per-warp padded smem tile so that global stores are 128-bit and row-contiguous.
-int g_inconv_variant = 0;   // 0: tensor-core kernel for fp16 output where it applies, 1: CUDA-core kernel
+int g_inconv_variant = 0;   // 0: tensor-core kernel for fp16 output where it applies, 1: CUDA-core kernel,
+                            // 2 (round-2 candidate, not yet run on a GPU): 0 with the A fragments of the NEXT 16-pixel m-tile
+                            //   loaded before the 48 MMAs of the current one (today every m-tile starts with an exposed
+                            //   L1/L2 round trip at 16 warps per SM); same arithmetic, bit-identical
 
 template <int NT>   // NT = C / 8
 __global__ void __launch_bounds__(128) input_conv_mma_kernel(const float4* __restrict__ state, int H, int W,
@@ -191,13 +194,150 @@ __global__ void __launch_bounds__(128) input_conv_mma_kernel(const float4* __res
   }
 }
 
-template <int NT>
+template <int NT, bool PREFETCH>   // NT = C / 8; the separate copy keeps the verified kernel above untouched
+__global__ void __launch_bounds__(128) input_conv_mma_pf_kernel(const float4* __restrict__ state, int H, int W,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             __half* __restrict__ out, float* __restrict__ stats, int slots,
+                                                             int num_tiles, float in_scale) {
+  constexpr int C = NT * 8;
+  constexpr int PITCH = C + 8;                       // halfs per staged row: conflict-free 32-bit writes, 16-B aligned rows
+  pdl_trigger();                                     // weights / bias are constant: staged before pdl_wait()
+  extern __shared__ __align__(16) uint8_t ic_smem[];
+  uint2* wfrag = reinterpret_cast<uint2*>(ic_smem);                                   // [3][NT][32]
+  __half* stage = reinterpret_cast<__half*>(ic_smem + (size_t)3 * NT * 32 * sizeof(uint2));   // [4 warps][32][PITCH]
+  float* red = reinterpret_cast<float*>(stage + (size_t)4 * 32 * PITCH);              // [4 warps][C][2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 3 * NT * 32; i += 128) {
+    const int l = i & 31, j = (i >> 5) % NT, s = i / (32 * NT);
+    const int gg = l >> 2, tt = l & 3;
+    const int c = j * 8 + gg;
+    const int k0 = 16 * s + 2 * tt;
+    auto wk = [&](int k) { return k < 36 ? w[k * C + c] : 0.f; };
+    const __half2 b0 = __floats2half2_rn(wk(k0), wk(k0 + 1));
+    const __half2 b1 = __floats2half2_rn(wk(k0 + 8), wk(k0 + 9));
+    wfrag[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
+  }
+  float bia[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { bia[j][0] = bias[j * 8 + 2 * t]; bia[j][1] = bias[j * 8 + 2 * t + 1]; }
+  __syncthreads();
+  pdl_wait();
+  const int HW = H * W;
+  __half* wstage = stage + (size_t)warp * 32 * PITCH;
+  // A fragments of m-tile `mt` of `tile`: rows g and g + 8.  Loads (raw fp32 pairs) and the conversion to fp16 fragments
+  // are separate steps so that the prefetching variant converts only after the current m-tile's MMAs were issued.
+  auto load_raw = [&](int tile, int mt, float2 (&raw)[12]) {
+    const int m0 = tile * 128;
+    const int n = m0 / HW, r0 = m0 - n * HW;
+    const float4* sp = state + (size_t)n * HW;
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int r = r0 + warp * 32 + mt * 16 + g + hr * 8;
+      const int py = r / W, px = r - py * W;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {                 // q-th k-octet: tap 2q + (t >> 1)
+        const int tap = 2 * q + (t >> 1);
+        float2 v = make_float2(0.f, 0.f);
+        if (tap < 9) {
+          const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;
+          if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W)
+            v = reinterpret_cast<const float2*>(sp + (size_t)y * W + x)[t & 1];
+        }
+        raw[hr * 6 + q] = v;
+      }
+    }
+  };
+  auto convert = [&](const float2 (&raw)[12], uint32_t (&af)[3][4]) {
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const __half2 hv = __floats2half2_rn(in_scale * raw[hr * 6 + q].x, in_scale * raw[hr * 6 + q].y);
+        af[q >> 1][(q & 1) * 2 + hr] = *reinterpret_cast<const uint32_t*>(&hv);
+      }
+  };
+  uint32_t af[3][4];
+  float2 raw[12];
+  if (PREFETCH && (int)blockIdx.x < num_tiles) { load_raw(blockIdx.x, 0, raw); convert(raw, af); }
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int m0 = tile * 128;
+    const int n = m0 / HW, r0 = m0 - n * HW;
+    float ssum[NT][2], ssq[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { ssum[j][0] = ssum[j][1] = ssq[j][0] = ssq[j][1] = 0.f; }
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      if (PREFETCH) {                                 // next m-tile's loads fly during this one's MMAs
+        if (mt == 0) load_raw(tile, 1, raw);
+        else if (tile + (int)gridDim.x < num_tiles) load_raw(tile + gridDim.x, 0, raw);
+      } else {
+        load_raw(tile, mt, raw);
+        convert(raw, af);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const uint2 b = wfrag[(s * NT + j) * 32 + lane];
+          oc_mma(acc, af[s], b.x, b.y);
+        }
+        // rows g (acc[0..1]) and g + 8 (acc[2..3]), channels 8j + 2t, +1
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const __half2 hv = __floats2half2_rn(acc[2 * hr] + bia[j][0], acc[2 * hr + 1] + bia[j][1]);
+          const float2 f = __half22float2(hv);
+          ssum[j][0] += f.x; ssq[j][0] = fmaf(f.x, f.x, ssq[j][0]);
+          ssum[j][1] += f.y; ssq[j][1] = fmaf(f.y, f.y, ssq[j][1]);
+          *reinterpret_cast<__half2*>(wstage + (size_t)(mt * 16 + g + hr * 8) * PITCH + j * 8 + 2 * t) = hv;
+        }
+      }
+      if (PREFETCH) convert(raw, af);
+    }
+    __syncwarp();
+    // 32 rows x C halfs -> global, 128-bit, row-contiguous
+    {
+      __half* op = out + (size_t)(m0 + warp * 32) * C;
+      constexpr int VPR = C / 8;                       // 16-B vectors per row
+      for (int i = lane; i < 32 * VPR; i += 32) {
+        const int row = i / VPR, cvv = i - row * VPR;
+        *reinterpret_cast<uint4*>(op + (size_t)row * C + cvv * 8) =
+            *reinterpret_cast<const uint4*>(wstage + (size_t)row * PITCH + cvv * 8);
+      }
+    }
+    if (stats) {
+      // per-channel partials of the 128-pixel tile: rows across lanes (fixed xor tree), then the 4 warps in order
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float s1 = ssum[j][e], s2 = ssq[j][e];
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+          if (g == 0) { red[(warp * C + j * 8 + 2 * t + e) * 2] = s1; red[(warp * C + j * 8 + 2 * t + e) * 2 + 1] = s2; }
+        }
+      __syncthreads();
+      for (int c = tid; c < C; c += 128) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 4; ++wv) { s1 += red[(wv * C + c) * 2]; s2 += red[(wv * C + c) * 2 + 1]; }
+        float* d = stats + (((size_t)n * slots + r0 / 128) * C + c) * 2;
+        d[0] = s1; d[1] = s2;
+      }
+      __syncthreads();
+    }
+    __syncwarp();
+  }
+}
+
+template <int NT, bool PREFETCH = false>
 static void input_conv_mma_launch(cudaStream_t st, const float4* state, int N, int H, int W, const float* w,
                                   const float* bias, TensorDesc& out, float in_scale) {
   constexpr int C = NT * 8;
   const int num_tiles = N * H * W / 128;
   const size_t smem = (size_t)3 * NT * 32 * sizeof(uint2) + (size_t)4 * 32 * (C + 8) * 2 + (size_t)4 * C * 2 * 4;
-  auto k = input_conv_mma_kernel<NT>;
+  auto k = PREFETCH ? input_conv_mma_pf_kernel<NT, true> : input_conv_mma_kernel<NT>;
   CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(num_tiles, 148 * 4);
   launch_k(k, dim3(grid), dim3(128), smem, st, state, H, W, w, bias, (__half*)out.p, out.stats, out.slots, num_tiles, in_scale);
@@ -208,6 +348,13 @@ void launch_input_conv(cudaStream_t st, const float4* state, int N, int H, int W
                        const float* bias, TensorDesc& out, float in_scale) {
   const int HW = H * W;
   SG_CHECK(HW % 32 == 0, "input conv: H*W must be a multiple of 32");
+  if (out.dt == DT_F16 && g_inconv_variant == 2 && HW % 128 == 0 && (out.C == 128 || out.C == 64 || out.C == 32)) {
+    out.slots = HW / 128;
+    if (out.C == 128) input_conv_mma_launch<16, true>(st, state, N, H, W, w, bias, out, in_scale);
+    else if (out.C == 64) input_conv_mma_launch<8, true>(st, state, N, H, W, w, bias, out, in_scale);
+    else input_conv_mma_launch<4, true>(st, state, N, H, W, w, bias, out, in_scale);
+    return;
+  }
   if (out.dt == DT_F16 && g_inconv_variant == 0 && HW % 128 == 0 && (out.C == 128 || out.C == 64 || out.C == 32)) {
     out.slots = HW / 128;
     if (out.C == 128) input_conv_mma_launch<16>(st, state, N, H, W, w, bias, out, in_scale);
@@ -416,7 +563,11 @@ __global__ void __launch_bounds__(256) out_conv_coop_kernel(const T* __restrict_
 // fp16 tensor-core variant (mma.sync m16n8k16, N = 8 with the 4 real outputs in columns 0..3): a block stages a
 // 16x16 pixel tile (+1 halo) of the activation in shared memory once, every warp computes two 16-pixel rows with
 // 9 taps x C/16 MMAs each.  ~15x fewer instructions than the CUDA-core kernels above; HBM/L2-bound.
-template <int C>
+// ASYNC (outconv_variant 3, round-2 candidate, not yet run on a GPU): the 18x18-pixel tile is staged with cp.async
+// (16 B each, zero-filled outside the image), i.e. all ~20 (C = 128) / ~40 (C = 256) loads of a thread are in flight at
+// once.  The SASS of the plain staging loop is LDG.128 -> STS.128 -> branch: one memory round trip per loop trip, which
+// is why the kernel sits at 2.1 TB/s (260 us for 545 MB).  Same bytes in shared memory, same arithmetic: bit-identical.
+template <int C, bool ASYNC = false>
 __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restrict__ act, int H, int W,
                                                            const float* __restrict__ w, float4 bias,
                                                            const float4* __restrict__ addend, float4* __restrict__ out,
@@ -457,6 +608,19 @@ __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restr
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const float4 v = q[k]; ga[2 * k] = v.x; gb[2 * k] = v.y; ga[2 * k + 1] = v.z; gb[2 * k + 1] = v.w; }
   }
+  if constexpr (ASYNC) {
+    for (int i = tid; i < 18 * 18 * (C / 8); i += 256) {
+      const int px = i / (C / 8), cv = i % (C / 8);
+      const int y = y0 - 1 + px / 18, x = x0 - 1 + px % 18;
+      const bool in = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+      // src-size 0 -> the 16 destination bytes are zero-filled; the (unused) source address stays inside the tensor
+      const __half* src = act + (((size_t)n * H + (in ? y : 0)) * W + (in ? x : 0)) * C + cv * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                   ::"r"(smem_u32(tile + (size_t)px * LD + cv * 8)), "l"(src), "r"(in ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else
   for (int i = tid; i < 18 * 18 * (C / 8); i += 256) {
     const int px = i / (C / 8), cv = i % (C / 8);
     const int y = y0 - 1 + px / 18, x = x0 - 1 + px % 18;
@@ -510,11 +674,11 @@ __global__ void __launch_bounds__(256) out_conv_mma_kernel(const __half* __restr
   }
 }
 
-template <int C>
+template <int C, bool ASYNC = false>
 static void out_conv_mma_launch(cudaStream_t st, const TensorDesc& act, const float* w, float4 b, const float4* addend,
                                 float4* out, const float2* gn_ab, const uint2* wfrag) {
   const size_t smem = (size_t)18 * 18 * (C + 8) * 2 + (size_t)9 * (C / 16) * 32 * sizeof(uint2);
-  auto k = out_conv_mma_kernel<C>;
+  auto k = out_conv_mma_kernel<C, ASYNC>;
   CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(act.W, 16), cdiv(act.H, 16), act.N);
   launch_k(k, grid, dim3(256), smem, st, (const __half*)act.p, act.H, act.W, w, b, addend, out, gn_ab, wfrag);
@@ -561,6 +725,11 @@ void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, con
   // `bias` is a HOST pointer to 4 floats (kept with the layer description)
   const float4 b = make_float4(bias[0], bias[1], bias[2], bias[3]);
   if (act.dt == DT_F16 && g_outconv_variant != 1 && (act.C == 128 || act.C == 256)) {
+    if (g_outconv_variant == 3 && !gn_ab) {
+      if (act.C == 128) out_conv_mma_launch<128, true>(st, act, w, b, addend, out, gn_ab, wfrag);
+      else out_conv_mma_launch<256, true>(st, act, w, b, addend, out, gn_ab, wfrag);
+      return;
+    }
     if (act.C == 128) out_conv_mma_launch<128>(st, act, w, b, addend, out, gn_ab, wfrag);
     else out_conv_mma_launch<256>(st, act, w, b, addend, out, gn_ab, wfrag);
     return;
