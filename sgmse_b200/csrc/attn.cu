@@ -168,7 +168,11 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 
 namespace {
-template <int C>
+// ASYNC (attn_variant 2, round-2 candidate, not yet run on a GPU): Q/K/V tiles are staged with cp.async (zero-fill past the
+// last token).  The SASS of the plain load_tile loop is LDG.128 -> STS.128 -> branch, 16 (C = 128) / 32 (C = 256) serialized
+// round trips per tile and two tiles per key block: ~50 us of a 53 us launch whose 4.3 GFLOP need < 10.  Same bytes in
+// shared memory, same arithmetic: bit-identical.
+template <int C, bool ASYNC = false>
 __global__ void __launch_bounds__(128) attention_tc_kernel(const __half* __restrict__ qkv, int S, float scale_log2e,
                                                            __half* __restrict__ out) {
   pdl_trigger(); pdl_wait();
@@ -185,9 +189,22 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __half* __restr
   auto load_tile = [&](__half* dst, int row0, int col0) {
     for (int i = tid; i < 64 * (C / 8); i += 128) {
       const int r = i / (C / 8), cv = i % (C / 8);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (row0 + r < S) v = *reinterpret_cast<const uint4*>(base + (size_t)(row0 + r) * 3 * C + col0 + cv * 8);
-      *reinterpret_cast<uint4*>(dst + r * LD + cv * 8) = v;
+      if constexpr (ASYNC) {
+        const bool in = row0 + r < S;             // src-size 0 -> zero fill; the unused address stays inside the tensor
+        const __half* src = base + (size_t)(in ? row0 + r : 0) * 3 * C + col0 + cv * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(dst + r * LD + cv * 8)), "l"(src), "r"(in ? 16 : 0) : "memory");
+      } else {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row0 + r < S) v = *reinterpret_cast<const uint4*>(base + (size_t)(row0 + r) * 3 * C + col0 + cv * 8);
+        *reinterpret_cast<uint4*>(dst + r * LD + cv * 8) = v;
+      }
+    }
+  };
+  auto tiles_landed = [&]() {
+    if constexpr (ASYNC) {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
   };
   load_tile(Qs, q0, 0);
@@ -201,6 +218,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __half* __restr
     __syncthreads();
     load_tile(Ks, k0, C);
     load_tile(Vs, k0, 2 * C);
+    tiles_landed();
     __syncthreads();
     float sacc[8][4];
 #pragma unroll
@@ -268,10 +286,10 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __half* __restr
   }
 }
 
-template <int C>
+template <int C, bool ASYNC = false>
 void run_tc(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int S) {
   const size_t smem = (size_t)3 * 64 * (C + 8) * sizeof(__half);
-  auto kern = attention_tc_kernel<C>;
+  auto kern = attention_tc_kernel<C, ASYNC>;
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(S, 64), qkv.N);
   launch_k(kern, grid, dim3(128), smem, st, (const __half*)qkv.p, S, 1.4426950408889634f / sqrtf((float)C), (__half*)out.p);
@@ -279,12 +297,16 @@ void run_tc(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int S) {
 }
 }  // namespace
 
-int g_attn_variant = 0;   // 0: tensor-core kernel where it applies, 1: always the fp32 CUDA-core kernel
+int g_attn_variant = 0;   // 0: tensor-core kernel where it applies, 1: always the fp32 CUDA-core kernel, 2: 0 with cp.async tile staging
 
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out) {
   const int C = out.C, S = qkv.H * qkv.W;
   SG_CHECK(qkv.C == 3 * C && C % 8 == 0, "attention: qkv must have 3C channels");
-  if (qkv.dt == DT_F16 && g_attn_variant == 0) {
+  if (qkv.dt == DT_F16 && g_attn_variant == 2) {
+    if (C == 256) { run_tc<256, true>(st, qkv, out, S); return; }
+    if (C == 128) { run_tc<128, true>(st, qkv, out, S); return; }
+  }
+  if (qkv.dt == DT_F16 && (g_attn_variant == 0 || g_attn_variant == 2)) {
     if (C == 256) { run_tc<256>(st, qkv, out, S); return; }
     if (C == 128) { run_tc<128>(st, qkv, out, S); return; }
   }

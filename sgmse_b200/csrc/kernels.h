@@ -118,7 +118,7 @@ extern int g_inconv_variant;    // 0: mma.sync input conv for fp16 C in {32, 64,
 
 // ---- attention: qkv [N,H,W,3C] (q|k|v), out [N,H,W,C] = softmax(q k^T / sqrt(C)) v over H*W tokens
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out);
-extern int g_attn_variant;   // 0: fp16 mma.sync flash kernel where it applies (C in {128,256}), 1: fp32 CUDA-core kernel
+extern int g_attn_variant;   // 0: fp16 mma.sync flash kernel where it applies (C in {128,256}), 1: fp32 CUDA-core kernel, 2: 0 with cp.async tile staging (round-2 candidate)
 
 // ---- time embedding ----
 struct TembWeights {

@@ -66,10 +66,16 @@ def main():
         ops = lambda ls: sorted(l.split()[0 if not l.startswith("@") else 1] for l in ls)   # noqa: E731
         kind = "register allocation / scheduling only" if ops(old[k]) == ops(new[k]) else "DIFFERENT INSTRUCTION MIX"
         print(f"  changed ({kind}, {len(d)} lines): {k[:140]}")
+    new_only = sorted(set(new) - set(old))
     for k in sorted(set(old) - set(new)):
-        print(f"  only in {rev}: {k[:160]}")
-    for k in sorted(set(new) - set(old)):
-        print(f"  only in the working tree: {k[:160]}")
+        twins = [n for n in new_only if new[n] == old[k] and n.split("<")[0] == k.split("<")[0]]
+        if twins:
+            print(f"  renamed, identical instruction stream: {k[:110]}  ->  {twins[0][:110]}")
+            new_only = [n for n in new_only if n != twins[0]]
+        else:
+            print(f"  ONLY IN {rev} (no identical twin): {k[:160]}")
+    for k in new_only:
+        print(f"  new kernel: {k[:160]}")
 
 
 if __name__ == "__main__":
