@@ -114,6 +114,7 @@ void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, con
 extern int g_outconv_variant;   // 0: mma.sync kernel for fp16 C in {128, 256}; 1: CUDA-core kernels; 2: mma.sync kernel with
                                 // GroupNorm+SiLU fused into its staging (measured slower than gn_apply + conv: profiles/)
                                 // 3: the mma.sync kernel with its tile staged by cp.async (round-2 candidate, see small.cu)
+extern int g_combine_variant;   // 0: thread per channel (2-byte accesses); 1: thread per 8-channel vector (round-2 candidate, bit-identical)
 extern int g_inconv_variant;    // 0: mma.sync input conv for fp16 C in {32, 64, 128}; 1: CUDA-core kernel; 2: 0 with prefetched A fragments (round-2 candidate)
 
 // ---- attention: qkv [N,H,W,3C] (q|k|v), out [N,H,W,C] = softmax(q k^T / sqrt(C)) v over H*W tokens
