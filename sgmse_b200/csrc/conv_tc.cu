@@ -442,6 +442,7 @@ void launch_impl(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) 
 }  // namespace
 
 int g_tc_variant = 0;   // see kernels.h
+int g_tc1_narrow = 0;   // see launch_conv_tc
 volatile int* g_wait_code_host = nullptr;
 
 bool conv_tc_supported(const ConvArgs& a, const TensorDesc& out) {
@@ -467,6 +468,15 @@ void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* db
   if ((g_tc_variant == 0 || g_tc_variant >= 4) && conv_tc4_supported(a, out)) { launch_conv_tc4(st, a, out, dbg); return; }
   if (g_tc_variant == 3 && conv_tc3_supported(a, out)) { launch_conv_tc3(st, a, out, dbg); return; }
   if (g_tc_variant != 1 && conv_tc2_supported(a, out)) { launch_conv_tc2(st, a, out, dbg); return; }
+  // tc1_narrow (round-2 candidate, default off): on the levels below 16 rows a 128-wide channel tile leaves 32-64 CTAs that
+  // each stream 32 KB per 64-deep k-block; 64-wide tiles double the CTAs and cut the per-CTA stream to 24 KB.  The
+  // accumulation order of an output element does not depend on the tile width: bit-identical.
+  if (out.C % 128 == 0 && g_tc1_narrow) {
+    int bw, bh, bn;
+    choose_box(out.H, out.W, bw, bh, bn);
+    const int tiles128 = (out.W / bw) * (out.H / bh) * cdiv(out.N, bn) * (out.C / 128);
+    if (tiles128 * 2 <= num_sms()) { launch_impl<64, 6>(st, a, out, dbg); return; }
+  }
   if (out.C % 128 == 0) launch_impl<128, 5>(st, a, out, dbg);
   else launch_impl<64, 6>(st, a, out, dbg);
 }

@@ -1777,6 +1777,7 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "fir_variant") { sgmse::g_fir_variant = (int)value; clear_graphs(*e); }
   else if (k == "inconv_variant") { sgmse::g_inconv_variant = (int)value; clear_graphs(*e); }
   else if (k == "combine_variant") { sgmse::g_combine_variant = (int)value; clear_graphs(*e); }
+  else if (k == "tc1_narrow") { sgmse::g_tc1_narrow = (int)value; clear_graphs(*e); }
   else if (k == "outconv_variant") {
     sgmse::g_outconv_variant = (int)value;       // changes the buffers a forward needs (fused GroupNorm or not)
     if (e->lanes.size() > 1) ensure_lanes(*e, 1);

@@ -89,6 +89,7 @@ bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out);
 bool conv_tc6_fuse_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
 extern int g_tc6_rings, g_tc6_mma_style, g_tc6_tma_poll;   // conv_tc6 A/B switches, see conv_tc6.cu
+extern int g_tc1_narrow;   // 1: conv_tc v1 takes 64-wide channel tiles when 128-wide ones fill less than half the SMs (round-2 candidate)
 extern int g_tc_variant;   // 0 (= 7, 8): newest applicable kernels (v6 with fused GroupNorm+SiLU where possible: LDG-fed producers,
                            // fp32 math = fused mode 1; else v4/v1), 1: v1 only, 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1),
                            // 4: v4 (+v1) without GroupNorm fusion, 5: v5 fused GN (+v4), 6: v6 without fusion (+v4),
