@@ -19,12 +19,16 @@ ap.add_argument("--evals", type=int, default=2)
 ap.add_argument("--T", type=int, default=512)
 ap.add_argument("--mode", default="fp16_tc")
 ap.add_argument("--backbone", default="ncsnpp")
+ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="Engine.set_option before the evaluations")
 a = ap.parse_args()
 
 cfg = EngineConfig(mode=a.mode, max_batch=a.batch, use_graphs=False) if a.backbone == "ncsnpp" else \
     EngineConfig.ncsnpp_48k(mode=a.mode, max_batch=a.batch, use_graphs=False)
 eng = Engine(cfg)
 eng.load_blob(synthetic_blob(eng, 0))
+for kv in a.opt:
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 F = cfg.n_fft // 2 + 1
 g = torch.Generator().manual_seed(0)
 x = (torch.complex(torch.randn(a.batch, 2, F, a.T, generator=g), torch.randn(a.batch, 2, F, a.T, generator=g)) * 0.3).cuda()
