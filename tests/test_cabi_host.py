@@ -233,3 +233,19 @@ def test_pdl_twin_library_is_opt_in():
     assert twin.sgmse_b200_set_option(h, b"pdl", 1) == 0 and twin.sgmse_b200_get_counter(h, b"pdl") == 1
     assert twin.sgmse_b200_set_option(h, b"pdl", 0) == 0
     twin.sgmse_b200_destroy(h)
+
+
+def test_every_ab_switch_is_a_known_option():
+    """The A/B switches named in kernels.h / DESIGN.md are accepted by sgmse_b200_set_option (value 0 = the verified default),
+    anything else is reported as an error.  Host-only: none of these touches CUDA state on an engine that has run nothing."""
+    eng = Engine(CASES[2][1])
+    for key in ("tc_variant", "attn_variant", "tc6_rings", "tc6_mma", "tc6_tma_poll", "fir_variant", "inconv_variant",
+                "outconv_variant", "combine_variant", "tc1_narrow", "pdl", "record_taps", "use_graphs"):
+        eng.set_option(key, 0)
+    eng.set_option("max_graphs", 16)
+    eng.set_option("lanes", 1)
+    with pytest.raises(RuntimeError, match="unknown option"):
+        eng.set_option("no_such_switch", 1)
+    with pytest.raises(RuntimeError, match="max_graphs"):
+        eng.set_option("max_graphs", 0)
+    eng.close()
