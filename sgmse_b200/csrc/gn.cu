@@ -306,36 +306,40 @@ gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restr
   }
   const T* src = x0 + (size_t)n * Hi * Wi * C + c;
   if constexpr (MODE == 2) {
-    // same arithmetic as below, but every load of this thread is issued before the first use
+    // same arithmetic as below, but the loads of this thread are issued in batches of up to four before their first use
     constexpr int ITEMS = TIN * TIN * CV, ROUNDS = (ITEMS + 255) / 256;
+    constexpr int GROUP = ROUNDS > 4 ? (ROUNDS + 1) / 2 : ROUNDS;     // 6 rounds (FIR-down) -> 3 + 3: 64 instead of 80 registers
     static_assert(256 % CV == 0, "a thread must keep its channel vector across rounds");
-    Vec8<T> v[ROUNDS];
-    bool inside[ROUNDS];
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-      const int item = threadIdx.x + r * 256;
-      const int px = item / CV;
-      const int y = iy0 + px / TIN, x = ix0 + px % TIN;
-      inside[r] = item < ITEMS && (unsigned)y < (unsigned)Hi && (unsigned)x < (unsigned)Wi;
-      if (inside[r]) v[r].load(src + ((size_t)y * Wi + x) * C);
-    }
+    for (int r0 = 0; r0 < ROUNDS; r0 += GROUP) {
+      Vec8<T> v[GROUP];
+      bool inside[GROUP];
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-      const int item = threadIdx.x + r * 256;
-      if (item < ITEMS) {
+      for (int r = 0; r < GROUP; ++r) {
+        const int item = threadIdx.x + (r0 + r) * 256;
         const int px = item / CV;
-        float f[8], h[8];
-        if (inside[r]) {
-          v[r].get(f);
+        const int y = iy0 + px / TIN, x = ix0 + px % TIN;
+        inside[r] = r0 + r < ROUNDS && item < ITEMS && (unsigned)y < (unsigned)Hi && (unsigned)x < (unsigned)Wi;
+        if (inside[r]) v[r].load(src + ((size_t)y * Wi + x) * C);
+      }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) h[i] = silu_tanh_half_arg(fmaf(a[i], f[i], b[i]));
-        } else {
+      for (int r = 0; r < GROUP; ++r) {
+        const int item = threadIdx.x + (r0 + r) * 256;
+        if (r0 + r < ROUNDS && item < ITEMS) {
+          const int px = item / CV;
+          float f[8], h[8];
+          if (inside[r]) {
+            v[r].get(f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { f[i] = 0.f; h[i] = 0.f; }
+            for (int i = 0; i < 8; ++i) h[i] = silu_tanh_half_arg(fmaf(a[i], f[i], b[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { f[i] = 0.f; h[i] = 0.f; }
+          }
+          Vec8<__half> o;
+          o.set(h); o.store(&hs[px][cv * 8]);
+          o.set(f); o.store(&xs[px][cv * 8]);
         }
-        Vec8<__half> o;
-        o.set(h); o.store(&hs[px][cv * 8]);
-        o.set(f); o.store(&xs[px][cv * 8]);
       }
     }
   } else
@@ -414,9 +418,10 @@ gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restr
     for (int item = threadIdx.x; item < TI * TI * CV; item += 256) {
       const int ipx = item / CV;
       const int ly = ipx / TI + 1, lx = ipx % TI + 1;
-      uint4 q[2][4];                                       // [tensor][dy*2+dx]
+      const int Y = blockIdx.y * TOUT + 2 * (ly - 1), X = blockIdx.x * TOUT + 2 * (lx - 1);
 #pragma unroll
       for (int tsr = 0; tsr < 2; ++tsr) {
+        uint4 q[4];                                        // [dy*2+dx]
         uint4 e[3], o[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -439,8 +444,8 @@ gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restr
         const uint32_t* e0 = reinterpret_cast<const uint32_t*>(&e[0]); const uint32_t* e1 = reinterpret_cast<const uint32_t*>(&e[1]);
         const uint32_t* e2 = reinterpret_cast<const uint32_t*>(&e[2]); const uint32_t* o0 = reinterpret_cast<const uint32_t*>(&o[0]);
         const uint32_t* o1 = reinterpret_cast<const uint32_t*>(&o[1]); const uint32_t* o2 = reinterpret_cast<const uint32_t*>(&o[2]);
-        uint32_t* q00 = reinterpret_cast<uint32_t*>(&q[tsr][0]); uint32_t* q01 = reinterpret_cast<uint32_t*>(&q[tsr][1]);
-        uint32_t* q10 = reinterpret_cast<uint32_t*>(&q[tsr][2]); uint32_t* q11 = reinterpret_cast<uint32_t*>(&q[tsr][3]);
+        uint32_t* q00 = reinterpret_cast<uint32_t*>(&q[0]); uint32_t* q01 = reinterpret_cast<uint32_t*>(&q[1]);
+        uint32_t* q10 = reinterpret_cast<uint32_t*>(&q[2]); uint32_t* q11 = reinterpret_cast<uint32_t*>(&q[3]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           q00[k] = h2_fma(K75, e1[k], h2_mul(K25, e0[k]));
@@ -448,13 +453,12 @@ gn_apply_fir_tiled_kernel(const T* __restrict__ x0, int C, const float2* __restr
           q10[k] = h2_fma(K75, e1[k], h2_mul(K25, e2[k]));
           q11[k] = h2_fma(K75, o1[k], h2_mul(K25, o2[k]));
         }
-      }
-      const int Y = blockIdx.y * TOUT + 2 * (ly - 1), X = blockIdx.x * TOUT + 2 * (lx - 1);
+        T* dst = tsr == 0 ? out0 : out1;
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const size_t o = (((size_t)n * Ho + Y + (d >> 1)) * Wo + X + (d & 1)) * C + c;
-        *reinterpret_cast<uint4*>(out0 + o) = q[0][d];
-        *reinterpret_cast<uint4*>(out1 + o) = q[1][d];
+        for (int d = 0; d < 4; ++d) {
+          const size_t o = (((size_t)n * Ho + Y + (d >> 1)) * Wo + X + (d & 1)) * C + c;
+          *reinterpret_cast<uint4*>(dst + o) = q[d];
+        }
       }
     }
   } else
