@@ -217,12 +217,15 @@ int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, 
  * "time_convs" (0/1: bracket every convolution launch with CUDA events; disables graph replay),
  * "lanes" (1..8 concurrent launch sequences inside a captured sampler graph), "max_graphs" (captured sampler graphs kept,
  * least recently used evicted; default 16).  The kernel A/B switches the tools use ("tc_variant", "attn_variant",
- * "fir_variant", "inconv_variant", "outconv_variant", "tc6_*") select code paths PROCESS-WIDE, not per engine. */
+ * "fir_variant", "inconv_variant", "outconv_variant", "combine_variant", "tc1_narrow", "tc6_*") select code paths
+ * PROCESS-WIDE, not per engine; 0 is always the verified default.  "pdl" (0/1: programmatic dependent launch between the
+ * kernels of the launch sequence) is accepted only by the twin library built with -DSGMSE_B200_PDL (libsgmse_b200_pdl.so,
+ * counter "pdl_compiled" = 1); the default library refuses it. */
 int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value);
 /* counters: "kernel_launches" (since creation), "graph_launches", "cached_graphs", "workspace_bytes", "weights_bytes",
  * "tc_convs_last_forward", "direct_convs_last_forward", "launches_last_forward",
  * "timed_conv_tc_us" / "timed_conv_tc_mflop" / "timed_conv_tc_kbytes" / "timed_conv_tc_count" /
- * "timed_conv_direct_us" (sums over the launches timed since "time_convs" was switched on) */
+ * "timed_conv_direct_us" (sums over the launches timed since "time_convs" was switched on), "pdl_compiled", "pdl" */
 long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key);
 
 #ifdef __cplusplus
