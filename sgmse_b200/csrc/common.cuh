@@ -44,6 +44,17 @@ extern volatile int* g_wait_code_host;
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per device: a launcher remembers (bit per device ordinal) where its kernel already has the
+// attribute, so that engines on several devices of one process all get it.  Not a stream operation: legal during capture.
+static inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // ----------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  Compiled in only with -DSGMSE_B200_PDL (sgmse_b200/build.py --pdl builds a
 // second library, libsgmse_b200_pdl.so): the default library's SASS carries none of these instructions.  Contract of

@@ -429,10 +429,9 @@ void launch_impl(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) 
   P.stats = out.stats; P.slots = out.slots;
   P.dbg = dbg;
   auto kern = conv_tc_kernel<BLOCK_N, NUM_STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_device(attr_devs)) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-    attr_set = true;
   }
   const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
   launch_k(kern, dim3(grid), dim3(NUM_THREADS), (size_t)L::DYN_BYTES, st, ma[0], ma[1], ma[2], mb, md, mr, P);

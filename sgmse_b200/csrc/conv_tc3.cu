@@ -405,10 +405,9 @@ void launch3(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   P.stats = out.stats; P.slots = out.slots;
   P.dbg = dbg;
   auto kern = conv_tc3_kernel<A_STAGES, B_STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_device(attr_devs)) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-    attr_set = true;
   }
   int clusters = num_sms() / 2;
   if (P.num_tiles < clusters) clusters = P.num_tiles;

@@ -444,10 +444,9 @@ void launch5(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   P.stats = out.stats; P.slots = out.slots;
   P.dbg = dbg;
   auto kern = conv_tc5_kernel<A_STAGES, B_STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_device(attr_devs)) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-    attr_set = true;
   }
   const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, st>>>(mx0, mx1, mr0, mr1, mw, md, P);
