@@ -6,6 +6,7 @@
 mkdir -p gpurun_out
 python -m pytest tests -q -m gpu -x -s 2>&1 | tail -80 > gpurun_out/gpu_tests.log
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
+SGMSE_B200_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_zz_next_rows.py -q -m gpu -s -k round2_candidate 2>&1 | tail -30 > gpurun_out/gpu_tests_candidates.log
 timeout 600 python tools/check_candidates.py > gpurun_out/candidates.log 2>&1
 timeout 900 python tools/ab_forward.py fir_variant=2 outconv_variant=3 inconv_variant=2 attn_variant=2 combine_variant=1 tc1_narrow=1 \
     fir_variant=2,outconv_variant=3,inconv_variant=2,attn_variant=2,combine_variant=1,tc1_narrow=1 > gpurun_out/ab_small.log 2>&1
