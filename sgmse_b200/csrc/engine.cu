@@ -401,14 +401,27 @@ struct Fwd {
     count();
   }
 
-  float2* gn(const TensorDesc& x0, const TensorDesc* x1, long long g_off, long long b_off) {
+  // `plain_consumer`: the only reader of (a, b) is apply_plain below -- with the gn_self candidate it rebuilds the
+  // coefficients itself and the finalize launch is skipped (the table is still allocated: same workspace either way)
+  float2* gn(const TensorDesc& x0, const TensorDesc* x1, long long g_off, long long b_off, bool plain_consumer = false) {
     const int Ct = x0.C + (x1 ? x1->C : 0);
     // (a, b) as float2 [N][Ct], followed by the half2 table [N][Ct/2] x 16 B of the in-conv producers (ab16_of)
     float2* ab = (float2*)e.arena.alloc((size_t)x0.N * Ct * 16);
     const int groups = gn_groups(Ct);
     uint4* ab16 = (Ct / groups) % 2 == 0 ? (uint4*)(ab + (size_t)x0.N * Ct) : nullptr;
+    if (plain_consumer && gn_self_applies(x0, x1)) return ab;
     if (!dry) { launch_gn_finalize(st, x0, x1, e.blob_dev + g_off, e.blob_dev + b_off, groups, ab, ab16); count(); }
     return ab;
+  }
+  // y = [silu](a x + b) without resampling: gn_apply_plain on the finalized table, or (gn_self) finalize + apply in one kernel
+  void apply_plain(const TensorDesc& x0, const TensorDesc* x1, const float2* ab, long long g_off, long long b_off, bool silu,
+                   TensorDesc& out) {
+    if (dry) return;
+    if (gn_self_applies(x0, x1))
+      launch_gn_norm_apply(st, x0, x1, e.blob_dev + g_off, e.blob_dev + b_off, gn_groups(x0.C + (x1 ? x1->C : 0)), silu, out);
+    else
+      launch_gn_apply(st, x0, x1, ab, silu, RS_NONE, out, nullptr);
+    count();
   }
 
   TensorDesc resblock(const Layer& l, const TensorDesc& x0, const TensorDesc* x1) {
@@ -417,7 +430,6 @@ struct Fwd {
     const Resample rs = l.up ? RS_UP : (l.down ? RS_DOWN : RS_NONE);
     const int Ho = l.up ? x0.H * 2 : (l.down ? x0.H / 2 : x0.H);
     const int Wo = l.up ? x0.W * 2 : (l.down ? x0.W / 2 : x0.W);
-    float2* ab0 = gn(x0, x1, l.gn0_w, l.gn0_b);
     // Fused path (conv_tc5): the 3x3 convs read the RAW tensor and apply GroupNorm+SiLU on the way into shared
     // memory, so the gn_apply pass (one read + one write of the tensor) and its buffer disappear.
     const bool fuse_ok = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && (g_tc_variant == 0 || g_tc_variant == 5 || g_tc_variant >= 7);
@@ -426,6 +438,7 @@ struct Fwd {
     const int nraw1 = l.shortcut ? ((rs == RS_NONE && x1) ? 2 : 1) : 1;
     const bool fuse1 = fuse_ok && ((e.tc_mask >> 9) & 1) && l.c1.w_tc && shape_ok(Ho, Wo, l.cout, 0, l.cout, nraw1) &&
                        (l.shortcut || l.c1.identity_tail);
+    float2* ab0 = gn(x0, x1, l.gn0_w, l.gn0_b, rs == RS_NONE && !fuse0);
     TensorDesc h0;
     TensorDesc xr;                                 // FIR-resampled raw input (up/down blocks)
     if (rs != RS_NONE) {
@@ -435,7 +448,7 @@ struct Fwd {
       if (!dry) { launch_gn_apply(st, x0, nullptr, ab0, true, rs, h0, &xr); count(); }
     } else if (!fuse0) {
       h0 = act(N, Ho, Wo, Ct, false);
-      if (!dry) { launch_gn_apply(st, x0, x1, ab0, true, RS_NONE, h0, nullptr); count(); }
+      apply_plain(x0, x1, ab0, l.gn0_w, l.gn0_b, true, h0);
     }
     TensorDesc h1 = act(N, Ho, Wo, l.cout, true);
     {
@@ -452,11 +465,11 @@ struct Fwd {
       a.temb = temb + l.temb_off; a.temb_stride = temb_stride;   // Conv_0.bias is folded into the table
       conv(a, h1, 0);
     }
-    float2* ab1 = gn(h1, nullptr, l.gn1_w, l.gn1_b);
+    float2* ab1 = gn(h1, nullptr, l.gn1_w, l.gn1_b, !fuse1);
     TensorDesc h2;
     if (!fuse1) {
       h2 = act(N, Ho, Wo, l.cout, false);
-      if (!dry) { launch_gn_apply(st, h1, nullptr, ab1, true, RS_NONE, h2, nullptr); count(); }
+      apply_plain(h1, nullptr, ab1, l.gn1_w, l.gn1_b, true, h2);
     }
     TensorDesc out = act(N, Ho, Wo, l.cout, true);
     {
@@ -486,9 +499,9 @@ struct Fwd {
   TensorDesc attn(const Layer& l, const TensorDesc& x) {
     const int C = l.cin;
     SG_CHECK(x.C == C, "attention %d: channel mismatch", l.idx);
-    float2* ab = gn(x, nullptr, l.gn0_w, l.gn0_b);
+    float2* ab = gn(x, nullptr, l.gn0_w, l.gn0_b, true);
     TensorDesc hn = act(x.N, x.H, x.W, C, false);
-    if (!dry) { launch_gn_apply(st, x, nullptr, ab, false, RS_NONE, hn, nullptr); count(); }
+    apply_plain(x, nullptr, ab, l.gn0_w, l.gn0_b, false, hn);
     TensorDesc qkv = act(x.N, x.H, x.W, 3 * C, false);
     {
       ConvArgs a;
@@ -512,14 +525,14 @@ struct Fwd {
   }
 
   const float4* outconv(const Layer& l, const TensorDesc& h, const float4* addend) {
-    float2* ab = gn(h, nullptr, l.gn0_w, l.gn0_b);
+    float2* ab = gn(h, nullptr, l.gn0_w, l.gn0_b, !out_conv_fuses_gn(h));
     if (out_conv_fuses_gn(h)) {                    // GroupNorm-apply + SiLU happen while the conv stages its tile
       float4* out = act4(h.N, h.H, h.W);
       if (!dry) { launch_out_conv(st, h, l.small_w, l.out_bias_host, addend, out, ab, l.small_wfrag); count(); }
       return out;
     }
     TensorDesc a = act(h.N, h.H, h.W, h.C, false);
-    if (!dry) { launch_gn_apply(st, h, nullptr, ab, true, RS_NONE, a, nullptr); count(); }
+    apply_plain(h, nullptr, ab, l.gn0_w, l.gn0_b, true, a);
     float4* out = act4(h.N, h.H, h.W);
     if (!dry) { launch_out_conv(st, a, l.small_w, l.out_bias_host, addend, out, nullptr, l.small_wfrag); count(); }
     return out;
@@ -1778,6 +1791,7 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "inconv_variant") { sgmse::g_inconv_variant = (int)value; clear_graphs(*e); }
   else if (k == "combine_variant") { sgmse::g_combine_variant = (int)value; clear_graphs(*e); }
   else if (k == "tc1_narrow") { sgmse::g_tc1_narrow = (int)value; clear_graphs(*e); }
+  else if (k == "gn_self") { sgmse::g_gn_self = (int)value; clear_graphs(*e); }
   else if (k == "outconv_variant") {
     sgmse::g_outconv_variant = (int)value;       // changes the buffers a forward needs (fused GroupNorm or not)
     if (e->lanes.size() > 1) ensure_lanes(*e, 1);

@@ -191,6 +191,114 @@ gn_apply_plain_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1
 }
 
 // ------------------------------------------------------------------------------------------------
+// gn_self (round-2 candidate, default off, not yet run on a GPU): gn_finalize folded into the gn_apply_plain that
+// consumes it, for the small tensors of the levels below 32 rows (H*W <= 512), where a forward spends ~46 launches of
+// ~6 us on finalizing statistics that fit in a few hundred bytes.  Every block first rebuilds (a, b) of ITS sample in
+// shared memory -- warp w reduces groups w, w+8, ...: lane j adds the group's (channel, slot) items j, j+32, ... in
+// double and the warp combines them with the same xor tree gn_finalize uses, so for channels-per-group x slots <= 32
+// (one item per lane) the coefficients are bit-identical by construction; beyond that (a Combine output has 16 slots of 32
+// pixels at 16x32) the association differs, but these are fp64 sums of <= 512 fp32 partials, which do not round unless the
+// partials span more than ~2^20 in magnitude -- and then applies them exactly like gn_apply_plain.
+// ------------------------------------------------------------------------------------------------
+int g_gn_self = 0;
+
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(256)
+gn_norm_apply_kernel(const T* __restrict__ x0, int C0, const float* __restrict__ st0, int slots0,
+                     const T* __restrict__ x1, int C1, const float* __restrict__ st1, int slots1,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int cpg, double inv_count,
+                     int HW, int ppb, T* __restrict__ out) {
+  pdl_trigger(); pdl_wait();
+  extern __shared__ float2 ab_s[];                        // [Ct]
+  const int Ct = C0 + C1, groups = Ct / cpg, n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int max_slots = slots0 > slots1 ? slots0 : slots1;
+  for (int g = warp; g < groups; g += (int)(blockDim.x >> 5)) {
+    double s = 0.0, q = 0.0;
+    for (int j = lane; j < cpg * max_slots; j += 32) {
+      const int cl = j % cpg, slot = j / cpg;
+      const int ch = g * cpg + cl;
+      if (ch < C0) {
+        if (slot < slots0) {
+          const float2 v = *reinterpret_cast<const float2*>(st0 + (((size_t)n * slots0 + slot) * C0 + ch) * 2);
+          s += v.x; q += v.y;
+        }
+      } else {
+        if (slot < slots1) {
+          const float2 v = *reinterpret_cast<const float2*>(st1 + (((size_t)n * slots1 + slot) * C1 + (ch - C0)) * 2);
+          s += v.x; q += v.y;
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-6));
+    for (int cl = lane; cl < cpg; cl += 32) {
+      const int ch = g * cpg + cl;
+      const float a = gamma[ch] * rstd;
+      ab_s[ch] = make_float2(a, beta[ch] - (float)mean * a);
+    }
+  }
+  __syncthreads();
+  const int cvpp = Ct >> 3;
+  const int cv = threadIdx.x % cvpp, pl = threadIdx.x / cvpp;
+  if (pl >= ppb) return;
+  const int c = cv << 3;
+  const T* src; int Cs, cs;
+  if (c < C0) { src = x0; Cs = C0; cs = c; } else { src = x1; Cs = C1; cs = c - C0; }
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float2 v = ab_s[c + i]; a[i] = v.x; b[i] = v.y; }
+  const T* sp = src + (size_t)n * HW * Cs + cs;
+  T* op = out + (size_t)n * HW * Ct + c;
+  const int stride = gridDim.x * ppb;
+  for (int p = blockIdx.x * ppb + pl; p < HW; p += stride) {
+    Vec8<T> v; float f[8];
+    v.load(sp + (size_t)p * Cs);
+    v.get(f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float h = fmaf(a[i], f[i], b[i]);
+      if (SILU) h = silu_f(h);
+      f[i] = h;
+    }
+    v.set(f);
+    v.store(op + (size_t)p * Ct);
+  }
+}
+
+bool gn_self_applies(const TensorDesc& x0, const TensorDesc* x1) {
+  const int Ct = x0.C + (x1 ? x1->C : 0);
+  return g_gn_self != 0 && x0.H * x0.W <= 512 && Ct % 8 == 0 && Ct / 8 <= 256;
+}
+
+void launch_gn_norm_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float* gamma, const float* beta,
+                          int groups, bool silu, TensorDesc& out) {
+  const int C1 = x1 ? x1->C : 0;
+  const int Ct = x0.C + C1, cvpp = Ct / 8;
+  SG_CHECK(Ct % groups == 0 && out.C == Ct && out.N == x0.N && out.H == x0.H && out.W == x0.W, "gn_norm_apply: shape mismatch");
+  SG_CHECK(x0.stats && x0.slots > 0 && (!x1 || (x1->stats && x1->slots > 0)), "GroupNorm input has no statistics");
+  const int cpg = Ct / groups;
+  const double inv_count = 1.0 / ((double)x0.H * x0.W * cpg);
+  const int ppb = 256 / cvpp, HW = x0.H * x0.W;
+  int gx = cdiv(HW, ppb * 4);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, x0.N);
+  const size_t smem = (size_t)Ct * sizeof(float2);
+#define GO(T, S) launch_k(gn_norm_apply_kernel<T, S>, grid, dim3(256), smem, st, (const T*)x0.p, x0.C, x0.stats, x0.slots, \
+                          x1 ? (const T*)x1->p : (const T*)nullptr, C1, x1 ? x1->stats : (const float*)nullptr, x1 ? x1->slots : 0, gamma, beta, cpg, inv_count, HW, ppb, (T*)out.p)
+  if (x0.dt == DT_F16) { if (silu) GO(__half, true); else GO(__half, false); }
+  else { if (silu) GO(float, true); else GO(float, false); }
+#undef GO
+  CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
 // gn_apply + FIR up/down: one thread = one output pixel x 8 channels; grid (blocks, N).
 // out0 = FIR(silu(a*x+b)), out1 = FIR(x) (the ResBlock shortcut input), one read of x.
 // ------------------------------------------------------------------------------------------------

@@ -34,6 +34,11 @@ enum Resample { RS_NONE = 0, RS_DOWN = 1, RS_UP = 2 };
 void launch_gn_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float2* ab, bool silu,
                      Resample rs, TensorDesc& out0, TensorDesc* out1);
 
+// gn_self (round-2 candidate): GroupNorm finalize folded into the plain apply for tensors with H*W <= 512 (see gn.cu)
+extern int g_gn_self;
+bool gn_self_applies(const TensorDesc& x0, const TensorDesc* x1);
+void launch_gn_norm_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float* gamma, const float* beta,
+                          int groups, bool silu, TensorDesc& out);
 extern int g_fir_variant;   // 0: one-MUFU (tanh-form) silu + half2 FIR-down arithmetic in the tiled fp16 kernels; 1: expf silu, fp32 FIR
                             // 2: 0 + phase-1 loads in flight at once + half2 quad FIR-up (round-2 candidate, see gn.cu)
 

@@ -4,7 +4,7 @@
 
 For each option it evaluates the score network with the option off and on -- the reduced config of the golden fixtures
 and the full-size network at [2, 256, 128] and [2, 256, 512] -- and checks what the candidate promises:
-bit-identical output for `outconv_variant 3`, `inconv_variant 2`, `attn_variant 2`, `combine_variant 1`, `tc1_narrow 1`
+bit-identical output for `outconv_variant 3`, `inconv_variant 2`, `attn_variant 2`, `combine_variant 1`, `tc1_narrow 1`, `gn_self 1`
 (same arithmetic, different memory pipelining / tiling); rel-L2 <= 2e-3 for `fir_variant 2` (half2 FIR-up arithmetic).
 A candidate that passes goes into `tools/ab_forward.py` for timing and, if it pays, becomes the default together with a
 GPU test in tests/test_gpu_parity.py::test_small_end_kernel_variants_agree.
@@ -19,7 +19,7 @@ from sgmse_b200 import Engine, EngineConfig
 from sgmse_b200.synth import synthetic_blob
 
 CANDIDATES = [("outconv_variant", 3, 0.0), ("inconv_variant", 2, 0.0), ("attn_variant", 2, 0.0), ("combine_variant", 1, 0.0),
-              ("tc1_narrow", 1, 0.0), ("fir_variant", 2, 2e-3)]
+              ("tc1_narrow", 1, 0.0), ("gn_self", 1, 0.0), ("fir_variant", 2, 2e-3)]
 SMALL = dict(nf=32, ch_mult=(1, 2, 2), image_size=64, num_res_blocks=1, attn_resolutions=(16,), n_fft=126, hop_length=32)
 CASES = [("small nf=32 [2,64,64]", EngineConfig(mode="fp16_tc", max_batch=2, use_graphs=False, **SMALL), (2, 2, 64, 64)),
          ("full size [2,256,128]", EngineConfig(mode="fp16_tc", max_batch=2, use_graphs=False), (2, 2, 256, 128)),
