@@ -217,7 +217,7 @@ int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, 
  * "time_convs" (0/1: bracket every convolution launch with CUDA events; disables graph replay),
  * "lanes" (1..8 concurrent launch sequences inside a captured sampler graph), "max_graphs" (captured sampler graphs kept,
  * least recently used evicted; default 16).  The kernel A/B switches the tools use ("tc_variant", "attn_variant",
- * "fir_variant", "inconv_variant", "outconv_variant", "combine_variant", "tc1_narrow", "gn_self", "tc6_*") select code paths
+ * "fir_variant", "inconv_variant", "outconv_variant", "combine_variant", "tc1_narrow", "gn_self", "gnfin_variant", "tc6_*") select code paths
  * PROCESS-WIDE, not per engine; 0 is always the verified default.  "pdl" (0/1: programmatic dependent launch between the
  * kernels of the launch sequence) is accepted only by the twin library built with -DSGMSE_B200_PDL (libsgmse_b200_pdl.so,
  * counter "pdl_compiled" = 1); the default library refuses it. */

@@ -13,6 +13,12 @@ namespace sgmse {
 // ------------------------------------------------------------------------------------------------
 // gn_finalize: grid (groups, N).  Sums the producer's per-slot partials in double, fixed order.
 // ------------------------------------------------------------------------------------------------
+// BATCH (gnfin_variant 1, round-2 candidate, not yet run on a GPU): the partials of a thread are loaded eight at a time before
+// they are added, in the same order (the plain loop is load -> add -> branch: 8 serialized round trips per thread at the 512-slot
+// levels, most of the kernel's 5.9 us); bit-identical.
+int g_gnfin_variant = 0;
+
+template <bool BATCH>
 __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int slots0,
                                    const float* __restrict__ st1, int C1, int slots1,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -22,6 +28,28 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int sl
   const int Ct = C0 + C1;
   const int max_slots = slots0 > slots1 ? slots0 : slots1;
   double s = 0.0, q = 0.0;
+  if (BATCH) {
+    const int items = cpg * max_slots;
+    for (int j0 = threadIdx.x; j0 < items; j0 += 8 * blockDim.x) {
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u * blockDim.x;
+        v[u] = make_float2(0.f, 0.f);
+        if (j < items) {
+          const int cl = j % cpg, slot = j / cpg;
+          const int ch = g * cpg + cl;
+          if (ch < C0) {
+            if (slot < slots0) v[u] = *reinterpret_cast<const float2*>(st0 + (((size_t)n * slots0 + slot) * C0 + ch) * 2);
+          } else {
+            if (slot < slots1) v[u] = *reinterpret_cast<const float2*>(st1 + (((size_t)n * slots1 + slot) * C1 + (ch - C0)) * 2);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s += v[u].x; q += v[u].y; }   // an absent item adds +0.0: the sum is unchanged
+    }
+  } else
   for (int j = threadIdx.x; j < cpg * max_slots; j += blockDim.x) {
     const int cl = j % cpg, slot = j / cpg;
     const int ch = g * cpg + cl;
@@ -95,7 +123,13 @@ void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc*
   SG_CHECK(!ab16 || cpg % 2 == 0, "GroupNorm: the half2 coefficient table needs an even number of channels per group");
   const double inv_count = 1.0 / ((double)s0.H * s0.W * cpg);
   dim3 grid(groups, s0.N);
-  launch_k(gn_finalize_kernel, grid, dim3(256), 0, st, s0.stats, s0.C, s0.slots, s1 ? s1->stats : nullptr, C1,
+  if (g_gnfin_variant == 1) {
+    launch_k(gn_finalize_kernel<true>, grid, dim3(256), 0, st, s0.stats, s0.C, s0.slots, s1 ? s1->stats : nullptr, C1,
+             s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab, ab16);
+    CUDA_OK(cudaGetLastError());
+    return;
+  }
+  launch_k(gn_finalize_kernel<false>, grid, dim3(256), 0, st, s0.stats, s0.C, s0.slots, s1 ? s1->stats : nullptr, C1,
                                            s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab, ab16);
   CUDA_OK(cudaGetLastError());
 }

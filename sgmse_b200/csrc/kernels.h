@@ -35,6 +35,7 @@ void launch_gn_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1
                      Resample rs, TensorDesc& out0, TensorDesc* out1);
 
 // gn_self (round-2 candidate): GroupNorm finalize folded into the plain apply for tensors with H*W <= 512 (see gn.cu)
+extern int g_gnfin_variant;   // 1: gn_finalize with its partial loads batched eight at a time (round-2 candidate, bit-identical)
 extern int g_gn_self;
 bool gn_self_applies(const TensorDesc& x0, const TensorDesc* x1);
 void launch_gn_norm_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float* gamma, const float* beta,

@@ -240,7 +240,7 @@ def test_every_ab_switch_is_a_known_option():
     anything else is reported as an error.  Host-only: none of these touches CUDA state on an engine that has run nothing."""
     eng = Engine(CASES[2][1])
     for key in ("tc_variant", "attn_variant", "tc6_rings", "tc6_mma", "tc6_tma_poll", "fir_variant", "inconv_variant",
-                "outconv_variant", "combine_variant", "tc1_narrow", "gn_self", "pdl", "record_taps", "use_graphs"):
+                "outconv_variant", "combine_variant", "tc1_narrow", "gn_self", "gnfin_variant", "pdl", "record_taps", "use_graphs"):
         eng.set_option(key, 0)
     eng.set_option("max_graphs", 16)
     eng.set_option("lanes", 1)

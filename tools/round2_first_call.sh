@@ -8,12 +8,12 @@ python -m pytest tests -q -m gpu -x -s 2>&1 | tail -80 > gpurun_out/gpu_tests.lo
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
 SGMSE_B200_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_zz_next_rows.py -q -m gpu -s -k round2_candidate 2>&1 | tail -30 > gpurun_out/gpu_tests_candidates.log
 timeout 600 python tools/check_candidates.py > gpurun_out/candidates.log 2>&1
-timeout 900 python tools/ab_forward.py fir_variant=2 outconv_variant=3 inconv_variant=2 attn_variant=2 combine_variant=1 tc1_narrow=1 gn_self=1 \
-    fir_variant=2,outconv_variant=3,inconv_variant=2,attn_variant=2,combine_variant=1,tc1_narrow=1,gn_self=1 > gpurun_out/ab_small.log 2>&1
+timeout 900 python tools/ab_forward.py fir_variant=2 outconv_variant=3 inconv_variant=2 attn_variant=2 combine_variant=1 tc1_narrow=1 gn_self=1 gnfin_variant=1 \
+    fir_variant=2,outconv_variant=3,inconv_variant=2,attn_variant=2,combine_variant=1,tc1_narrow=1,gn_self=1,gnfin_variant=1 > gpurun_out/ab_small.log 2>&1
 SGMSE_B200_PDL=1 timeout 900 python tools/check_pdl.py > gpurun_out/pdl.log 2>&1
 SGMSE_B200_PDL=1 timeout 600 python bench.py --steps 3 --warmup 3 --opt pdl=1 --no-cpu-baseline > gpurun_out/bench_c2_pdl.json 2> gpurun_out/bench_c2_pdl.err
 timeout 600 python bench.py --steps 3 --warmup 3 --lanes 2 --no-cpu-baseline --no-roofline > gpurun_out/bench_c2_lanes2.json 2> gpurun_out/bench_c2_lanes2.err
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-roofline --opt fir_variant=2 --opt outconv_variant=3 --opt inconv_variant=2 --opt attn_variant=2 --opt combine_variant=1 --opt tc1_narrow=1 --opt gn_self=1 > gpurun_out/bench_c2_candidates.json 2> gpurun_out/bench_c2_candidates.err
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-roofline --opt fir_variant=2 --opt outconv_variant=3 --opt inconv_variant=2 --opt attn_variant=2 --opt combine_variant=1 --opt tc1_narrow=1 --opt gn_self=1 --opt gnfin_variant=1 > gpurun_out/bench_c2_candidates.json 2> gpurun_out/bench_c2_candidates.err
 (nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/mufu_bench tools/mufu_bench.cu && timeout 120 /tmp/mufu_bench) > gpurun_out/mufu.log 2>&1
 timeout 600 python bench.py --config 3 --steps 2 --warmup 3 --no-roofline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err
 timeout 900 python bench.py --config 4 --steps 2 --warmup 3 --no-roofline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err

@@ -68,7 +68,8 @@ def main():
         print(f"  changed ({kind}, {len(d)} lines): {k[:140]}")
     new_only = sorted(set(new) - set(old))
     for k in sorted(set(old) - set(new)):
-        twins = [n for n in new_only if new[n] == old[k] and n.split("<")[0] == k.split("<")[0]]
+        base = lambda x: x.split("(")[0].split("<")[0].split()[-1]   # noqa: E731  (drop return type, template and argument lists)
+        twins = [n for n in new_only if new[n] == old[k] and base(n) == base(k)]
         if twins:
             print(f"  renamed, identical instruction stream: {k[:110]}  ->  {twins[0][:110]}")
             new_only = [n for n in new_only if n != twins[0]]
