@@ -81,6 +81,14 @@ struct Tc6Params {
   int mma_style;                 // 0: one elect + 4 UMMAs + commit per tap (mma_tap_elect); 1: one elect per UMMA
   int tma_poll;                  // 0: ordered issue loop; 1: two cursors (activations, weights) polled without blocking
   int* dbg;
+#ifdef SGMSE_B200_PDL
+  // ABLATIONS (twin library only, option "tc6_ablate"; results are WRONG on purpose, only the time is of interest):
+  //   bit 0: weight tiles are loaded for a CTA's first tile only, later tiles reuse whatever the ring holds -> what the
+  //          288 KB of weight tiles per 256-pixel tile cost (the L2 -> SM hypothesis of DESIGN.md §3)
+  //   bit 1: the fused producers copy the raw activations (no GroupNorm, no tanh) -> what the MUFU / FMA work of the
+  //          transform costs
+  int ablate;
+#endif
 };
 
 template <int A_STAGES, int B_STAGES>
@@ -212,6 +220,12 @@ __device__ __forceinline__ uint32_t silu_half_pair(float hz0, float hz1) {
   asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(yu) : "r"(hzu), "r"(tu));
   return yu;
 }
+
+#ifdef SGMSE_B200_PDL
+#define TC6_ABLATE_RAW_COPY (P.ablate & 2)
+#else
+#define TC6_ABLATE_RAW_COPY false
+#endif
 
 template <int A_STAGES, int B_STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -380,8 +394,15 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             for (int tap = 0; tap < ntap; ++tap) {
               const int kb = P.seg_kb0[s] + tap * chunks + ch;
               mbar_wait(&w_empty[sb], pb ^ 1, P.dbg, 150 + sb);
-              mbar_arrive_expect_tx(&w_full[sb], W_BYTES);
-              tma_load_2d(smem + L::OFF_W + sb * W_BYTES, &map_w, &w_full[sb], kb * BLOCK_K, c_blk * BLOCK_C);
+#ifdef SGMSE_B200_PDL
+              if ((P.ablate & 1) && tile != (int)blockIdx.x) {
+                mbar_arrive(&w_full[sb]);            // ablation: no load, the stage keeps its previous bytes
+              } else
+#endif
+              {
+                mbar_arrive_expect_tx(&w_full[sb], W_BYTES);
+                tma_load_2d(smem + L::OFF_W + sb * W_BYTES, &map_w, &w_full[sb], kb * BLOCK_K, c_blk * BLOCK_C);
+              }
               if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
             }
           }
@@ -661,10 +682,14 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           if (row < HALO_ROWS && (unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W) {
             const __half2* h = reinterpret_cast<const __half2*>(&v[j]);
             uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+            if (TC6_ABLATE_RAW_COPY) {               // ablation (twin library only): raw copy instead of silu(a*x+b)
+              o = v[j];
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = __half22float2(h[k]);
-              ow[k] = silu_half_pair(fmaf(a[2 * k], f.x, b[2 * k]), fmaf(a[2 * k + 1], f.y, b[2 * k + 1]));
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                ow[k] = silu_half_pair(fmaf(a[2 * k], f.x, b[2 * k]), fmaf(a[2 * k + 1], f.y, b[2 * k + 1]));
+              }
             }
           }
           if (row < HALO_ROWS) *reinterpret_cast<uint4*>(stage + row * 128 + ((cv ^ (row & 7)) << 4)) = o;
@@ -746,6 +771,9 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   P.desc_mode = desc_mode;
   P.mma_style = g_tc6_mma_style; P.tma_poll = g_tc6_tma_poll;
   P.dbg = dbg;
+#ifdef SGMSE_B200_PDL
+  P.ablate = g_tc6_ablate;
+#endif
   auto kern = conv_tc6_kernel<A_STAGES, B_STAGES>;
   static unsigned long long attr_devs = 0;
   if (first_use_on_device(attr_devs)) {
@@ -770,6 +798,7 @@ bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out) {
 }
 
 // A/B switches (engine options "tc6_rings", "tc6_mma", "tc6_tma_poll")
+int g_tc6_ablate = 0;   // twin library only (see Tc6Params::ablate)
 int g_tc6_rings = [] { const char* v = getenv("SGMSE_B200_TC6_RINGS"); return v ? atoi(v) : 0; }();   // 0: 2 activation + 6 weight stages; 1: 3 + 4
 int g_tc6_mma_style = 0;
 int g_tc6_tma_poll = 0;

@@ -1793,6 +1793,11 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "tc1_narrow") { sgmse::g_tc1_narrow = (int)value; clear_graphs(*e); }
   else if (k == "gn_self") { sgmse::g_gn_self = (int)value; clear_graphs(*e); }
   else if (k == "gnfin_variant") { sgmse::g_gnfin_variant = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_ablate") {
+    SG_CHECK(value == 0 || sgmse::pdl_compiled(), "option 'tc6_ablate' exists in the -DSGMSE_B200_PDL twin library only");
+    sgmse::g_tc6_ablate = (int)value;
+    clear_graphs(*e);
+  }
   else if (k == "outconv_variant") {
     sgmse::g_outconv_variant = (int)value;       // changes the buffers a forward needs (fused GroupNorm or not)
     if (e->lanes.size() > 1) ensure_lanes(*e, 1);

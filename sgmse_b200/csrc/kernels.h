@@ -94,6 +94,7 @@ void launch_conv_tc5(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* d
 bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out);
 bool conv_tc6_fuse_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
+extern int g_tc6_ablate;   // timing ablations of conv_tc6, compiled into the -DSGMSE_B200_PDL twin only (results are wrong on purpose)
 extern int g_tc6_rings, g_tc6_mma_style, g_tc6_tma_poll;   // conv_tc6 A/B switches, see conv_tc6.cu
 extern int g_tc1_narrow;   // 1: conv_tc v1 takes 64-wide channel tiles when 128-wide ones fill less than half the SMs (round-2 candidate)
 extern int g_tc_variant;   // 0 (= 7, 8): newest applicable kernels (v6 with fused GroupNorm+SiLU where possible: LDG-fed producers,

@@ -10,6 +10,9 @@ SGMSE_B200_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_zz_next_rows
 timeout 600 python tools/check_candidates.py > gpurun_out/candidates.log 2>&1
 timeout 900 python tools/ab_forward.py fir_variant=2 outconv_variant=3 inconv_variant=2 attn_variant=2 combine_variant=1 tc1_narrow=1 gn_self=1 gnfin_variant=1 \
     fir_variant=2,outconv_variant=3,inconv_variant=2,attn_variant=2,combine_variant=1,tc1_narrow=1,gn_self=1,gnfin_variant=1 > gpurun_out/ab_small.log 2>&1
+# ablations of conv_tc6 (twin library; outputs are wrong on purpose, only the conv time matters): 1 = weights loaded once per CTA,
+# 2 = producers copy instead of GroupNorm+SiLU, 3 = both; tc_variant=6 = TMA-fed operands
+SGMSE_B200_PDL=1 timeout 900 python tools/ab_forward.py tc6_ablate=1 tc6_ablate=2 tc6_ablate=3 tc_variant=6 tc_variant=6,tc6_ablate=1 > gpurun_out/ab_ablate.log 2>&1
 SGMSE_B200_PDL=1 timeout 900 python tools/check_pdl.py > gpurun_out/pdl.log 2>&1
 SGMSE_B200_PDL=1 timeout 600 python bench.py --steps 3 --warmup 3 --opt pdl=1 --no-cpu-baseline > gpurun_out/bench_c2_pdl.json 2> gpurun_out/bench_c2_pdl.err
 timeout 600 python bench.py --steps 3 --warmup 3 --lanes 2 --no-cpu-baseline --no-roofline > gpurun_out/bench_c2_lanes2.json 2> gpurun_out/bench_c2_lanes2.err
