@@ -63,3 +63,17 @@ def test_reference_arm_runs_on_rank_0_only():
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_tools_are_importable_python_and_shell_scripts_parse():
+    """The round-2 tools were written without a GPU: at least their syntax is checked here (py_compile, bash -n)."""
+    import glob
+    import os
+    import py_compile
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in sorted(glob.glob(os.path.join(root, "tools", "*.py"))):
+        py_compile.compile(f, doraise=True)
+    for f in sorted(glob.glob(os.path.join(root, "tools", "*.sh"))):
+        r = subprocess.run(["bash", "-n", f], capture_output=True, text=True)
+        assert r.returncode == 0, f"{f}: {r.stderr}"
