@@ -4,7 +4,7 @@
 #   gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'
 # Every step writes its own log under gpurun_out/; a failing step does not stop the next one.
 mkdir -p gpurun_out
-python -m pytest tests -q -m gpu -x -s 2>&1 | tail -80 > gpurun_out/gpu_tests.log
+python -m pytest tests -q -m gpu -s --maxfail=20 2>&1 | tail -120 > gpurun_out/gpu_tests.log
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
 SGMSE_B200_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_zz_next_rows.py -q -m gpu -s -k round2_candidate 2>&1 | tail -30 > gpurun_out/gpu_tests_candidates.log
 timeout 600 python tools/check_candidates.py > gpurun_out/candidates.log 2>&1
