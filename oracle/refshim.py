@@ -1,12 +1,15 @@
 """Import shim for the *live* reference (build container only).
 
 ``/root/reference`` is mounted read-only in the build container and does not
-exist on the GPU box.  ``sgmse.model`` / ``sgmse.data_module`` / ``sgmse.util.other``
+exist on the GPU box; there the byte-for-byte staged copy ``oracle/_ref/`` is used
+(``oracle/build_ref.py``, run by ``__graft_entry__.build()``; git-ignored, ships with the
+gpurun snapshot).  ``sgmse.model`` / ``sgmse.data_module`` / ``sgmse.util.other``
 import six packages that are not installed (pytorch_lightning, torch_ema, librosa,
 pesq, pystoi, torch_pesq); none carries hot-path arithmetic, so
 inert stand-ins are injected into ``sys.modules`` before import.
 
-Used by oracle/make_golden.py and tests/test_oracle_vs_reference.py.
+Used by oracle/make_golden.py, tests/test_oracle_vs_reference.py, the ``-m gpu`` drop-in tests and the
+CPU arm of bench.py.
 TEST INFRASTRUCTURE – see oracle/__init__.py.
 """
 from __future__ import annotations
@@ -19,11 +22,31 @@ from typing import List
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("SGMSE_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("SGMSE_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isdir(os.path.join(cand, "sgmse")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "sgmse"))
+
+
+def reference_kind() -> str:
+    """'live' = /root/reference itself, 'staged' = the oracle/_ref copy, 'none'."""
+    if not reference_available():
+        return "none"
+    return "staged" if os.path.abspath(REFERENCE_ROOT) == os.path.abspath(_STAGED) else "live"
 
 
 def _install_stubs():
@@ -83,16 +106,28 @@ def _install_stubs():
             sys.modules[name] = m
 
 
-def import_reference():
-    """Returns the reference's ``sgmse`` package (imported from REFERENCE_ROOT)."""
+def import_reference(cuda_op: bool = False):
+    """Returns the reference's ``sgmse`` package (imported from REFERENCE_ROOT).
+
+    cuda_op=False (default): the reference stays a CPU checker -- its upfirdn2d CUDA op is JIT-compiled by
+    ``torch.utils.cpp_extension.load`` at import time wherever ``torch.cuda.is_available()``
+    (op/upfirdn2d.py:11-20), a minute of nvcc on every fresh GPU box; CUDA is hidden for the duration of the
+    first import so CPU tensors take ``upfirdn2d_native`` exactly as in the build container.  cuda_op=True
+    lets the JIT happen (tools/bench_reference_gpu.py: the reference's own GPU path on the same B200)."""
     if not reference_available():
         raise RuntimeError("reference not available at " + REFERENCE_ROOT)
     _install_stubs()
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    import sgmse  # noqa
-    import sgmse.model, sgmse.data_module, sgmse.sdes, sgmse.sampling, sgmse.backbones  # noqa
-    import sgmse.util.other  # noqa
+    orig = torch.cuda.is_available
+    if not cuda_op and "sgmse.backbones.ncsnpp_utils.op.upfirdn2d" not in sys.modules:
+        torch.cuda.is_available = lambda: False
+    try:
+        import sgmse  # noqa
+        import sgmse.model, sgmse.data_module, sgmse.sdes, sgmse.sampling, sgmse.backbones  # noqa
+        import sgmse.util.other  # noqa
+    finally:
+        torch.cuda.is_available = orig
     return sgmse
 
 

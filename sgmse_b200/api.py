@@ -72,6 +72,12 @@ def config_from_score_model(model, mode="fp16_tc", max_batch=8, use_graphs=True)
         if backbone != "ncsnpp_v2":
             raise NotImplementedError("the Schroedinger-bridge SDE is driven by the preconditioned 'ncsnpp_v2' forward")
         # get_sb_sampler works on sde.copy() = SBVESDE(k, c, N) (sdes.py:265-266): the stabiliser eps falls back to 1e-8
+        # ... while ScoreModel.forward evaluates self.sde._std(t) on the model's OWN sde with its configured --eps
+        # (sdes.py:242,297-301).  The engine carries one stabiliser: refuse a checkpoint trained with another eps
+        # rather than silently precondition with different c_in / c_out / c_skip.
+        if abs(float(getattr(sde, "eps", 1e-8)) - 1e-8) > 1e-14:
+            raise NotImplementedError(f"SBVESDE eps={sde.eps!r}: only the default stabiliser 1e-8 is accelerated "
+                                      "(ScoreModel.forward preconditions with the model's own sde.eps, the samplers with sde.copy()'s 1e-8)")
         sde_kw = dict(sde="sbve", sb_k=float(sde.k), sb_c=float(sde.c), sb_eps=1e-8)
     else:
         raise NotImplementedError("only the OUVE and SBVE SDEs are accelerated")
@@ -172,6 +178,14 @@ def make_enhance(engine: Engine):
         """One-call speech enhancement of noisy speech `y` [1, T] (or [B, T])."""
         start = time.time()
         yy = y if y.dim() == 2 else y[None]
+        # the reference forwards **kwargs to get_pc_sampler / get_ode_sampler (model.py:443-447): what the engine honours is
+        # passed on, anything else is refused instead of being dropped silently
+        known = {"seed", "pad_mode", "denoise", "probability_flow", "eps", "intermediate", "noise", "rtol", "atol", "method"}
+        unknown = sorted(set(kwargs) - known)
+        if unknown:
+            raise NotImplementedError(f"enhance(): keyword(s) {unknown} are not supported by the sgmse_b200 engine")
+        if kwargs.get("intermediate", False):
+            raise NotImplementedError("enhance(): intermediate=True is not supported by the sgmse_b200 engine")
         common = dict(seed=kwargs.get("seed", int(torch.randint(0, 2 ** 62, (1,)).item())), pad_mode=kwargs.get("pad_mode", "zero_pad"))
         sde_name = type(self.sde).__name__
         if sde_name == "SBVESDE":                     # model.py:450-452: get_sb_sampler(sde, Y, sampler_type=sde.sampler_type)
@@ -187,8 +201,11 @@ def make_enhance(engine: Engine):
         else:
             if getattr(self.sde, "sampler_type", "pc") != "pc":
                 raise ValueError("Invalid sampler type for SGMSE sampling: {}".format(sampler_type))   # model.py:448-449
+            if "eps" in kwargs and abs(kwargs["eps"] - engine.cfg.t_eps) > 1e-12:
+                raise NotImplementedError("eps other than ScoreModel.t_eps is baked into the engine configuration")
             x_hat = engine.enhance(yy.detach().cpu().float(), N=N, predictor=predictor, corrector=corrector,
-                                   corrector_steps=corrector_steps, snr=snr, **common)
+                                   corrector_steps=corrector_steps, snr=snr, denoise=kwargs.get("denoise", True),
+                                   probability_flow=kwargs.get("probability_flow", False), noise=kwargs.get("noise", None), **common)
             sb_nfe = None
         x_hat = x_hat.squeeze().numpy()
         end = time.time()
@@ -225,7 +242,7 @@ def install(model, engine: Optional[Engine] = None, rebind_forward=True, refresh
         uninstall(model)                              # re-installing: start again from the model's own methods
     if engine is None:
         engine = engine_from_score_model(model, **kw)
-    model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "get_ode_sampler", "enhance", "forward", "eval")}
+    model._sgmse_b200_saved = {k: model.__dict__.get(k) for k in ("get_pc_sampler", "get_ode_sampler", "enhance", "forward", "train")}
     model._sgmse_b200_engine = engine
     model.get_pc_sampler = types.MethodType(make_pc_sampler(engine, default_N=model.sde.N), model)
     if type(model.sde).__name__ == "OUVESDE" and not (engine.cfg.backbone == "ncsnpp_v2" and
@@ -249,13 +266,19 @@ def install(model, engine: Optional[Engine] = None, rebind_forward=True, refresh
         model.forward = types.MethodType(forward, model)
 
     if refresh_on_eval:
-        orig_eval = model.eval
+        # ScoreModel.train(mode, no_ema=False) is the ONE place the reference swaps EMA weights in and out
+        # (model.py:111-122); ScoreModel.eval() delegates to it (:124-125), and so does everything that never calls
+        # ScoreModel.eval: Lightning's on_validation_model_eval() calls trainer.model.eval() on the DDP wrapper
+        # (train.py:104, strategy="ddp"), i.e. nn.Module.eval(wrapper) -> child.train(False).  Hooking the instance's
+        # `train` covers both routes (`self.train` inside ScoreModel.eval resolves to the instance attribute).
+        orig_train = model.train
 
-        def eval_and_refresh(self, *a, **k):
-            res = orig_eval(*a, **k)                  # EMA store + copy_to (model.py:111-122)
-            refresh(self)
+        def train_and_refresh(self, mode=True, *a, **k):
+            res = orig_train(mode, *a, **k)           # EMA store + copy_to when mode is False (model.py:113-117)
+            if not mode:
+                refresh(self)
             return res
-        model.eval = types.MethodType(eval_and_refresh, model)
+        model.train = types.MethodType(train_and_refresh, model)
 
     def get_sb_sampler(self, sde, y, sampler_type="ode", N=None, **kwargs):
         # model.py:392-397 + sampling/__init__.py:145 (eps=1e-4, n_steps=50 defaults)

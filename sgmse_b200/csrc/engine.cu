@@ -1084,8 +1084,11 @@ void pc_sample(Engine& e, const float2* y, int B, int F, int T, const sgmse_b200
       CUDA_OK(cudaStreamSynchronize(st));
       CUDA_OK(cudaMemcpyAsync(le.stft_buf[3], y + (b0 + lb[i]) * px1, ln[i] * px1 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
     }
+    // generations of ALL existing lanes, not of the first L: calls that alternate between L = 1 and L = 2 (bucket
+    // remainders of the batched service, the last micro-batch of B % max_batch == 1) would otherwise see a different
+    // sum every time and throw every captured graph away
     long long gen = 0;
-    for (int i = 0; i < L; ++i) gen += e.lanes[i]->generation;
+    for (size_t i = 0; i < e.lanes.size(); ++i) gen += e.lanes[i]->generation;
     if (gen != e.lanes_generation_seen) {          // some lane re-allocated a buffer a captured graph points to
       for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec);
       e.graphs.clear();

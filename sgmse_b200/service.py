@@ -7,7 +7,9 @@ launch sequence: this module buckets clips by padded frames, runs the per-clip f
 the clip's own length and peak), stacks the padded spectrograms of a bucket into batches for ``sgmse_b200_pc_sample``
 (PC or Schroedinger-bridge kind) and runs the per-clip back end (``sgmse_b200_synthesis``).  Every clip's result is
 bit-identical to enhancing it alone with the same ``(seed, utterance id)``; the ids are assigned in processing order
-and returned.
+and returned.  The one sampler this cannot hold for is ``corrector='langevin'``, whose step size is a batch mean
+(correctors.py:50-52: the clips of a batch are coupled): with it every clip is sampled as a batch of its own, which
+is what the reference's file loop does.
 
 Resampling and file I/O stay outside the engine (enhancement.py:66-71,100-103): pass callables.
 """
@@ -80,7 +82,9 @@ class BatchedEnhancer:
                     raise ValueError(f"clips are at {sr} Hz, the model at {target_sr} Hz: pass resample=")
                 w = torch.as_tensor(resample(w, sr, target_sr), dtype=torch.float32).reshape(-1)
             clips.append(w)
-        plan = plan_batches([int(w.numel()) for w in clips], eng.padded_frames, self.max_batch)
+        # corrector 'langevin' couples the clips of a batch (correctors.py:50-52) -> batches of one clip, as enhancement.py runs them
+        max_batch = 1 if sampler_kw.get("corrector", "ald") == "langevin" else self.max_batch
+        plan = plan_batches([int(w.numel()) for w in clips], eng.padded_frames, max_batch)
         outs: List[Optional[torch.Tensor]] = [None] * len(clips)
         for tp, idx in plan.batches:
             specs, norms = [], []

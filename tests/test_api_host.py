@@ -163,3 +163,65 @@ def test_installing_twice_starts_from_the_models_own_methods():
     sgmse_b200.uninstall(m)
     assert not any(k in m.__dict__ for k in ("get_pc_sampler", "get_ode_sampler", "get_sb_sampler", "enhance", "_sgmse_b200_engine"))
     sgmse_b200.uninstall(m)                              # idempotent
+
+
+def test_refresh_hooks_the_ema_swap_in_train_not_only_eval():
+    """ScoreModel.train(mode, no_ema) is where the reference swaps EMA weights (model.py:111-122).  Lightning + DDP never
+    call ScoreModel.eval(): on_validation_model_eval() runs nn.Module.eval() on the wrapper, which recurses as
+    child.train(False).  The refresh must fire on that route, on model.eval() (which delegates to train, model.py:124-125)
+    and on model.train(False) -- and not on model.train(True)."""
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dnn = torch.nn.Linear(2, 2)
+            self.sde = OUVESDE()
+            self.swaps = []
+
+        def train(self, mode=True, no_ema=False):
+            res = super().train(mode)
+            self.swaps.append(bool(mode))
+            return res
+
+        def eval(self, no_ema=False):
+            return self.train(False, no_ema=no_ema)
+
+    eng = FakeEngine()
+    loads = []
+    eng.load_state_dict = lambda sd, on_device=False: loads.append(sorted(sd))
+    m = M()
+    sgmse_b200.install(m, engine=eng, rebind_forward=False, refresh_on_eval=True)
+    wrapper = torch.nn.Sequential(m)                 # stands for DistributedDataParallel(model)
+    torch.nn.Module.eval(wrapper)                    # what Lightning's on_validation_model_eval does
+    assert len(loads) == 1 and m.swaps[-1] is False
+    wrapper.train()                                  # back to training: no refresh
+    assert len(loads) == 1 and m.swaps[-1] is True
+    m.eval()
+    assert len(loads) == 2
+    m.train(False)
+    assert len(loads) == 3
+    sgmse_b200.uninstall(m)
+    m.eval()
+    assert len(loads) == 3 and "train" not in m.__dict__
+
+
+def test_enhance_forwards_sampler_kwargs_and_refuses_what_it_cannot_honour():
+    """The reference forwards enhance(**kwargs) into get_pc_sampler (model.py:443-445): denoise / probability_flow take
+    effect there, so they must here; eps other than t_eps and unknown keywords raise instead of being dropped."""
+    wav = 0.5 * torch.ones(1, 1000)
+    eng = FakeEngine()
+    m = make_model(OUVESDE("pc"))
+    sgmse_b200.install(m, engine=eng, rebind_forward=False)
+    m.enhance(wav, denoise=False, probability_flow=True, seed=2)
+    kw = eng.calls[-1][2]
+    assert kw["denoise"] is False and kw["probability_flow"] is True
+    m.enhance(wav, seed=2)
+    kw = eng.calls[-1][2]
+    assert kw["denoise"] is True and kw["probability_flow"] is False
+    m.enhance(wav, eps=0.03, intermediate=False)     # what the reference itself passes (model.py:444)
+    with pytest.raises(NotImplementedError, match="eps"):
+        m.enhance(wav, eps=0.05)
+    with pytest.raises(NotImplementedError, match="bogus_kw"):
+        m.enhance(wav, bogus_kw=1)
+    with pytest.raises(NotImplementedError, match="intermediate"):
+        m.enhance(wav, intermediate=True)
+    sgmse_b200.uninstall(m)

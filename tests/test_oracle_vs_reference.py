@@ -160,10 +160,14 @@ def test_install_for_in_training_evaluation(model16k):
         model16k.train(True)                                                         # ScoreModel.train(mode, no_ema=False), model.py:98-109
         model16k.eval(no_ema=True)
         assert len(loads) == 2
+        # Lightning + DDP never call ScoreModel.eval(): nn.Module.eval(wrapper) -> child.train(False)
+        model16k.train(True)
+        torch.nn.Module.eval(torch.nn.Sequential(model16k))
+        assert len(loads) == 3
     finally:
         sgmse_b200.uninstall(model16k)
         model16k.eval()
-    assert "eval" not in model16k.__dict__ and "enhance" not in model16k.__dict__
+    assert "train" not in model16k.__dict__ and "eval" not in model16k.__dict__ and "enhance" not in model16k.__dict__
     eng.close()
 
 
@@ -208,3 +212,19 @@ def test_ode_oracle_matches_reference_live():
                                 prior_noise=draws[0])
     assert nfe == nfe_ref
     assert ((ref - got).abs().max() / ref.abs().max()).item() < 1e-6
+
+
+def test_staged_reference_is_unmodified():
+    """oracle/_ref/ (what the GPU box and bench.py's reference arm import) is a byte-for-byte copy of /root/reference:
+    every staged file matches its manifest hash, and where the live checkout is present, the live file."""
+    import os
+    from oracle import build_ref
+    if not os.path.isdir("/root/reference/sgmse"):
+        pytest.skip("live checkout not present")
+    dst = build_ref.build()
+    assert dst and build_ref.staged() and build_ref.verify() == []
+    import json
+    man = json.load(open(os.path.join(dst, "MANIFEST.json")))
+    assert "sgmse/model.py" in man["files"] and "enhancement.py" in man["files"] and len(man["files"]) >= 25
+    for rel in man["files"]:
+        assert open(os.path.join(dst, rel), "rb").read() == open(os.path.join("/root/reference", rel), "rb").read(), rel

@@ -78,3 +78,16 @@ def test_pad_mode_and_resampling_follow_enhancement_py():
         enh([torch.ones(16000)], sr=16000)
     outs, _ = enh([torch.ones(16000)], sr=16000, resample=lambda w, a, b: w.repeat_interleave(b // a))
     assert outs[0].numel() == 48000 and eng.calls[0] == ("analysis", (1, 48000), "reflection")
+
+
+def test_langevin_corrector_is_sampled_clip_by_clip():
+    """correctors.py:50-52: the Langevin step size is a batch mean, so clips sharing a batch are coupled; the reference's file
+    loop (enhancement.py:58-103) never batches.  The service keeps that: one clip per sampler call, ids still contiguous."""
+    eng = FakeEngine(max_batch=4)
+    waves = [torch.full((8000,), 0.5), torch.full((8100,), 0.1), torch.full((7000,), 0.2)]
+    outs, ids = BatchedEnhancer(eng, device="cpu")(waves, seed=1, corrector="langevin")
+    pcs = [c for c in eng.calls if c[0] == "pc_sample"]
+    assert [c[1][0] for c in pcs] == [1, 1, 1] and [c[3] for c in pcs] == [0, 1, 2] and ids == [0, 1, 2]
+    eng.calls.clear()
+    BatchedEnhancer(eng, device="cpu")(waves, seed=1, corrector="ald")
+    assert [c[1][0] for c in eng.calls if c[0] == "pc_sample"] == [3]
