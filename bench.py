@@ -5,7 +5,7 @@ clips, N=30 predictor-corrector steps = 60 score-network evaluations per utteran
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
+    python bench.py --impl reference ...      # the reference's own enhancement.py path on the host CPU cores (oracle/_ref)
 
 A "step" is one pass of the hot path over one batch of synthetic noisy speech: STFT -> magnitude
 compression -> pad -> N-step PC sampling with the NCSN++ score network -> decompression -> iSTFT.
@@ -105,86 +105,143 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port) on the host cores, bounded sample
+# CPU arm: the reference's OWN enhancement.py path on the host cores (oracle/_ref = the unmodified reference package,
+# staged by oracle/build_ref.py; falls back to the oracle port, loudly, where it is not staged), bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(state):
-    """One bounded sample: 1 utterance, STFT -> 1 of the N=30 PC steps (2 of 60 network evaluations) -> iSTFT.
-    Returns seconds; utterances/s is extrapolated by scaling the sampler part to 30 steps."""
-    import torch
-    from oracle import pipeline as o_pipe, sde as o_sde, spec as o_spec
-    sd, ncfg, wav, draws = state
-    t0 = time.perf_counter()
-    o_pipe.enhance(sd, ncfg, o_spec.SpecConfig(), o_sde.OUVE(), wav, draws, N=1)
-    return time.perf_counter() - t0
+_CPU = {"threads": None, "sweep": None, "forward_s": None, "source": None}
 
 
-_CPU_THREADS = None
-
-
-def pick_cpu_threads(sd, ncfg):
-    """Use as many host threads as actually help: a quarter-second probe (one forward on a [1,2,256,64] input)
-    per candidate, best wins (oversubscribed MKL-DNN convolutions get slower, not faster)."""
-    global _CPU_THREADS
-    if _CPU_THREADS is not None:
-        return _CPU_THREADS
-    import torch
-    from oracle import ncsnpp as o_net
+def _thread_candidates():
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cands = sorted({c for c in (avail, avail // 2, 64, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
-    x = torch.complex(torch.randn(1, 2, 256, 64), torch.randn(1, 2, 256, 64))
-    t = torch.tensor([0.5])
-    best = (float("inf"), avail)
-    for c in cands:
+    import torch
+    cands = {avail, avail // 2, avail // 4, 32, 16, torch.get_num_threads()}
+    return sorted((c for c in cands if 1 <= c <= avail), reverse=True)
+
+
+def pick_cpu_threads(forward):
+    """Thread sweep on the FULL shape of the workload: one warm + one timed score-network evaluation on a
+    [1, 2, 256, 512] input per candidate count; the fastest wins (oversubscribed MKL-DNN convolutions get slower, not
+    faster).  The table goes into the JSON line (`cpu_baseline.thread_sweep`)."""
+    if _CPU["threads"] is not None:
+        return _CPU["threads"]
+    import torch
+    sweep, best = {}, (float("inf"), 1)
+    for c in _thread_candidates():
         torch.set_num_threads(c)
-        with torch.no_grad():
-            o_net.forward(sd, ncfg, x, t)
-            t0 = time.perf_counter()
-            o_net.forward(sd, ncfg, x, t)
-            dt = time.perf_counter() - t0
+        forward()
+        t0 = time.perf_counter()
+        forward()
+        dt = time.perf_counter() - t0
+        sweep[str(c)] = round(dt, 3)
         if dt < best[0]:
             best = (dt, c)
-    _CPU_THREADS = best[1]
-    torch.set_num_threads(_CPU_THREADS)
-    return _CPU_THREADS
+    _CPU.update(threads=best[1], sweep=sweep, forward_s=best[0])
+    torch.set_num_threads(best[1])
+    return best[1]
 
 
 def cpu_state():
+    """(kind, step_fn): step_fn(n_pc_steps) runs ONE utterance through the enhancement.py:75-96 sequence with an
+    n-step PC sampler and returns (seconds total, seconds outside the sampler)."""
     import torch
-    from oracle import weights as o_w, sde as o_sde
-    from oracle.arch import NetConfig
-    ncfg = NetConfig.ncsnpp()
-    sd = o_w.make_state_dict(ncfg, seed=0)
-    pick_cpu_threads(sd, ncfg)
+    from oracle import refshim
     from sgmse_b200.synth import synthetic_speech
     wav = synthetic_speech(1, SR * CLIP_S)
-    draws = o_sde.make_noise((1, 1, 256, 512), 3, seed=2000)
-    return sd, ncfg, wav, draws
+    if refshim.reference_available():
+        # BASELINE.md section 3: the reference's own modules, random init (init_scale=1.0), eval(), device='cpu'
+        model = refshim.make_score_model("ncsnpp", seed=0)
+        from sgmse.util.other import pad_spec
+        xprobe = torch.complex(torch.randn(1, 2, 256, 512), torch.randn(1, 2, 256, 512))
+        tprobe = torch.tensor([0.5])
+
+        def forward():
+            with torch.no_grad():
+                model.dnn(xprobe, tprobe)
+
+        def step(n):
+            t0 = time.perf_counter()
+            y = wav.clone()
+            T_orig = y.size(1)                                   # enhancement.py:68
+            norm_factor = y.abs().max()                          # :71-72
+            y = y / norm_factor
+            Y = torch.unsqueeze(model._forward_transform(model._stft(y.to("cpu"))), 0)     # :75
+            Y = pad_spec(Y, mode="zero_pad")                     # :76
+            sampler = model.get_pc_sampler("reverse_diffusion", "ald", Y.to("cpu"), N=n, corrector_steps=1, snr=0.5)   # :81-82
+            t1 = time.perf_counter()
+            sample, _ = sampler()                                # :93
+            t2 = time.perf_counter()
+            x_hat = model.to_audio(sample.squeeze(), T_orig)     # :96
+            x_hat = x_hat * norm_factor                          # :99
+            x_hat.cpu().numpy()
+            t3 = time.perf_counter()
+            return t3 - t0, (t1 - t0) + (t3 - t2)
+        kind = "reference"
+        _CPU["source"] = refshim.reference_kind() + ": " + refshim.REFERENCE_ROOT     # 'staged: .../oracle/_ref' on the GPU box
+    else:
+        print("bench.py: oracle/_ref is not staged (run __graft_entry__.build() where /root/reference exists): "
+              "the CPU arm falls back to the oracle PORT", file=sys.stderr)
+        from oracle import weights as o_w, sde as o_sde, spec as o_spec, pipeline as o_pipe, ncsnpp as o_net
+        from oracle.arch import NetConfig
+        ncfg = NetConfig.ncsnpp()
+        sd = o_w.make_state_dict(ncfg, seed=0)
+        xprobe = torch.complex(torch.randn(1, 2, 256, 512), torch.randn(1, 2, 256, 512))
+        tprobe = torch.tensor([0.5])
+
+        def forward():
+            with torch.no_grad():
+                o_net.forward(sd, ncfg, xprobe, tprobe)
+
+        def step(n):
+            draws = o_sde.make_noise((1, 1, 256, 512), 1 + 2 * n, seed=2000)
+            t0 = time.perf_counter()
+            o_pipe.enhance(sd, ncfg, o_spec.SpecConfig(), o_sde.OUVE(), wav, draws, N=n)
+            return time.perf_counter() - t0, 0.0
+        kind = "port"
+    pick_cpu_threads(forward)
+    return kind, step
 
 
-def cpu_baseline(n_steps_total=30, reps=1):
-    st = cpu_state()
-    ts = [cpu_reference_step(st) for _ in range(reps)]
-    t = min(ts)
-    return {"value": 1.0 / (t * n_steps_total), "unit": "utterances/s", "cores": _CPU_THREADS, "host_cpus": os.cpu_count(), "kind": "port",
-            "sample": f"1 utterance (4 s, 16 kHz), STFT + 1 of {n_steps_total} PC steps (2 of {2 * n_steps_total} NCSN++ "
-                      f"evaluations) + iSTFT on the fp32 torch-CPU oracle port, {t:.1f} s; utterances/s extrapolated x{n_steps_total}"}
+def _cpu_line(kind, n_sample, N, ts):
+    """ts = [(total seconds, seconds outside the sampler)] of the timed samples."""
+    t = sum(a for a, _ in ts) / len(ts)
+    tout = sum(b for _, b in ts) / len(ts)
+    per_utt = tout + (t - tout) * N / n_sample                  # only the sampler part scales with the number of PC steps
+    what = ("the unmodified reference (oracle/_ref: sgmse.model.ScoreModel, enhancement.py:75-96 sequence, device='cpu')"
+            if kind == "reference" else "the fp32 torch-CPU oracle PORT (oracle/_ref not staged)")
+    return {"value": 1.0 / per_utt, "unit": "utterances/s", "cores": _CPU["threads"], "host_cpus": os.cpu_count(), "kind": kind,
+            "sample": f"1 utterance (4 s, 16 kHz) through {what}: STFT + {n_sample} of {N} PC steps ({2 * n_sample} of {2 * N} "
+                      f"NCSN++ evaluations) + iSTFT, {t:.1f} s measured per sample ({tout:.2f} s of it outside the sampler); "
+                      f"utterances/s = 1 / (outside + sampler x {N}/{n_sample})",
+            "reference_source": _CPU.get("source"), "sample_s": round(t, 3), "extrapolated_s_per_utterance": round(per_utt, 2),
+            "thread_sweep_s_per_forward": _CPU["sweep"]}, t
+
+
+def cpu_baseline(n_steps_total=30, n_sample=2):
+    kind, step = cpu_state()
+    ts = [step(n_sample)]
+    return _cpu_line(kind, n_sample, n_steps_total, ts)[0]
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    st = cpu_state()
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_step(st)
-    ts = [cpu_reference_step(st) for _ in range(args.steps)]
-    t = sum(ts) / len(ts)
-    v = 1.0 / (t * args.N)
-    cb = {"value": v, "unit": "utterances/s", "cores": _CPU_THREADS, "host_cpus": os.cpu_count(), "kind": "port",
-          "sample": f"per step: 1 utterance, STFT + 1 of {args.N} PC steps + iSTFT; extrapolated x{args.N}"}
+    kind, step = cpu_state()
+    # bounded sample per step: as many real PC steps as fit ~4 minutes for the whole --steps/--warmup run
+    n_warm = max(0, min(args.warmup, 1))
+    per_pc_step = 2 * _CPU["forward_s"]
+    n_sample = int(max(1, min(args.N, 240.0 / ((args.steps + n_warm) * per_pc_step))))
+    for _ in range(n_warm):
+        step(n_sample)
+    ts = [step(n_sample) for _ in range(args.steps)]
+    cb, t = _cpu_line(kind, n_sample, args.N, ts)
+    v = cb["value"]
     print(json.dumps({
         "impl": "reference", "metric": "utterances/sec (4 s, 16 kHz, N=30 PC)", "value": v, "unit": "utterances/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * args.N,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        # the MEASURED time of one step (= one bounded sample), so that steps x ms_per_step is the real timed region;
+        # the whole-utterance figure behind `value` is cpu_baseline.extrapolated_s_per_utterance
+        "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args), "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))

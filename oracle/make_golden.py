@@ -240,6 +240,52 @@ def golden_ode_v2(name="ode_v2_small"):
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), y=_np(y), prior_seed=np.int64(19), tol=np.float64(1e-3), **out)
 
 
+MID = dict(nf=64, ch_mult=(1, 2, 2), image_size=64, attn_resolutions=(16,), num_res_blocks=1)
+
+
+def golden_mid_tc(name="ncsnpp_mid"):
+    """Reference-generated sampler / enhancement fixtures on a config whose layers are tcgen05-tileable (64..128 channels),
+    so that the PRODUCT mode (fp16_tc) -- not only the fp32 validation mode -- is compared with outputs of the unmodified
+    reference.  Like full_n30: weights (oracle/weights.py seed 5, loaded into the reference model),
+    inputs and noise are regenerated from seeds on the GPU box; only the reference's OUTPUTS are stored.
+    Sampler: the four predictor/corrector pairs at N = 3, the default pair also at N = 12 (24 evaluations: drift over a
+    longer chain); chain: enhancement.py:75-96 at N = 6 on two clips."""
+    from . import weights as o_w
+    cfg = NetConfig.ncsnpp(**MID)
+    model = refshim.make_score_model("ncsnpp", seed=0, n_fft=126, hop_length=32, **MID)
+    from sgmse.util.other import pad_spec
+    model.dnn.load_state_dict(o_w.make_state_dict(cfg, seed=5))
+    g = torch.Generator().manual_seed(105)
+    B, F, T = 2, 64, 128
+    y = torch.complex(torch.randn(B, 1, F, T, generator=g), torch.randn(B, 1, F, T, generator=g)) * 0.3
+    x = y + 0.2 * torch.complex(torch.randn(B, 1, F, T, generator=g), torch.randn(B, 1, F, T, generator=g))
+    t = torch.tensor([0.83, 0.11])
+    out = {}
+    with torch.no_grad():
+        out["score"] = _np(model(x, y, t))
+    for pred, corr, N in [("reverse_diffusion", "ald", 3), ("reverse_diffusion", "langevin", 3), ("none", "ald", 3),
+                          ("reverse_diffusion", "none", 3), ("reverse_diffusion", "ald", 12)]:
+        draws = sde_mod.make_noise((B, 1, F, T), sde_mod.n_noise_draws(N, pred, corr, 1), seed=7)
+        with refshim.injected_noise(draws):
+            smp, nfe = model.get_pc_sampler(pred, corr, y, N=N, corrector_steps=1, snr=0.5)()
+        out[f"pc_{pred}_{corr}_N{N}"] = _np(smp)
+        out[f"nfe_{pred}_{corr}_N{N}"] = np.int64(nfe)
+    L, N = 4000, 6
+    wav = 0.1 * torch.randn(B, L, generator=g)
+    enh = []
+    for b in range(B):
+        yb = wav[b:b + 1]
+        norm = yb.abs().max()
+        Y = pad_spec(torch.unsqueeze(model._forward_transform(model._stft(yb / norm)), 0))
+        draws = [d[b:b + 1] for d in sde_mod.make_noise((B, 1, F, Y.shape[-1]), sde_mod.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=11)]
+        with refshim.injected_noise(draws):
+            smp, _ = model.get_pc_sampler("reverse_diffusion", "ald", Y, N=N, corrector_steps=1, snr=0.5)()
+        enh.append(_np(model.to_audio(smp.squeeze(), L) * norm))
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), x=_np(x), y=_np(y), t=_np(t), wav=_np(wav), enh=np.stack(enh),
+                        weight_seed=np.int64(5), input_seed=np.int64(105), **out)
+    print(name, "params", sum(v.numel() for v in model.dnn.state_dict().values()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     golden_ops()
@@ -249,6 +295,7 @@ def main():
     golden_ode("ode_small", "ncsnpp_small", "ncsnpp", NetConfig.ncsnpp(attn_resolutions=(16,), **SMALL), seed=1)
     golden_ode("ode48k_small", "ncsnpp48k_small", "ncsnpp_48k", NetConfig.ncsnpp_48k(**SMALL), seed=2)
     golden_ode_v2()
+    golden_mid_tc()
     golden_full_n30()            # ~2.5 minutes: the full-size reference run
 
 

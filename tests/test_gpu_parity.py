@@ -390,3 +390,45 @@ def test_full_size_sampler_properties(full_sd):
     assert not torch.equal(a, e)
     assert eng.counter("graph_launches") >= 2
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# the PRODUCT mode (fp16_tc) against reference-generated fixtures (tests/golden/ncsnpp_mid.npz, oracle/make_golden.py:
+# golden_mid_tc: outputs of the unmodified reference on a tcgen05-tileable config; weights / inputs / noise from seeds)
+# ------------------------------------------------------------------------------------------------
+MID_PAIRS = [("reverse_diffusion", "ald", 3), ("reverse_diffusion", "langevin", 3), ("none", "ald", 3),
+             ("reverse_diffusion", "none", 3), ("reverse_diffusion", "ald", 12)]
+# measured on a B200 (profiles/r02_parity.txt), bounds <= 2x the measured error of the worst pair
+MID_TOL = {"fp32": dict(score=2e-4, pc=1e-3, enh=2e-3), "fp16_tc": dict(score=2e-2, pc=2e-2, enh=2e-2)}
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16_tc"])
+def test_golden_mid_sampler_and_chain(golden_dir, mode):
+    z = np.load(os.path.join(golden_dir, "ncsnpp_mid.npz"))
+    sd = o_w.make_state_dict(MID_N, seed=int(z["weight_seed"]))
+    eng = Engine(EngineConfig(mode=mode, max_batch=2, **MID_E))
+    eng.load_state_dict(sd)
+    x, y, t = (torch.from_numpy(z[k]).cuda() for k in ("x", "y", "t"))
+    tol = MID_TOL[mode]
+    e_score = rel_l2(eng.score(x, y, t), z["score"])
+    if mode == "fp16_tc":
+        assert eng.counter("tc_convs_last_forward") > 0
+    report = [f"score {e_score:.3e}"]
+    assert e_score < tol["score"]
+    for pred, corr, N in MID_PAIRS:
+        draws = o_sde.make_noise(tuple(y.shape), o_sde.n_noise_draws(N, pred, corr, 1), seed=7)
+        smp, nfe = eng.pc_sample(y, noise=torch.stack(draws).cuda(), N=N, predictor=pred, corrector=corr, corrector_steps=1, snr=0.5)
+        assert nfe == int(z[f"nfe_{pred}_{corr}_N{N}"])
+        e = rel_l2(smp, z[f"pc_{pred}_{corr}_N{N}"])
+        report.append(f"{pred}+{corr} N={N} {e:.3e}")
+        assert e < tol["pc"], report
+    wav = torch.from_numpy(z["wav"])
+    draws = o_sde.make_noise((2, 1, 64, 128), o_sde.n_noise_draws(6, "reverse_diffusion", "ald", 1), seed=11)
+    xh = eng.enhance(wav.cuda(), noise=torch.stack(draws).cuda(), N=6).cpu()
+    ref = torch.from_numpy(z["enh"]).reshape(xh.shape)
+    e_enh = rel_l2(xh, ref)
+    sdr = min(o_pipe.si_sdr(ref[b].numpy(), xh[b].numpy()) for b in range(2))
+    report.append(f"enhance chain N=6 {e_enh:.3e} (SI-SDR {sdr:.1f} dB)")
+    print(f"mid-size reference fixture, {mode}: " + "; ".join(report))
+    assert e_enh < tol["enh"]
+    eng.close()

@@ -228,3 +228,30 @@ def test_ode_sampler_on_v2_score_models(golden_dir, tag):
                             rtol=tol, atol=tol, prior_noise=prior)
     assert nfe == int(z[f"nfe_{tag}"])
     assert _rel(x, z[f"x_{tag}"]) < 1e-5
+
+
+MID = dict(nf=64, ch_mult=(1, 2, 2), image_size=64, attn_resolutions=(16,), num_res_blocks=1)
+MID_PAIRS = [("reverse_diffusion", "ald", 3), ("reverse_diffusion", "langevin", 3), ("none", "ald", 3),
+             ("reverse_diffusion", "none", 3), ("reverse_diffusion", "ald", 12)]
+
+
+def test_mid_size_fixture_is_reproduced_by_the_oracle(golden_dir):
+    """tests/golden/ncsnpp_mid.npz (oracle/make_golden.py: golden_mid_tc): reference outputs on the tcgen05-tileable
+    mid-size config, weights from oracle/weights.py seed 5 -- the pin of the product-mode GPU tests."""
+    from oracle import weights as o_w
+    z = np.load(os.path.join(golden_dir, "ncsnpp_mid.npz"))
+    cfg = NetConfig.ncsnpp(**MID)
+    sd = o_w.make_state_dict(cfg, seed=int(z["weight_seed"]))
+    x, y, t = (torch.from_numpy(z[k]) for k in ("x", "y", "t"))
+    with torch.no_grad():
+        assert _rel(ncsnpp.score(sd, cfg, x, y, t), z["score"]) < 1e-5
+        for pred, corr, N in MID_PAIRS:
+            draws = sde_mod.make_noise(tuple(y.shape), sde_mod.n_noise_draws(N, pred, corr, 1), seed=7)
+            smp, nfe = sde_mod.pc_sample(lambda a, b, c: ncsnpp.score(sd, cfg, a, b, c), y, sde_mod.OUVE(), N=N,
+                                         predictor=pred, corrector=corr, corrector_steps=1, snr=0.5, noise=draws)
+            assert nfe == int(z[f"nfe_{pred}_{corr}_N{N}"])
+            assert _rel(smp, z[f"pc_{pred}_{corr}_N{N}"]) < 5e-4, (pred, corr, N)
+    wav = torch.from_numpy(z["wav"])
+    draws = sde_mod.make_noise((2, 1, 64, 128), sde_mod.n_noise_draws(6, "reverse_diffusion", "ald", 1), seed=11)
+    xh = pipeline.enhance(sd, cfg, spec_mod.SpecConfig(n_fft=126, hop_length=32), sde_mod.OUVE(), wav, draws, N=6)
+    assert _rel(xh, z["enh"][:, 0] if z["enh"].ndim == 3 else z["enh"]) < 1e-3
