@@ -198,7 +198,11 @@ int sgmse_b200_analysis(sgmse_b200_engine* e, const float* wav, int B, int L, in
 int sgmse_b200_synthesis(sgmse_b200_engine* e, const void* X, const float* norm, int B, int Tpad, int L, float* wav,
                          void* stream);
 /* One call: wav [B,L] -> enhanced wav [B,L].  host_buffers != 0: wav/out are host pointers (pinned memory
- * recommended); the H2D / D2H copies are part of the call and it returns after the result is in `out`. */
+ * recommended); the H2D / D2H copies are part of the call and it returns after the result is in `out`.
+ * fp16 range: in the fp16 modes a raw convolution output beyond +-65504 is stored as inf; GroupNorm's statistics pass counts
+ * every such event (counter "fp16_range_events").  With host buffers the call checks the counter before returning and FAILS
+ * (non-zero code, message in sgmse_b200_last_error, counter reset) rather than hand out a NaN waveform; device-resident
+ * callers read the counter themselves (it synchronises) and clear it with option "reset_range_events". */
 int sgmse_b200_enhance(sgmse_b200_engine* e, const float* wav, int B, int L, const sgmse_b200_sampler* s,
                        const void* noise, float* out, int host_buffers, void* stream);
 
@@ -225,7 +229,8 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
 /* counters: "kernel_launches" (since creation), "graph_launches", "cached_graphs", "workspace_bytes", "weights_bytes",
  * "tc_convs_last_forward", "direct_convs_last_forward", "launches_last_forward",
  * "timed_conv_tc_us" / "timed_conv_tc_mflop" / "timed_conv_tc_kbytes" / "timed_conv_tc_count" /
- * "timed_conv_direct_us" (sums over the launches timed since "time_convs" was switched on), "pdl_compiled", "pdl" */
+ * "timed_conv_direct_us" (sums over the launches timed since "time_convs" was switched on), "pdl_compiled", "pdl",
+ * "fp16_range_events" (see sgmse_b200_enhance; synchronises the device) */
 long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key);
 
 #ifdef __cplusplus

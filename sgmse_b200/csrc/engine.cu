@@ -258,6 +258,10 @@ void free_weights(Engine& e) {
 
 void load_weights(Engine& e, const float* blob) {
   free_weights(e);
+  if (!e.range_flag) {                        // fp16 range detector word (gn.cu), shared with the lanes created later
+    CUDA_OK(cudaMalloc((void**)&e.range_flag, sizeof(unsigned int)));
+    CUDA_OK(cudaMemset(e.range_flag, 0, sizeof(unsigned int)));
+  }
   const sgmse_b200_config& c = e.cfg;
   CUDA_OK(cudaMalloc(&e.blob_dev, (size_t)e.weights_numel * 4));
   CUDA_OK(cudaMemcpy(e.blob_dev, blob, (size_t)e.weights_numel * 4, cudaMemcpyHostToDevice));
@@ -410,7 +414,7 @@ struct Fwd {
     const int groups = gn_groups(Ct);
     uint4* ab16 = (Ct / groups) % 2 == 0 ? (uint4*)(ab + (size_t)x0.N * Ct) : nullptr;
     if (plain_consumer && gn_self_applies(x0, x1)) return ab;
-    if (!dry) { launch_gn_finalize(st, x0, x1, e.blob_dev + g_off, e.blob_dev + b_off, groups, ab, ab16); count(); }
+    if (!dry) { launch_gn_finalize(st, x0, x1, e.blob_dev + g_off, e.blob_dev + b_off, groups, ab, ab16, e.range_flag); count(); }
     return ab;
   }
   // y = [silu](a x + b) without resampling: gn_apply_plain on the finalized table, or (gn_self) finalize + apply in one kernel
@@ -418,7 +422,7 @@ struct Fwd {
                    TensorDesc& out) {
     if (dry) return;
     if (gn_self_applies(x0, x1))
-      launch_gn_norm_apply(st, x0, x1, e.blob_dev + g_off, e.blob_dev + b_off, gn_groups(x0.C + (x1 ? x1->C : 0)), silu, out);
+      launch_gn_norm_apply(st, x0, x1, e.blob_dev + g_off, e.blob_dev + b_off, gn_groups(x0.C + (x1 ? x1->C : 0)), silu, out, e.range_flag);
     else
       launch_gn_apply(st, x0, x1, ab, silu, RS_NONE, out, nullptr);
     count();
@@ -1424,6 +1428,20 @@ void synthesis(Engine& e, const float2* X, const float* norm, int B, int Tpad, i
   e.kernel_launches += 3;
 }
 
+// Host-buffer entry points end with a stream synchronisation anyway: read the fp16 range detector with it and refuse to hand
+// out a waveform that went through an overflowed (inf -> NaN) activation.  fp32 mode cannot trip it below 3.4e38.
+void check_range(Engine& e, cudaStream_t st) {
+  unsigned int v = 0;
+  if (!e.range_flag) { CUDA_OK(cudaStreamSynchronize(st)); return; }
+  CUDA_OK(cudaMemcpyAsync(&v, e.range_flag, sizeof(v), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (v) {
+    CUDA_OK(cudaMemsetAsync(e.range_flag, 0, sizeof(unsigned int), st));
+    SG_CHECK(false, "fp16 activation range exceeded: %u GroupNorm input group(s) held values beyond +-65504 (stored as inf); "
+                    "the result is not usable -- run this model in mode fp32", v);
+  }
+}
+
 void enhance(Engine& e, const float* wav, int B, int L, const sgmse_b200_sampler& s, const float2* noise, float* out,
              bool host, cudaStream_t st) {
   const int Tpad = padded_frames(e, L), F = e.cfg.n_fft / 2 + 1;
@@ -1447,7 +1465,7 @@ void enhance(Engine& e, const float* wav, int B, int L, const sgmse_b200_sampler
   synthesis(e, X, norm, B, Tpad, L, odst, st);
   if (host) {
     CUDA_OK(cudaMemcpyAsync(out, out_d, (size_t)B * L * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    check_range(e, st);                          // synchronises; device-resident callers poll counter "fp16_range_events"
   }
 }
 
@@ -1478,7 +1496,7 @@ void enhance_ode(Engine& e, const float* wav, int B, int L, const sgmse_b200_ode
   synthesis(e, X, norm, B, Tpad, L, odst, st);
   if (host) {
     CUDA_OK(cudaMemcpyAsync(out, out_d, (size_t)B * L * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    check_range(e, st);
   }
 }
 
@@ -1508,7 +1526,7 @@ int sgmse_b200_create(const sgmse_b200_config* cfg, sgmse_b200_engine** out) {
   if (e->cfg.max_batch <= 0) e->cfg.max_batch = 8;
   if (const char* v = getenv("SGMSE_B200_TC_VARIANT")) sgmse::g_tc_variant = atoi(v);   // A/B switch for profiling
   SG_CHECK(cfg->mode >= 0 && cfg->mode <= 2, "unknown mode %d", cfg->mode);
-  build_network(*e);
+  build_network(*e);                          // host only: no CUDA call before the first weights arrive
   *out = e.release();
   API_END
 }
@@ -1519,6 +1537,7 @@ void sgmse_b200_destroy(sgmse_b200_engine* e) {
   try { if (e->lanes.size() > 1) ensure_lanes(*e, 1); } catch (...) {}
   for (cudaEvent_t ev : e->lane_events) cudaEventDestroy(ev);
   try { free_weights(*e); free_workspace(*e); } catch (...) {}   // a dead context must not terminate the host process
+  cudaFree(e->range_flag);
   delete e;
 }
 
@@ -1779,6 +1798,9 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
     e->time_convs = value != 0;
   }
   else if (k == "use_graphs") e->cfg.use_graphs = value != 0;
+  else if (k == "reset_range_events") {
+    if (e->range_flag) { CUDA_OK(cudaDeviceSynchronize()); CUDA_OK(cudaMemset(e->range_flag, 0, sizeof(unsigned int))); }
+  }
   else if (k == "tc_variant") {
     // changes which intermediate buffers a forward needs: drop cached workspace sizes, graphs and shadow lanes
     sgmse::g_tc_variant = (int)value;
@@ -1790,6 +1812,7 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "tc6_rings") { sgmse::g_tc6_rings = (int)value; clear_graphs(*e); }
   else if (k == "tc6_mma") { sgmse::g_tc6_mma_style = (int)value; clear_graphs(*e); }
   else if (k == "tc6_tma_poll") { sgmse::g_tc6_tma_poll = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_roles") { sgmse::g_tc6_roles = (int)value; clear_graphs(*e); }
   else if (k == "fir_variant") { sgmse::g_fir_variant = (int)value; clear_graphs(*e); }
   else if (k == "inconv_variant") { sgmse::g_inconv_variant = (int)value; clear_graphs(*e); }
   else if (k == "combine_variant") { sgmse::g_combine_variant = (int)value; clear_graphs(*e); }
@@ -1846,6 +1869,12 @@ long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key) {
   if (k == "tc_convs_last_forward") return e->tc_convs;
   if (k == "direct_convs_last_forward") return e->direct_convs;
   if (k == "launches_last_forward") return e->launches_this_forward;
+  if (k == "fp16_range_events") {               // GroupNorm inputs with non-finite statistics since the last reset (synchronises)
+    unsigned int v = 0;
+    if (!e->range_flag || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(&v, e->range_flag, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (long long)v;
+  }
   if (k == "barrier_wait_code") return sgmse::g_wait_code_host ? (long long)*sgmse::g_wait_code_host : 0;   // readable after a trap
   if (k == "timed_conv_tc_us" || k == "timed_conv_tc_mflop" || k == "timed_conv_tc_count" || k == "timed_conv_tc_kbytes" ||
       k == "timed_conv_direct_us") {

@@ -137,6 +137,7 @@ struct sgmse_b200_engine {
   sgmse::RngParams* rng_dev = nullptr;
   float* lv_scratch = nullptr;
   int* dbg_flag = nullptr;
+  unsigned int* range_flag = nullptr;         // device word, shared with the lanes: fp16 overflow events seen by GroupNorm (gn.cu)
   size_t persist_px = 0;                      // capacity of state/xmean in pixels
   int persist_rows = 0;                       // capacity of temb_table in rows
 

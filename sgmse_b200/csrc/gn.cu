@@ -22,7 +22,8 @@ template <bool BATCH>
 __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int slots0,
                                    const float* __restrict__ st1, int C1, int slots1,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   int cpg, double inv_count, float2* __restrict__ ab, uint4* __restrict__ ab16) {
+                                   int cpg, double inv_count, float2* __restrict__ ab, uint4* __restrict__ ab16,
+                                   unsigned int* __restrict__ range_flag) {
   pdl_trigger(); pdl_wait();
   const int g = blockIdx.x, n = blockIdx.y;
   const int Ct = C0 + C1;
@@ -84,6 +85,9 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int sl
     if (lane == 0) { sh_s[0] = s; sh_q[0] = q; }
   }
   __syncthreads();
+  // fp16 range detector: the producers' partial sums are taken over the ROUNDED fp16 values they store, so an activation
+  // beyond +-65504 (stored as inf) makes the sums non-finite -- and every later result NaN.  Count it instead of staying silent.
+  if (range_flag && threadIdx.x == 0 && !(isfinite(sh_s[0]) && isfinite(sh_q[0]))) atomicAdd(range_flag, 1u);
   const double mean = sh_s[0] * inv_count;
   double var = sh_q[0] * inv_count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -113,7 +117,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int sl
 }
 
 void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc* s1, const float* gamma,
-                        const float* beta, int groups, float2* ab, uint4* ab16) {
+                        const float* beta, int groups, float2* ab, uint4* ab16, unsigned int* range_flag) {
   const int C1 = s1 ? s1->C : 0;
   const int Ct = s0.C + C1;
   SG_CHECK(Ct % groups == 0, "GroupNorm: %d channels not divisible by %d groups", Ct, groups);
@@ -125,12 +129,12 @@ void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc*
   dim3 grid(groups, s0.N);
   if (g_gnfin_variant == 1) {
     launch_k(gn_finalize_kernel<true>, grid, dim3(256), 0, st, s0.stats, s0.C, s0.slots, s1 ? s1->stats : nullptr, C1,
-             s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab, ab16);
+             s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab, ab16, range_flag);
     CUDA_OK(cudaGetLastError());
     return;
   }
   launch_k(gn_finalize_kernel<false>, grid, dim3(256), 0, st, s0.stats, s0.C, s0.slots, s1 ? s1->stats : nullptr, C1,
-                                           s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab, ab16);
+                                           s1 ? s1->slots : 0, gamma, beta, cpg, inv_count, ab, ab16, range_flag);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(256)
 gn_norm_apply_kernel(const T* __restrict__ x0, int C0, const float* __restrict__ st0, int slots0,
                      const T* __restrict__ x1, int C1, const float* __restrict__ st1, int slots1,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int cpg, double inv_count,
-                     int HW, int ppb, T* __restrict__ out) {
+                     int HW, int ppb, T* __restrict__ out, unsigned int* __restrict__ range_flag) {
   pdl_trigger(); pdl_wait();
   extern __shared__ float2 ab_s[];                        // [Ct]
   const int Ct = C0 + C1, groups = Ct / cpg, n = blockIdx.y;
@@ -268,6 +272,7 @@ gn_norm_apply_kernel(const T* __restrict__ x0, int C0, const float* __restrict__
       s += __shfl_xor_sync(0xffffffffu, s, o);
       q += __shfl_xor_sync(0xffffffffu, q, o);
     }
+    if (range_flag && blockIdx.x == 0 && lane == 0 && !(isfinite(s) && isfinite(q))) atomicAdd(range_flag, 1u);   // see gn_finalize
     const double mean = s * inv_count;
     double var = q * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -312,7 +317,7 @@ bool gn_self_applies(const TensorDesc& x0, const TensorDesc* x1) {
 }
 
 void launch_gn_norm_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float* gamma, const float* beta,
-                          int groups, bool silu, TensorDesc& out) {
+                          int groups, bool silu, TensorDesc& out, unsigned int* range_flag) {
   const int C1 = x1 ? x1->C : 0;
   const int Ct = x0.C + C1, cvpp = Ct / 8;
   SG_CHECK(Ct % groups == 0 && out.C == Ct && out.N == x0.N && out.H == x0.H && out.W == x0.W, "gn_norm_apply: shape mismatch");
@@ -325,7 +330,7 @@ void launch_gn_norm_apply(cudaStream_t st, const TensorDesc& x0, const TensorDes
   dim3 grid(gx, x0.N);
   const size_t smem = (size_t)Ct * sizeof(float2);
 #define GO(T, S) launch_k(gn_norm_apply_kernel<T, S>, grid, dim3(256), smem, st, (const T*)x0.p, x0.C, x0.stats, x0.slots, \
-                          x1 ? (const T*)x1->p : (const T*)nullptr, C1, x1 ? x1->stats : (const float*)nullptr, x1 ? x1->slots : 0, gamma, beta, cpg, inv_count, HW, ppb, (T*)out.p)
+                          x1 ? (const T*)x1->p : (const T*)nullptr, C1, x1 ? x1->stats : (const float*)nullptr, x1 ? x1->slots : 0, gamma, beta, cpg, inv_count, HW, ppb, (T*)out.p, range_flag)
   if (x0.dt == DT_F16) { if (silu) GO(__half, true); else GO(__half, false); }
   else { if (silu) GO(float, true); else GO(float, false); }
 #undef GO

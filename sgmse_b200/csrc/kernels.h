@@ -26,7 +26,8 @@ struct TensorDesc {
 // ab[n][c] = (a, b) with y = a*x + b  (a = gamma*rstd, b = beta - mean*rstd*gamma), eps = 1e-6
 // ab16 (optional): [n][Ct/2] per channel pair {half2 m_hi, half2 m_lo, half2 a/2, half2 beta/2}, mean = m_hi + m_lo
 void launch_gn_finalize(cudaStream_t st, const TensorDesc& s0, const TensorDesc* s1, const float* gamma,
-                        const float* beta, int groups, float2* ab, uint4* ab16 = nullptr);
+                        const float* beta, int groups, float2* ab, uint4* ab16 = nullptr,
+                        unsigned int* range_flag = nullptr);   // += 1 per (sample, group) whose fp16 input overflowed (non-finite sums)
 // stand-alone per-(sample, channel) statistics (slots = 1) for levels too small for per-tile partials
 void launch_channel_stats(cudaStream_t st, TensorDesc& t);
 enum Resample { RS_NONE = 0, RS_DOWN = 1, RS_UP = 2 };
@@ -39,7 +40,7 @@ extern int g_gnfin_variant;   // 1: gn_finalize with its partial loads batched e
 extern int g_gn_self;
 bool gn_self_applies(const TensorDesc& x0, const TensorDesc* x1);
 void launch_gn_norm_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float* gamma, const float* beta,
-                          int groups, bool silu, TensorDesc& out);
+                          int groups, bool silu, TensorDesc& out, unsigned int* range_flag = nullptr);
 extern int g_fir_variant;   // 0: one-MUFU (tanh-form) silu + half2 FIR-down arithmetic in the tiled fp16 kernels; 1: expf silu, fp32 FIR
                             // 2: 0 + phase-1 loads in flight at once + half2 quad FIR-up (round-2 candidate, see gn.cu)
 
@@ -95,7 +96,7 @@ bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out);
 bool conv_tc6_fuse_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
 extern int g_tc6_ablate;   // timing ablations of conv_tc6, compiled into the -DSGMSE_B200_PDL twin only (results are wrong on purpose)
-extern int g_tc6_rings, g_tc6_mma_style, g_tc6_tma_poll;   // conv_tc6 A/B switches, see conv_tc6.cu
+extern int g_tc6_rings, g_tc6_mma_style, g_tc6_tma_poll, g_tc6_roles;   // conv_tc6 A/B switches, see conv_tc6.cu
 extern int g_tc1_narrow;   // 1: conv_tc v1 takes 64-wide channel tiles when 128-wide ones fill less than half the SMs (round-2 candidate)
 extern int g_tc_variant;   // 0 (= 7, 8): newest applicable kernels (v6 with fused GroupNorm+SiLU where possible: LDG-fed producers,
                            // fp32 math = fused mode 1; else v4/v1), 1: v1 only, 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1),

@@ -432,3 +432,54 @@ def test_golden_mid_sampler_and_chain(golden_dir, mode):
     print(f"mid-size reference fixture, {mode}: " + "; ".join(report))
     assert e_enh < tol["enh"]
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# fp16 activation range (the product mode stores raw convolution outputs and the residual stream as fp16 BEFORE
+# GroupNorm): large-but-representable activations keep parity, an overflow is detected and refused, never silent
+# ------------------------------------------------------------------------------------------------
+def _scale_resblock_convs(sd, s):
+    """Scale the input conv and every ResBlock's Conv_0 / Conv_1 (weights and biases) by s: pre-GroupNorm activations grow
+    linearly with s (the tap maximum of this network and input is 4.29 s), the network function barely moves (GroupNorm
+    is scale-invariant; only the temb bias and the unscaled 1x1 shortcuts shift weight)."""
+    return {k: (v * s if (".Conv_0." in k or ".Conv_1." in k or k.startswith("all_modules.3.")) else v) for k, v in sd.items()}
+
+
+def test_fp16_activation_range_is_kept_or_reported():
+    base = o_w.make_state_dict(MID_N, seed=5)
+    g = torch.Generator().manual_seed(3)
+    x = torch.complex(torch.randn(2, 2, 64, 128, generator=g), torch.randn(2, 2, 64, 128, generator=g)) * 0.4
+    t = torch.tensor([0.9, 0.05])
+    # (1) residual stream up to ~2e4 (fp16 ulp 16 there): representable -> finite, no range event, parity holds
+    sd = _scale_resblock_convs(base, 4660.0)
+    taps = {}
+    with torch.no_grad():
+        ref = o_net.forward(sd, MID_N, x, t, taps=taps)
+    peak = max(v.abs().max().item() for k, v in taps.items() if k != "temb")
+    assert 1.5e4 < peak < 3e4
+    eng = Engine(EngineConfig(mode="fp16_tc", max_batch=2, **MID_E))
+    eng.load_state_dict(sd)
+    out = eng.dnn_forward(x.cuda(), t.cuda())
+    err = rel_l2(out, ref)
+    print(f"fp16 range stress: block outputs up to {peak:.3g}, rel-L2 {err:.3e}, range events {eng.counter('fp16_range_events')}")
+    assert torch.isfinite(torch.view_as_real(out)).all() and eng.counter("fp16_range_events") == 0 and err < 2e-2
+    # (2) 8x more: block outputs ~1.6e5 > 65504 -> inf in storage; the statistics pass counts it, the host-buffer call refuses
+    sd8 = _scale_resblock_convs(base, 8 * 4660.0)
+    eng.load_state_dict(sd8)
+    out8 = eng.dnn_forward(x.cuda(), t.cuda())
+    ev = eng.counter("fp16_range_events")
+    assert ev > 0 and not torch.isfinite(torch.view_as_real(out8)).all()
+    eng.set_option("reset_range_events", 1)
+    assert eng.counter("fp16_range_events") == 0
+    wav = 0.1 * torch.randn(1, 4000, generator=g)
+    with pytest.raises(RuntimeError, match="fp16 activation range"):
+        eng.enhance(wav, N=1, seed=1)                      # host buffers: checked before the call returns
+    assert eng.counter("fp16_range_events") == 0           # ... and cleared for the next call
+    eng.close()
+    # the fp32 validation mode carries the same weights without trouble
+    e32 = Engine(EngineConfig(mode="fp32", max_batch=2, **MID_E))
+    e32.load_state_dict(sd8)
+    with torch.no_grad():
+        ref8 = o_net.forward(sd8, MID_N, x, t)
+    assert rel_l2(e32.dnn_forward(x.cuda(), t.cuda()), ref8) < 2e-4 and e32.counter("fp16_range_events") == 0
+    e32.close()
