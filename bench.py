@@ -352,13 +352,21 @@ def run_b200(args):
         eng.set_option("time_convs", 0)
         pk = peaks()
         ach = mflop / max(us, 1)            # MFLOP/us = TFLOP/s
-        # DRAM traffic of the dominant kernel comes from the committed ncu capture (one launch of the dominant shape)
+        # DRAM traffic of the dominant kernel: ncu counters of one launch of the dominant shape, captured from THIS build
+        # (tools/make_conv_traffic.py records a digest of the kernel's sources next to the counters); a capture of another
+        # build is not reported
         traffic, traffic_note = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
         if os.path.exists(tpath):
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from make_conv_traffic import source_digest
             tj = json.load(open(tpath))
-            traffic = tj["traffic_bytes_per_launch"]
-            traffic_note = {k: tj[k] for k in ("kernel", "shape", "algorithmic_bytes_per_launch", "source")}
+            if tj.get("source_digest") == source_digest():
+                traffic = tj["traffic_bytes_per_launch"]
+                traffic_note = {k: tj[k] for k in ("kernel", "shape", "algorithmic_bytes_per_launch", "ratio", "source", "source_digest")}
+            else:
+                traffic_note = {"stale": f"profiles/r02_conv_traffic.json was captured from kernel sources {tj.get('source_digest')}, "
+                                         f"this build is {source_digest()}: re-run tools/make_conv_traffic.py"}
         roof = {"kernel": "tcgen05 implicit-GEMM convolutions (conv_tc6 with fused GroupNorm+SiLU producers; conv_tc4 / conv_tc on the levels below 32 rows)",
                 "bound": "tensor", "achieved": round(ach, 1),
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 4),

@@ -221,10 +221,13 @@ int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, 
  * "time_convs" (0/1: bracket every convolution launch with CUDA events; disables graph replay),
  * "lanes" (1..8 concurrent launch sequences inside a captured sampler graph), "max_graphs" (captured sampler graphs kept,
  * least recently used evicted; default 16).  The kernel A/B switches the tools use ("tc_variant", "attn_variant",
- * "fir_variant", "inconv_variant", "outconv_variant", "combine_variant", "tc1_narrow", "gn_self", "gnfin_variant", "tc6_*") select code paths
- * PROCESS-WIDE, not per engine; 0 is always the verified default.  "pdl" (0/1: programmatic dependent launch between the
- * kernels of the launch sequence) is accepted only by the twin library built with -DSGMSE_B200_PDL (libsgmse_b200_pdl.so,
- * counter "pdl_compiled" = 1); the default library refuses it. */
+ * "fir_variant", "inconv_variant", "outconv_variant", "combine_variant", "tc1_narrow", "gn_self", "gnfin_variant", "tc6_*") are
+ * state of THIS engine: every entry point installs the calling engine's selection before it launches anything, so another
+ * engine of the same process (another device, another host thread) never sees them, and a captured sampler graph keeps
+ * the selection it was captured with; 0 is always the verified default.  No environment variable changes kernel
+ * selection.  "tc_variant" 2 / 3 / 5 (superseded convolution generations), "tc6_ablate" and "pdl" (0/1: programmatic
+ * dependent launch between the kernels of the launch sequence) exist only in the lab twin built with -DSGMSE_B200_PDL
+ * (libsgmse_b200_pdl.so, counter "pdl_compiled" = 1); the product library refuses them. */
 int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value);
 /* counters: "kernel_launches" (since creation), "graph_launches", "cached_graphs", "workspace_bytes", "weights_bytes",
  * "tc_convs_last_forward", "direct_convs_last_forward", "launches_last_forward",

@@ -18,7 +18,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libsgmse_b200.so"
-SOURCES = ["gn.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_tc4.cu", "conv_tc5.cu", "conv_tc6.cu", "small.cu", "attn.cu", "misc.cu", "ode.cu", "engine.cu"]
+SOURCES = ["gn.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc4.cu", "conv_tc6.cu", "small.cu", "attn.cu", "misc.cu", "ode.cu", "engine.cu"]
+# superseded tcgen05 convolution generations (tc_variant 2 / 3 / 5): kept for the A/B record, compiled into the lab twin only
+LAB_SOURCES = ["conv_tc2.cu", "conv_tc3.cu", "conv_tc5.cu"]
 HEADERS = ["common.cuh", "kernels.h", "engine.h", "rk45.h", os.path.join("..", "..", "include", "sgmse_b200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -28,7 +30,9 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "--expt-relaxed-constexpr", "-diag-suppress", "177"]
 
 
-PDL_LIBNAME = "libsgmse_b200_pdl.so"   # same sources with -DSGMSE_B200_PDL (programmatic dependent launch, common.cuh)
+# the LAB twin: the product sources + LAB_SOURCES with -DSGMSE_B200_PDL (programmatic dependent launch, timing ablations of
+# conv_tc6, the superseded convolution generations); never loaded unless SGMSE_B200_PDL=1
+PDL_LIBNAME = "libsgmse_b200_pdl.so"
 
 
 def lib_path(pdl: bool = False) -> str:
@@ -38,7 +42,7 @@ def lib_path(pdl: bool = False) -> str:
 def _digest(extra: str = "") -> str:
     h = hashlib.sha256()
     h.update(extra.encode())
-    for f in SOURCES + HEADERS:
+    for f in SOURCES + LAB_SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(ARCH + CFLAGS).encode())
@@ -68,8 +72,9 @@ def build(force: bool = False, verbose: bool = False, pdl: bool = False) -> str:
             print(r.stdout, r.stderr, file=sys.stderr)
         return obj
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+    sources = SOURCES + (LAB_SOURCES if pdl else [])
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
+        objs = list(ex.map(compile_one, sources))
     cmd = [NVCC, *ARCH, "-shared", "-cudart", "static", "-o", out, *objs,
            "-L" + CUDA_LIB, "-lcufft", "-Xlinker", "-rpath," + CUDA_LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -297,7 +297,7 @@ void run_tc(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int S) {
 }
 }  // namespace
 
-int g_attn_variant = 0;   // 0: tensor-core kernel where it applies, 1: always the fp32 CUDA-core kernel, 2: 0 with cp.async tile staging
+thread_local int g_attn_variant = 0;   // 0: tensor-core kernel where it applies, 1: always the fp32 CUDA-core kernel, 2: 0 with cp.async tile staging
 
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out) {
   const int C = out.C, S = qkv.H * qkv.W;

@@ -76,7 +76,7 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 #endif
-extern int g_pdl;              // runtime switch (option "pdl"); refused unless the library was built with SGMSE_B200_PDL
+extern thread_local int g_pdl;              // runtime switch (option "pdl"); refused unless the library was built with SGMSE_B200_PDL
 bool pdl_compiled();
 
 #ifdef __CUDACC__

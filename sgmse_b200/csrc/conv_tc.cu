@@ -440,8 +440,8 @@ void launch_impl(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) 
 
 }  // namespace
 
-int g_tc_variant = 0;   // see kernels.h
-int g_tc1_narrow = 0;   // see launch_conv_tc
+thread_local int g_tc_variant = 0;   // see kernels.h
+thread_local int g_tc1_narrow = 0;   // see launch_conv_tc
 volatile int* g_wait_code_host = nullptr;
 
 bool conv_tc_supported(const ConvArgs& a, const TensorDesc& out) {
@@ -460,13 +460,18 @@ void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* db
   }
   if (a.residual) SG_CHECK(a.residual->C == out.C && a.residual->dt == DT_F16, "conv_tc: residual mismatch");
   if (a.gn_ab) {                                                      // the engine only asks for fusion when it applies
-    if (g_tc_variant == 5) launch_conv_tc5(st, a, out, dbg); else launch_conv_tc6(st, a, out, dbg);
+#ifdef SGMSE_B200_PDL        // the superseded generations (conv_tc2/3/5) live in the lab twin only (build.py)
+    if (g_tc_variant == 5) { launch_conv_tc5(st, a, out, dbg); return; }
+#endif
+    launch_conv_tc6(st, a, out, dbg);
     return;
   }
   if ((g_tc_variant == 0 || g_tc_variant >= 6) && conv_tc6_supported(a, out)) { launch_conv_tc6(st, a, out, dbg); return; }
   if ((g_tc_variant == 0 || g_tc_variant >= 4) && conv_tc4_supported(a, out)) { launch_conv_tc4(st, a, out, dbg); return; }
+#ifdef SGMSE_B200_PDL
   if (g_tc_variant == 3 && conv_tc3_supported(a, out)) { launch_conv_tc3(st, a, out, dbg); return; }
   if (g_tc_variant != 1 && conv_tc2_supported(a, out)) { launch_conv_tc2(st, a, out, dbg); return; }
+#endif
   // tc1_narrow (round-2 candidate, default off): on the levels below 16 rows a 128-wide channel tile leaves 32-64 CTAs that
   // each stream 32 KB per 64-deep k-block; 64-wide tiles double the CTAs and cut the per-CTA stream to 24 KB.  The
   // accumulation order of an output element does not depend on the tile width: bit-identical.

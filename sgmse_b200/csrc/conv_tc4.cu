@@ -348,17 +348,21 @@ void launch4(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
 
 }  // namespace
 
-bool conv_tc4_supported(const ConvArgs& a, const TensorDesc& out) { return conv_tc2_supported(a, out); }
+bool conv_tc4_supported(const ConvArgs& a, const TensorDesc& out) {
+  if (out.dt != DT_F16 || out.C % 128 != 0 || a.w_tc == nullptr) return false;
+  if (out.W % 8 != 0 || out.H % 16 != 0) return false;
+  for (int i = 0; i < a.nseg; ++i)
+    if (a.seg[i].src.C % 64 != 0 || a.seg[i].src.dt != DT_F16) return false;
+  if (a.residual && (!a.tc_identity_tail || a.nseg >= MAX_SEG || a.residual->C != out.C)) return false;
+  return true;
+}
 
 void launch_conv_tc4(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   SG_CHECK(conv_tc4_supported(a, out), "conv_tc4: unsupported shape");
   // Ring depths trade prefetch distance against shared memory left for co-resident blocks of the HBM-bound kernels
   // that the other lane of the sampler graph runs concurrently (each needs 1 KB of reserved smem per block).
-  static const int ring_cfg = [] { const char* v = getenv("SGMSE_B200_TC4_RINGS"); return v ? atoi(v) : 0; }();
   if (out.H % 32 == 0) {
-    if (ring_cfg == 1) launch4<2, 2, 5>(st, a, out, dbg);
-    else if (ring_cfg == 2) launch4<2, 2, 4>(st, a, out, dbg);
-    else launch4<2, 3, 5>(st, a, out, dbg);
+    launch4<2, 3, 5>(st, a, out, dbg);
   } else {
     launch4<1, 4, 6>(st, a, out, dbg);
   }

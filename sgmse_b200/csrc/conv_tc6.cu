@@ -774,8 +774,7 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   P.scale = a.scale;
   out.slots = P.tiles_w * P.tiles_h;
   P.stats = out.stats; P.slots = out.slots;
-  static const int desc_mode = [] { const char* v = getenv("SGMSE_B200_TC6_DESC"); return v ? atoi(v) : 0; }();
-  P.desc_mode = desc_mode;
+  P.desc_mode = 0;
   P.mma_style = g_tc6_mma_style; P.tma_poll = g_tc6_tma_poll; P.role_map = g_tc6_roles;
   P.dbg = dbg;
 #ifdef SGMSE_B200_PDL
@@ -805,11 +804,11 @@ bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out) {
 }
 
 // A/B switches (engine options "tc6_rings", "tc6_mma", "tc6_tma_poll")
-int g_tc6_ablate = 0;   // twin library only (see Tc6Params::ablate)
-int g_tc6_rings = [] { const char* v = getenv("SGMSE_B200_TC6_RINGS"); return v ? atoi(v) : 0; }();   // 0: 2 activation + 6 weight stages; 1: 3 + 4
-int g_tc6_mma_style = 0;
-int g_tc6_tma_poll = 0;
-int g_tc6_roles = 0;    // Tc6Params::role_map
+thread_local int g_tc6_ablate = 0;   // twin library only (see Tc6Params::ablate)
+thread_local int g_tc6_rings = 0;   // 0: 2 activation + 6 weight stages; 1: 3 + 4
+thread_local int g_tc6_mma_style = 0;
+thread_local int g_tc6_tma_poll = 0;
+thread_local int g_tc6_roles = 0;    // Tc6Params::role_map
 
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   if (a.gn_ab) {

@@ -437,7 +437,11 @@ struct Fwd {
     // Fused path (conv_tc5): the 3x3 convs read the RAW tensor and apply GroupNorm+SiLU on the way into shared
     // memory, so the gn_apply pass (one read + one write of the tensor) and its buffer disappear.
     const bool fuse_ok = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && (g_tc_variant == 0 || g_tc_variant == 5 || g_tc_variant >= 7);
+#ifdef SGMSE_B200_PDL
     auto shape_ok = g_tc_variant == 5 ? conv_tc5_shape_ok : conv_tc6_fuse_shape_ok;
+#else
+    auto shape_ok = conv_tc6_fuse_shape_ok;
+#endif
     const bool fuse0 = fuse_ok && ((e.tc_mask >> 8) & 1) && rs == RS_NONE && l.c0.w_tc && shape_ok(Ho, Wo, x0.C, x1 ? x1->C : 0, l.cout, 0);
     const int nraw1 = l.shortcut ? ((rs == RS_NONE && x1) ? 2 : 1) : 1;
     const bool fuse1 = fuse_ok && ((e.tc_mask >> 9) & 1) && l.c1.w_tc && shape_ok(Ho, Wo, l.cout, 0, l.cout, nraw1) &&
@@ -1505,6 +1509,17 @@ void enhance_ode(Engine& e, const float* wav, int B, int L, const sgmse_b200_ode
 // ================================================================================================
 // C-ABI
 // ================================================================================================
+// Install the calling engine's kernel selection into the thread-local switches the launch helpers read.
+static void activate(const sgmse_b200_engine& e) {
+  const auto& o = e.opts;
+  sgmse::g_tc_variant = o.tc_variant; sgmse::g_tc1_narrow = o.tc1_narrow; sgmse::g_tc6_rings = o.tc6_rings;
+  sgmse::g_tc6_mma_style = o.tc6_mma; sgmse::g_tc6_tma_poll = o.tc6_tma_poll; sgmse::g_tc6_roles = o.tc6_roles;
+  sgmse::g_tc6_ablate = o.tc6_ablate; sgmse::g_attn_variant = o.attn_variant; sgmse::g_fir_variant = o.fir_variant;
+  sgmse::g_inconv_variant = o.inconv_variant; sgmse::g_outconv_variant = o.outconv_variant;
+  sgmse::g_combine_variant = o.combine_variant; sgmse::g_gn_self = o.gn_self; sgmse::g_gnfin_variant = o.gnfin_variant;
+  sgmse::g_pdl = o.pdl;
+}
+
 #define API_BEGIN try {
 #define API_END                                                          \
   return 0;                                                              \
@@ -1524,7 +1539,6 @@ int sgmse_b200_create(const sgmse_b200_config* cfg, sgmse_b200_engine** out) {
   std::unique_ptr<Engine> e(new Engine());
   e->cfg = *cfg;
   if (e->cfg.max_batch <= 0) e->cfg.max_batch = 8;
-  if (const char* v = getenv("SGMSE_B200_TC_VARIANT")) sgmse::g_tc_variant = atoi(v);   // A/B switch for profiling
   SG_CHECK(cfg->mode >= 0 && cfg->mode <= 2, "unknown mode %d", cfg->mode);
   build_network(*e);                          // host only: no CUDA call before the first weights arrive
   *out = e.release();
@@ -1545,6 +1559,7 @@ int sgmse_b200_manifest_count(const sgmse_b200_engine* e) { return e ? (int)e->m
 int sgmse_b200_manifest_entry(const sgmse_b200_engine* e, int i, char* name, int name_cap, long long* numel) {
   API_BEGIN
   SG_CHECK(e && i >= 0 && i < (int)e->manifest.size(), "manifest index out of range");
+  activate(*e);
   if (name && name_cap > 0) { strncpy(name, e->manifest[i].name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
   if (numel) *numel = e->manifest[i].numel;
   API_END
@@ -1554,6 +1569,7 @@ long long sgmse_b200_weights_numel(const sgmse_b200_engine* e) { return e ? e->w
 int sgmse_b200_load_weights(sgmse_b200_engine* e, const float* blob, long long numel) {
   API_BEGIN
   SG_CHECK(e && blob, "null argument");
+  activate(*e);
   SG_CHECK(numel == e->weights_numel, "weight blob has %lld floats, the network needs %lld", numel, e->weights_numel);
   load_weights(*e, blob);
   API_END
@@ -1561,6 +1577,7 @@ int sgmse_b200_load_weights(sgmse_b200_engine* e, const float* blob, long long n
 int sgmse_b200_load_weights_device(sgmse_b200_engine* e, const float* blob_dev, long long numel, void* stream) {
   API_BEGIN
   SG_CHECK(e && blob_dev, "null argument");
+  activate(*e);
   SG_CHECK(numel == e->weights_numel, "weight blob has %lld floats, the network needs %lld", numel, e->weights_numel);
   std::vector<float> host((size_t)numel);
   CUDA_OK(cudaMemcpyAsync(host.data(), blob_dev, (size_t)numel * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -1572,6 +1589,7 @@ int sgmse_b200_load_weights_device(sgmse_b200_engine* e, const float* blob_dev, 
 int sgmse_b200_dnn_forward(sgmse_b200_engine* e, const void* x, const float* t, void* out, int B, int F, int T, void* stream) {
   API_BEGIN
   SG_CHECK(e && x && t && out && B > 0, "bad argument");
+  activate(*e);
   const float2* xx = (const float2*)x;   // [B][2][F*T]: channel 0 = x_t, channel 1 = y
   // the two channels of one sample are F*T apart; re-pack through pack_state per sample pair
   const size_t px1 = (size_t)F * T;
@@ -1588,6 +1606,7 @@ int sgmse_b200_dnn_forward(sgmse_b200_engine* e, const void* x, const float* t, 
 int sgmse_b200_score(sgmse_b200_engine* e, const void* x_t, const void* y, const float* t, void* out, int B, int F, int T, void* stream) {
   API_BEGIN
   SG_CHECK(e && x_t && y && t && out && B > 0, "bad argument");
+  activate(*e);
   dnn_forward(*e, (const float2*)x_t, (const float2*)y, t, (float2*)out, B, F, T, true, (cudaStream_t)stream);
   API_END
 }
@@ -1598,6 +1617,7 @@ int sgmse_b200_model_forward(sgmse_b200_engine* e, const void* x_t, const void* 
                              int T, void* stream) {
   API_BEGIN
   SG_CHECK(e && x_t && y && t && out && B > 0, "bad argument");
+  activate(*e);
   cudaStream_t st = (cudaStream_t)stream;
   if (!is_v2(*e)) {                                  // legacy branch (model.py:307-310)
     dnn_forward(*e, (const float2*)x_t, (const float2*)y, t, (float2*)out, B, F, T, true, st);
@@ -1639,6 +1659,7 @@ int sgmse_b200_sampler_schedule(const sgmse_b200_engine* e, const sgmse_b200_sam
                                 float* coef, int cap_updates, int* n_updates) {
   API_BEGIN
   SG_CHECK(e && s && s->N >= 1, "bad argument");
+  activate(*e);
   const SamplerTables tb = make_tables(*e, *s);
   if (ts) for (int i = 0; i < s->N; ++i) ts[i] = tb.ts[i];
   if (s->kind != SGMSE_B200_SAMPLER_PC) {
@@ -1674,6 +1695,7 @@ int sgmse_b200_pc_sample(sgmse_b200_engine* e, const void* y, int B, int F, int 
                          const void* noise, void* out, int* nfe, void* stream) {
   API_BEGIN
   SG_CHECK(e && y && s && out && B > 0, "bad argument");
+  activate(*e);
   const int mb = std::max(1, e->cfg.max_batch);
   ensure_stft_buf(*e, 3, (size_t)std::min(B, mb) * F * T * 8);
   pc_sample(*e, (const float2*)y, B, F, T, *s, (const float2*)noise, (float2*)out, nfe, (cudaStream_t)stream);
@@ -1684,6 +1706,7 @@ int sgmse_b200_ode_sample(sgmse_b200_engine* e, const void* y, int B, int F, int
                           const void* prior_noise, void* out, int* nfe, int stats[4], void* stream) {
   API_BEGIN
   SG_CHECK(e && y && o && out && B > 0, "bad argument");
+  activate(*e);
   ode_sample(*e, (const float2*)y, B, F, T, *o, (const float2*)prior_noise, (float2*)out, nfe, stats, (cudaStream_t)stream);
   API_END
 }
@@ -1710,12 +1733,14 @@ int sgmse_b200_padded_frames(const sgmse_b200_engine* e, int L) { return e ? pad
 int sgmse_b200_analysis(sgmse_b200_engine* e, const float* wav, int B, int L, int pad_mode, void* Y, float* norm, void* stream) {
   API_BEGIN
   SG_CHECK(e && wav && Y && norm, "bad argument");
+  activate(*e);
   analysis(*e, wav, B, L, pad_mode, (float2*)Y, norm, (cudaStream_t)stream);
   API_END
 }
 int sgmse_b200_synthesis(sgmse_b200_engine* e, const void* X, const float* norm, int B, int Tpad, int L, float* wav, void* stream) {
   API_BEGIN
   SG_CHECK(e && X && norm && wav, "bad argument");
+  activate(*e);
   synthesis(*e, (const float2*)X, norm, B, Tpad, L, wav, (cudaStream_t)stream);
   API_END
 }
@@ -1723,6 +1748,7 @@ int sgmse_b200_enhance(sgmse_b200_engine* e, const float* wav, int B, int L, con
                        const void* noise, float* out, int host_buffers, void* stream) {
   API_BEGIN
   SG_CHECK(e && wav && s && out && B > 0 && L > 0, "bad argument");
+  activate(*e);
   enhance(*e, wav, B, L, *s, (const float2*)noise, out, host_buffers != 0, (cudaStream_t)stream);
   API_END
 }
@@ -1731,6 +1757,7 @@ int sgmse_b200_enhance_ode(sgmse_b200_engine* e, const float* wav, int B, int L,
                            const void* prior_noise, float* out, int host_buffers, int* nfe, void* stream) {
   API_BEGIN
   SG_CHECK(e && wav && o && out && B > 0 && L > 0, "bad argument");
+  activate(*e);
   enhance_ode(*e, wav, B, L, *o, pad_mode, (const float2*)prior_noise, out, host_buffers != 0, nfe, (cudaStream_t)stream);
   API_END
 }
@@ -1738,6 +1765,7 @@ int sgmse_b200_enhance_ode(sgmse_b200_engine* e, const float* wav, int B, int L,
 int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, long long cap, int shape[4]) {
   API_BEGIN
   SG_CHECK(e && name, "bad argument");
+  activate(*e);
   CUDA_OK(cudaDeviceSynchronize());
   auto it = e->taps.find(name);
   if (it != e->taps.end()) {
@@ -1788,6 +1816,7 @@ long long sgmse_b200_workspace_bytes(sgmse_b200_engine* e, int B, int F, int T) 
 int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value) {
   API_BEGIN
   SG_CHECK(e && key, "bad argument");
+  activate(*e);
   const std::string k = key;
   if (k == "record_taps") e->record_taps = value != 0;
   else if (k == "time_convs") {
@@ -1803,38 +1832,42 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   }
   else if (k == "tc_variant") {
     // changes which intermediate buffers a forward needs: drop cached workspace sizes, graphs and shadow lanes
-    sgmse::g_tc_variant = (int)value;
+    // 2, 3, 5 = the superseded kernel generations conv_tc2 / conv_tc3 / conv_tc5: compiled into the lab twin only
+    SG_CHECK((value != 2 && value != 3 && value != 5) || sgmse::pdl_compiled(),
+             "tc_variant %lld selects a superseded kernel generation that exists in the lab twin library only "
+             "(python -m sgmse_b200.build --pdl, SGMSE_B200_PDL=1)", value);
+    e->opts.tc_variant = (int)value;
     if (e->lanes.size() > 1) ensure_lanes(*e, 1);
     e->arena_need.clear();
     clear_graphs(*e);
   }
-  else if (k == "attn_variant") { sgmse::g_attn_variant = (int)value; clear_graphs(*e); }
-  else if (k == "tc6_rings") { sgmse::g_tc6_rings = (int)value; clear_graphs(*e); }
-  else if (k == "tc6_mma") { sgmse::g_tc6_mma_style = (int)value; clear_graphs(*e); }
-  else if (k == "tc6_tma_poll") { sgmse::g_tc6_tma_poll = (int)value; clear_graphs(*e); }
-  else if (k == "tc6_roles") { sgmse::g_tc6_roles = (int)value; clear_graphs(*e); }
-  else if (k == "fir_variant") { sgmse::g_fir_variant = (int)value; clear_graphs(*e); }
-  else if (k == "inconv_variant") { sgmse::g_inconv_variant = (int)value; clear_graphs(*e); }
-  else if (k == "combine_variant") { sgmse::g_combine_variant = (int)value; clear_graphs(*e); }
-  else if (k == "tc1_narrow") { sgmse::g_tc1_narrow = (int)value; clear_graphs(*e); }
-  else if (k == "gn_self") { sgmse::g_gn_self = (int)value; clear_graphs(*e); }
-  else if (k == "gnfin_variant") { sgmse::g_gnfin_variant = (int)value; clear_graphs(*e); }
+  else if (k == "attn_variant") { e->opts.attn_variant = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_rings") { e->opts.tc6_rings = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_mma") { e->opts.tc6_mma = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_tma_poll") { e->opts.tc6_tma_poll = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_roles") { e->opts.tc6_roles = (int)value; clear_graphs(*e); }
+  else if (k == "fir_variant") { e->opts.fir_variant = (int)value; clear_graphs(*e); }
+  else if (k == "inconv_variant") { e->opts.inconv_variant = (int)value; clear_graphs(*e); }
+  else if (k == "combine_variant") { e->opts.combine_variant = (int)value; clear_graphs(*e); }
+  else if (k == "tc1_narrow") { e->opts.tc1_narrow = (int)value; clear_graphs(*e); }
+  else if (k == "gn_self") { e->opts.gn_self = (int)value; clear_graphs(*e); }
+  else if (k == "gnfin_variant") { e->opts.gnfin_variant = (int)value; clear_graphs(*e); }
   else if (k == "tc6_ablate") {
     SG_CHECK(value == 0 || sgmse::pdl_compiled(), "option 'tc6_ablate' exists in the -DSGMSE_B200_PDL twin library only");
-    sgmse::g_tc6_ablate = (int)value;
+    e->opts.tc6_ablate = (int)value;
     clear_graphs(*e);
   }
   else if (k == "outconv_variant") {
-    sgmse::g_outconv_variant = (int)value;       // changes the buffers a forward needs (fused GroupNorm or not)
+    e->opts.outconv_variant = (int)value;       // changes the buffers a forward needs (fused GroupNorm or not)
     if (e->lanes.size() > 1) ensure_lanes(*e, 1);
     e->arena_need.clear();
     clear_graphs(*e);
   }
   else if (k == "pdl") {
-    // programmatic dependent launch between the kernels of the launch sequence (process-wide, like the other A/B switches)
+    // programmatic dependent launch between the kernels of the launch sequence
     SG_CHECK(value == 0 || sgmse::pdl_compiled(),
              "option 'pdl' needs the library built with -DSGMSE_B200_PDL (python -m sgmse_b200.build --pdl, SGMSE_B200_LIB=...)");
-    sgmse::g_pdl = value != 0;
+    e->opts.pdl = value != 0;
     clear_graphs(*e);
   }
   else if (k == "max_graphs") {
@@ -1863,7 +1896,7 @@ long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key) {
   if (k == "graph_launches") return e->graph_launches;
   if (k == "cached_graphs") return (long long)e->graphs.size();
   if (k == "pdl_compiled") return sgmse::pdl_compiled() ? 1 : 0;
-  if (k == "pdl") return sgmse::g_pdl;
+  if (k == "pdl") return e->opts.pdl;
   if (k == "workspace_bytes") return (long long)e->arena.cap;
   if (k == "weights_bytes") return (long long)e->weights_bytes;
   if (k == "tc_convs_last_forward") return e->tc_convs;

@@ -16,7 +16,7 @@ namespace sgmse {
 // BATCH (gnfin_variant 1, round-2 candidate, not yet run on a GPU): the partials of a thread are loaded eight at a time before
 // they are added, in the same order (the plain loop is load -> add -> branch: 8 serialized round trips per thread at the 512-slot
 // levels, most of the kernel's 5.9 us); bit-identical.
-int g_gnfin_variant = 0;
+thread_local int g_gnfin_variant = 0;
 
 template <bool BATCH>
 __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, int slots0,
@@ -238,7 +238,7 @@ gn_apply_plain_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1
 // pixels at 16x32) the association differs, but these are fp64 sums of <= 512 fp32 partials, which do not round unless the
 // partials span more than ~2^20 in magnitude -- and then applies them exactly like gn_apply_plain.
 // ------------------------------------------------------------------------------------------------
-int g_gn_self = 0;
+thread_local int g_gn_self = 0;
 
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(256)
@@ -408,7 +408,7 @@ gn_apply_fir_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ 
 // Phase 1 stages h = silu(a*x+b) and the raw x of an input tile (+1 pixel halo) in smem as fp32->half pairs;
 // phase 2 applies the separable [1,3,3,1] FIR from smem and writes both outputs with 128-bit stores.
 // ------------------------------------------------------------------------------------------------
-int g_fir_variant = 0;   // 0: one-MUFU silu (tanh form) + half2 FIR-down arithmetic; 1: expf/divide silu, fp32 FIR;
+thread_local int g_fir_variant = 0;   // 0: one-MUFU silu (tanh form) + half2 FIR-down arithmetic; 1: expf/divide silu, fp32 FIR;
                          // 2 (round-2 candidate, not yet run on a GPU): 0 + all global loads of phase 1 in flight at once
                          //    (the SASS of 0 has ONE LDG.128 per loop trip in front of 8 MUFU: 4-6 serialized memory
                          //    round trips per thread) + half2 FIR-up over 2x2 output quads (9 instead of 16 LDS.128 and

@@ -8,7 +8,7 @@
 
 namespace sgmse {
 
-int g_pdl = 0;                 // see common.cuh
+thread_local int g_pdl = 0;                 // see common.cuh
 bool pdl_compiled() {
 #ifdef SGMSE_B200_PDL
   return true;

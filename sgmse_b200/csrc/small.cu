@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restric
 //   state float4 of neighbour tap 4s + (t >> 1) [a0/a1] and 4s + 2 + (t >> 1) [a2/a3]: straight from global/L1.
 //   B fragments (k x channels) are built once per block in shared memory; the block then walks tiles of 128 pixels.
 //   Output goes through a per-warp padded smem tile so that global stores are 128-bit and row-contiguous.
-int g_inconv_variant = 0;   // 0: tensor-core kernel for fp16 output where it applies, 1: CUDA-core kernel,
+thread_local int g_inconv_variant = 0;   // 0: tensor-core kernel for fp16 output where it applies, 1: CUDA-core kernel,
                             // 2 (round-2 candidate, not yet run on a GPU): 0 with the A fragments of the NEXT 16-pixel m-tile
                             //   loaded before the 48 MMAs of the current one (today every m-tile starts with an exposed
                             //   L1/L2 round trip at 16 warps per SM); same arithmetic, bit-identical
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(128) combine_kernel(const float4* __restrict__
 // 32-pixel tile and walks the tile's pixels in order -- the same per-channel expression and the same summation order as
 // the kernel above, so results and statistics are bit-identical -- with 8 vector loads in flight per thread instead of
 // four 2-byte ones (the scalar kernel keeps ~16 KB in flight per SM: 2.4 TB/s on the 268 MB of the top level).
-int g_combine_variant = 0;
+thread_local int g_combine_variant = 0;
 
 template <int CV>   // CV = C / 8 vectors per pixel (16 or 32); block = 128 threads = 128 / CV tiles
 __global__ void __launch_bounds__(128) combine_vec_kernel(const float4* __restrict__ pyr, const float* __restrict__ w,
@@ -756,7 +756,7 @@ static void out_conv_mma_launch(cudaStream_t st, const TensorDesc& act, const fl
   CUDA_OK(cudaGetLastError());
 }
 
-int g_outconv_variant = 0;   // see kernels.h
+thread_local int g_outconv_variant = 0;   // see kernels.h
 
 template <typename T>
 static void out_conv_dispatch(cudaStream_t st, const TensorDesc& act, const float4* w, float4 b, const float4* addend,

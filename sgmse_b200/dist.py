@@ -38,9 +38,17 @@ def broadcast_weights(blob: Optional[torch.Tensor], numel: int, device: torch.de
 
 def enhance_sharded(enhance_fn: Callable[..., torch.Tensor], wav: torch.Tensor, gather: bool = True, **kw):
     """``wav`` [B, L] (identical on every rank).  Each rank enhances its slice with
-    ``enhance_fn(wav_slice, utt_offset=lo, **kw)``; with ``gather`` every rank receives the full [B, L]."""
+    ``enhance_fn(wav_slice, utt_offset=lo, **kw)``; with ``gather`` every rank receives the full [B, L].
+
+    Per-utterance results do not depend on the number of ranks (noise is keyed by the global utterance id; bit-equal to
+    the single-process call, tools/nccl_invariance.py).  The one sampler for which that cannot hold is
+    ``corrector='langevin'``: its step size is a mean over the batch (/root/reference/sgmse/sampling/correctors.py:50-52),
+    so the utterances of a batch are coupled and sharding the batch would change every result -- refused for world > 1."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
+    if world > 1 and kw.get("corrector", "ald") == "langevin":
+        raise ValueError("corrector='langevin' couples the utterances of a batch (batch-mean step size, correctors.py:50-52): "
+                         "sharding the batch over ranks would change the results; run it on one rank or use 'ald'")
     B, L = wav.shape
     lo, hi = shard_range(B, rank, world)
     mine = enhance_fn(wav[lo:hi], utt_offset=lo, **kw) if hi > lo else wav.new_zeros((0, L))

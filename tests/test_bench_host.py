@@ -77,3 +77,22 @@ def test_tools_are_importable_python_and_shell_scripts_parse():
     for f in sorted(glob.glob(os.path.join(root, "tools", "*.sh"))):
         r = subprocess.run(["bash", "-n", f], capture_output=True, text=True)
         assert r.returncode == 0, f"{f}: {r.stderr}"
+
+
+def test_conv_traffic_capture_is_tied_to_the_kernel_sources(tmp_path, capsys):
+    """roofline.traffic comes from ncu counters of the CURRENT build: tools/make_conv_traffic.py stores a digest of the
+    dominant kernel's sources next to the counters, bench.py drops a capture whose digest differs (stale file -> null)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import make_conv_traffic as m
+    csvf = tmp_path / "t.csv"
+    hdr = '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"'
+    row = lambda name, val: f'"0","1","python","h","conv_tc6_kernel<2, 6>(...)","1","7","(448, 1, 1)","(148, 1, 1)","0","10.0","s","{name}","byte","{val}"'
+    csvf.write_text("==PROF== noise\n" + hdr + "\n" + row("dram__bytes_read.sum", "537,675,008") + "\n" +
+                    row("dram__bytes_write.sum", "499070464") + "\n" + row("gpu__time_duration.sum", "545760") + "\n")
+    m.main(str(csvf))
+    d = json.loads(capsys.readouterr().out)
+    assert d["traffic_bytes_per_launch"] == 537675008 + 499070464 and d["algorithmic_bytes_per_launch"] == 2 ** 30
+    assert d["source_digest"] == m.source_digest() and len(d["source_digest"]) == 16 and 0.9 < d["ratio"] < 1.0

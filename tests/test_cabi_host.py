@@ -249,3 +249,23 @@ def test_every_ab_switch_is_a_known_option():
     with pytest.raises(RuntimeError, match="max_graphs"):
         eng.set_option("max_graphs", 0)
     eng.close()
+
+
+def test_kernel_selection_is_per_engine_and_the_product_library_has_no_lab_kernels():
+    """Options are engine state (host-only calls here): the superseded convolution generations and programmatic dependent
+    launch are refused by the product library, a selection made on one engine is invisible to another."""
+    from sgmse_b200 import Engine, EngineConfig
+    a, b = Engine(EngineConfig(max_batch=1)), Engine(EngineConfig(max_batch=1))
+    if a.counter("pdl_compiled") == 0:
+        for v in (2, 3, 5):
+            with pytest.raises(RuntimeError, match="lab twin"):
+                a.set_option("tc_variant", v)
+        with pytest.raises(RuntimeError, match="SGMSE_B200_PDL"):
+            a.set_option("pdl", 1)
+    a.set_option("tc_variant", 6)
+    a.set_option("fir_variant", 1)
+    with pytest.raises(RuntimeError, match="unknown option"):
+        b.set_option("no_such_option", 1)
+    assert a.counter("pdl") == 0 and b.counter("pdl") == 0
+    a.close()
+    b.close()

@@ -34,7 +34,12 @@ def _worker(rank, world, port, B, out_q):
         blob = torch.arange(1000, dtype=torch.float32) if rank == 0 else None
         got_blob = broadcast_weights(blob, 1000, torch.device("cpu"))
         full = enhance_sharded(fake_enhance, wav, gather=True, scale=3.0)
-        out_q.put((rank, got_blob.sum().item(), full))
+        try:                                   # the batch-coupled corrector is refused when the batch is sharded (correctors.py:50-52)
+            enhance_sharded(fake_enhance, wav, gather=True, corrector="langevin")
+            refused = False
+        except ValueError as e:
+            refused = "langevin" in str(e)
+        out_q.put((rank, got_blob.sum().item(), full, refused))
     finally:
         dist.destroy_process_group()
 
@@ -54,9 +59,9 @@ def test_two_rank_sharding_matches_single_process(B):
     g = torch.Generator().manual_seed(0)
     wav = torch.randn(B, 50, generator=g)
     want = fake_enhance(wav, 0, scale=3.0)
-    for rank, blob_sum, full in res:
+    for rank, blob_sum, full, refused in res:
         assert blob_sum == float(sum(range(1000)))
-        assert torch.equal(full, want)
+        assert torch.equal(full, want) and refused
 
 
 def test_shard_range_covers_everything():

@@ -399,3 +399,18 @@ def test_round2_candidate_keeps_its_promise(full_sd, key, val, tol):
     print(f"{key}={val}: rel-L2 vs default {err:.3e}")
     assert torch.equal(got, ref) if tol == 0.0 else err <= tol
     eng.close()
+
+
+def test_two_rank_nccl_shard_invariance():
+    """SURVEY.md §4 multi-GPU row on real GPUs: 2 ranks over NCCL (weight broadcast + gather), per-utterance outputs bit-equal
+    to the single-process run; 'langevin' refused when sharded (tools/nccl_invariance.py).  Needs 2 devices."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "nccl_invariance.py")], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-400:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "sharded == single-process on every rank: True" in r.stdout and "langevin refused when sharded: True" in r.stdout
