@@ -114,14 +114,16 @@ _CPU = {"threads": None, "sweep": None, "forward_s": None, "source": None}
 def _thread_candidates():
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     import torch
-    cands = {avail, avail // 2, avail // 4, 32, 16, torch.get_num_threads()}
-    return sorted((c for c in cands if 1 <= c <= avail), reverse=True)
+    cands = {8, 16, 24, 32, 48, 64, avail // 2, avail, torch.get_num_threads()}
+    return sorted(c for c in cands if 1 <= c <= avail)
 
 
 def pick_cpu_threads(forward):
     """Thread sweep on the FULL shape of the workload: one warm + one timed score-network evaluation on a
-    [1, 2, 256, 512] input per candidate count; the fastest wins (oversubscribed MKL-DNN convolutions get slower, not
-    faster).  The table goes into the JSON line (`cpu_baseline.thread_sweep`)."""
+    [1, 2, 256, 512] input per candidate count, ascending; the fastest wins.  More threads are NOT faster for this
+    batch-1 network (MKL-DNN convolutions: 16 threads 3.75 s, 64 threads 5.3 s, 128 threads 73 s per evaluation on the
+    128-CPU host of the B200 box, profiles/r02_bench_reference_arm.json), so the sweep stops once a candidate is more than
+    twice as slow as the best so far.  The table goes into the JSON line (`cpu_baseline.thread_sweep_s_per_forward`)."""
     if _CPU["threads"] is not None:
         return _CPU["threads"]
     import torch
@@ -135,6 +137,9 @@ def pick_cpu_threads(forward):
         sweep[str(c)] = round(dt, 3)
         if dt < best[0]:
             best = (dt, c)
+        elif dt > 2.0 * best[0]:
+            sweep["stopped_after"] = c
+            break
     _CPU.update(threads=best[1], sweep=sweep, forward_s=best[0])
     torch.set_num_threads(best[1])
     return best[1]

@@ -302,11 +302,17 @@ thread_local int g_attn_variant = 0;   // 0: tensor-core kernel where it applies
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out) {
   const int C = out.C, S = qkv.H * qkv.W;
   SG_CHECK(qkv.C == 3 * C && C % 8 == 0, "attention: qkv must have 3C channels");
+  // 5: tcgen05 kernel (attn_umma.cu) where it applies (fp16, C = 256, 128 | tokens <= 512); 6: the same with the other reading
+  // of the MN-major descriptor strides (bring-up switch)
+  if ((g_attn_variant == 5 || g_attn_variant == 6) && attention_umma_supported(qkv, out)) {
+    launch_attention_umma(st, qkv, out, g_attn_variant == 6 ? 1 : 0, nullptr);
+    return;
+  }
   if (qkv.dt == DT_F16 && g_attn_variant == 2) {
     if (C == 256) { run_tc<256, true>(st, qkv, out, S); return; }
     if (C == 128) { run_tc<128, true>(st, qkv, out, S); return; }
   }
-  if (qkv.dt == DT_F16 && (g_attn_variant == 0 || g_attn_variant == 2)) {
+  if (qkv.dt == DT_F16 && (g_attn_variant == 0 || g_attn_variant == 2 || g_attn_variant >= 5)) {
     if (C == 256) { run_tc<256>(st, qkv, out, S); return; }
     if (C == 128) { run_tc<128>(st, qkv, out, S); return; }
   }

@@ -1,0 +1,261 @@
+// Single-head global self-attention on tcgen05 (AttnBlockpp core for the 512-token levels, C = 256).
+//
+// Reference: /root/reference/sgmse/backbones/ncsnpp_utils/layerspp.py:82-86
+//   w = softmax_k( sum_c q[c,tok] k[c,key] / sqrt(C) );  h[tok] = sum_key w v[key]
+//
+// qkv is the token-major [N][S][3C] fp16 output of the fused q/k/v projection.  One CTA = one sample x 128 queries:
+//   phase 1  S = Q K^T   : Q [128 x 256] staged once by TMA (4 SWIZZLE_128B chunks of 64 channels), K streamed in blocks of
+//                          128 keys through a 2-stage ring, 16 UMMAs (M128 N128 K16) per block into TMEM columns
+//                          [128 b, 128 b + 128): all 512 keys of a query row sit in the 512 TMEM columns of its lane;
+//   phase 2  softmax     : thread = query row = TMEM lane; two passes over the lane (max, then exp2 / sum), the
+//                          un-normalised probabilities go to shared memory as the K-major fp16 A operand of phase 3;
+//   phase 3  O = P V     : V streamed in blocks of 64 keys through a 3-stage ring; V stays the way the projection wrote
+//                          it ([key][channel]) and is consumed as an MN-major B operand (instruction descriptor bit 16),
+//                          32 UMMAs (M128 N256 K16) into TMEM columns [0, 256) (the scores are dead by then);
+//   epilogue             : O / rowsum -> fp16 -> padded shared rows -> coalesced 16-byte stores.
+// The mma.sync kernel (attn.cu) stays for token counts that are not a multiple of 128 (the 32-token bottleneck) and for C = 128.
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace sgmse {
+
+CUtensorMap make_w_map(const void* p, int Cout, int Ktot, int block_n);   // 2-D fp16 [rows][cols], box {64 cols, block_n rows}, SW128
+
+namespace {
+
+constexpr int C = 256;
+constexpr int QB = 128;                 // queries per CTA (UMMA M)
+constexpr int KB = 128;                 // keys per S block (UMMA N of phase 1)
+constexpr int VB = 64;                  // keys per V block
+constexpr int MAX_S = 512;              // TMEM columns
+constexpr int CHUNK = QB * 128;         // one 64-channel (or 64-key) SWIZZLE_128B chunk of 128 rows: 16 KB
+constexpr int Q_BYTES = 4 * CHUNK;      // 64 KB
+constexpr int K_BYTES = 4 * CHUNK;      // 64 KB per 128-key block
+constexpr int V_CHUNK = VB * 128;       // 8 KB: 64 keys x 64 channels
+constexpr int V_BYTES = 4 * V_CHUNK;    // 32 KB per 64-key block
+constexpr int OFF_Q = 0, OFF_K0 = Q_BYTES, OFF_K1 = 2 * Q_BYTES;          // phase 1
+constexpr int OFF_P = 0;                                                   // phases 2-3: 8 chunks of 64 keys = 128 KB
+constexpr int OFF_V = 128 * 1024;                                          // phase 3: 3 x 32 KB
+constexpr int V_STAGES = 3;
+constexpr int OFF_BARS = OFF_V + V_STAGES * V_BYTES;                       // 224 KB
+constexpr int OFF_TMEM_PTR = OFF_BARS + 16 * 8;
+constexpr int DYN_BYTES = OFF_TMEM_PTR + 16 + 1024;
+static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
+constexpr int OUT_LD = C * 2 + 16;      // padded output row in bytes
+
+__device__ __forceinline__ uint64_t desc_k_major(uint32_t smem_addr) {     // K-major SWIZZLE_128B, 8-row atoms 1024 B apart
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// MN-major SWIZZLE_128B: an atom is 64 MN-elements (128 B) x 8 K-rows; `lbo` = byte distance between atoms along MN
+// (the next 64 channels), `sbo` = between atoms along K (the next 8 keys)
+__device__ __forceinline__ uint64_t desc_mn_major(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(KB >> 3) << 17) | ((uint32_t)(QB >> 4) << 24);               // M128 N128, A and B K-major
+constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(QB >> 4) << 24);   // M128 N256, B MN-major
+
+__global__ void __launch_bounds__(128, 1)
+attention_umma_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v,
+                      int S, float scale_log2e, __half* __restrict__ out, int vdesc_mode, int* dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* s_done = bars + 5;        // 1
+  uint64_t* v_full = bars + 6;        // 3
+  uint64_t* v_empty = bars + 9;       // 3
+  uint64_t* o_done = bars + 12;       // 1
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y, q0 = blockIdx.x * QB;
+  const int row0 = n * S;                                   // first token row of this sample in the [N*S][3C] view
+  const int nkb = S / KB, nvb = S / VB;
+  pdl_trigger();
+  if (tid == 0) {
+    tma_prefetch_desc(&map_qk); tma_prefetch_desc(&map_v);
+    for (int i = 0; i < 13; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem = *tmem_ptr;
+
+  // ---------------- phase 1: S = Q K^T (thread 0 feeds TMA and the tensor core) ----------------
+  if (tid == 0) {
+    mbar_arrive_expect_tx(q_full, Q_BYTES);
+    for (int c = 0; c < 4; ++c) tma_load_2d(smem + OFF_Q + c * CHUNK, &map_qk, q_full, c * 64, row0 + q0);
+    auto load_k = [&](int b) {
+      uint8_t* dst = smem + ((b & 1) ? OFF_K1 : OFF_K0);
+      mbar_arrive_expect_tx(&k_full[b & 1], K_BYTES);
+      for (int c = 0; c < 4; ++c) tma_load_2d(dst + c * CHUNK, &map_qk, &k_full[b & 1], C + c * 64, row0 + b * KB);
+    };
+    load_k(0);
+    if (nkb > 1) load_k(1);
+    mbar_wait(q_full, 0, dbg, 900);
+    for (int b = 0; b < nkb; ++b) {
+      mbar_wait(&k_full[b & 1], (b >> 1) & 1, dbg, 901 + (b & 1));
+      tc_fence_after();
+      const uint32_t qa = smem_u32(smem + OFF_Q), ka = smem_u32(smem + ((b & 1) ? OFF_K1 : OFF_K0));
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tmem + (uint32_t)(b * KB), desc_k_major(qa + c * CHUNK) + (uint64_t)(2 * k),
+                     desc_k_major(ka + c * CHUNK) + (uint64_t)(2 * k), IDESC_S, (c | k) != 0);
+      tc_commit(&k_empty[b & 1]);
+      // refill the OTHER stage (block b - 1's) now that this block's UMMAs are queued behind it: the wait for its
+      // retirement overlaps the tensor core working on block b
+      if (b >= 1 && b + 1 < nkb) {
+        mbar_wait(&k_empty[(b - 1) & 1], ((b - 1) >> 1) & 1, dbg, 903 + ((b - 1) & 1));
+        load_k(b + 1);
+      }
+    }
+    tc_commit(s_done);
+  }
+  __syncwarp();
+  mbar_wait(s_done, 0, dbg, 905);
+  tc_fence_after();
+
+  // V blocks 0..2 travel while the softmax runs (their slots overlap the second K stage, which is dead now)
+  auto load_v = [&](int vb) {
+    uint8_t* dst = smem + OFF_V + (vb % V_STAGES) * V_BYTES;
+    mbar_arrive_expect_tx(&v_full[vb % V_STAGES], V_BYTES);
+    for (int c = 0; c < 4; ++c) tma_load_2d(dst + c * V_CHUNK, &map_v, &v_full[vb % V_STAGES], 2 * C + c * 64, row0 + vb * VB);
+  };
+  if (tid == 0) for (int vb = 0; vb < V_STAGES && vb < nvb; ++vb) load_v(vb);
+
+  // ---------------- phase 2: softmax of TMEM lane `tid` over S columns ----------------
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  float mx = -INFINITY;
+  for (int g = 0; g < S / 32; ++g) {
+    uint32_t r[32];
+    tmem_ld_32x32(lane_addr + (uint32_t)(g * 32), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+  }
+  const float m2 = mx * scale_log2e;
+  float sum = 0.f;
+  const uint32_t prow = smem_u32(smem + OFF_P) + (uint32_t)(tid * 128);
+  for (int g = 0; g < S / 32; ++g) {
+    uint32_t r[32];
+    tmem_ld_32x32(lane_addr + (uint32_t)(g * 32), r);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float p0 = exp2f(fmaf(__uint_as_float(r[2 * i]), scale_log2e, -m2));
+      const float p1 = exp2f(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2e, -m2));
+      sum += p0 + p1;
+      const __half2 h = __floats2half2_rn(p0, p1);
+      pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    // keys [32 g, 32 g + 32) = four 16-byte pieces of chunk g / 2 of this row, piece index (2 (g & 1) + j) ^ (row & 7)
+    const uint32_t base = prow + (uint32_t)((g >> 1) * CHUNK);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t piece = (uint32_t)(((g & 1) * 4 + j) ^ (tid & 7));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + piece * 16), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                   "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+    }
+  }
+  fence_proxy_async_smem();                                 // P was written through the generic proxy, UMMA reads it through the async one
+  tc_fence_before();                                        // ... and every lane's TMEM loads precede the UMMAs that overwrite columns [0, 256)
+  __syncthreads();
+  tc_fence_after();
+
+  // ---------------- phase 3: O = P V ----------------
+  if (tid == 0) {
+    const uint32_t pa = smem_u32(smem + OFF_P);
+    const uint32_t lbo = vdesc_mode == 1 ? 1024u : (uint32_t)V_CHUNK, sbo = vdesc_mode == 1 ? (uint32_t)V_CHUNK : 1024u;
+    for (int vb = 0; vb < nvb; ++vb) {
+      const int st = vb % V_STAGES;
+      mbar_wait(&v_full[st], (vb / V_STAGES) & 1, dbg, 906 + st);
+      tc_fence_after();
+      const uint32_t va = smem_u32(smem + OFF_V + st * V_BYTES);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)                           // 16 keys per UMMA: A advances 32 B inside the row, B two 8-key atoms
+        tc_mma_f16(tmem, desc_k_major(pa + vb * CHUNK) + (uint64_t)(2 * k), desc_mn_major(va + k * 2048, lbo, sbo), IDESC_O,
+                   (vb | k) != 0);
+      tc_commit(&v_empty[st]);
+      if (vb >= 1 && vb + V_STAGES - 1 < nvb) {             // refill block vb - 1's stage while the tensor core works on block vb
+        const int ps = (vb - 1) % V_STAGES;
+        mbar_wait(&v_empty[ps], ((vb - 1) / V_STAGES) & 1, dbg, 909 + ps);
+        load_v(vb + V_STAGES - 1);
+      }
+    }
+    tc_commit(o_done);
+  }
+  __syncwarp();
+  mbar_wait(o_done, 0, dbg, 912);
+  tc_fence_after();
+
+  // ---------------- epilogue: normalise, fp16, coalesced store ----------------
+  const float inv = 1.f / sum;
+  uint8_t* orow = smem + OFF_P + tid * OUT_LD;              // P is dead (o_done): 128 padded rows of 528 B
+  for (int g = 0; g < C / 32; ++g) {
+    uint32_t r[32];
+    tmem_ld_32x32(lane_addr + (uint32_t)(g * 32), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 v;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * i]) * inv, __uint_as_float(r[8 * j + 2 * i + 1]) * inv);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(orow + g * 64 + j * 16) = v;
+    }
+  }
+  __syncthreads();
+  __half* obase = out + ((size_t)row0 + q0) * C;
+  for (int p = tid; p < QB * (C / 8); p += 128) {           // 16-byte pieces, row-major: consecutive threads -> consecutive addresses
+    const int r = p / (C / 8), c16 = p % (C / 8);
+    *reinterpret_cast<uint4*>(obase + (size_t)r * C + c16 * 8) = *reinterpret_cast<const uint4*>(smem + OFF_P + r * OUT_LD + c16 * 16);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+}  // namespace
+
+bool attention_umma_supported(const TensorDesc& qkv, const TensorDesc& out) {
+  const int S = qkv.H * qkv.W;
+  return qkv.dt == DT_F16 && out.dt == DT_F16 && out.C == C && qkv.C == 3 * C && S % QB == 0 && S >= QB && S <= MAX_S;
+}
+
+void launch_attention_umma(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int vdesc_mode, int* dbg) {
+  SG_CHECK(attention_umma_supported(qkv, out), "attention_umma: needs fp16, C = 256 and a token count in {128, 256, 384, 512}");
+  const int S = qkv.H * qkv.W;
+  const CUtensorMap mqk = make_w_map(qkv.p, qkv.N * S, 3 * C, QB);
+  const CUtensorMap mv = make_w_map(qkv.p, qkv.N * S, 3 * C, VB);
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_device(attr_devs))
+    CUDA_OK(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
+  launch_k(attention_umma_kernel, dim3(S / QB, qkv.N), dim3(128), (size_t)DYN_BYTES, st, mqk, mv, S,
+           1.4426950408889634f / sqrtf((float)C), (__half*)out.p, vdesc_mode, dbg);
+  CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace sgmse

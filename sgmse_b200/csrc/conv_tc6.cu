@@ -80,6 +80,7 @@ struct Tc6Params {
   int desc_mode;                 // 0: base_offset field 0; 1: base_offset = (start >> 7) & 7
   int mma_style;                 // 0: one elect + 4 UMMAs + commit per tap (mma_tap_elect); 1: one elect per UMMA
   int tma_poll;                  // 0: ordered issue loop; 1: two cursors (activations, weights) polled without blocking
+  int lean;                      // fused mode 1 only: 1 = producers with per-thread precomputed offsets / edge masks (same arithmetic)
   int role_map;                  // 0: warp 0 TMA, 1 MMA, 2-5 epilogue, 6-13 producers; 1: producers 0-7, epilogue 8-11, TMA 12, MMA 13
   int* dbg;
 #ifdef SGMSE_B200_PDL
@@ -624,6 +625,113 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       }
     };
     if (P.fused == 3) produce(std::true_type{}); else produce(std::false_type{});
+  } else if (P.fused && P.lean) {
+    // =========================== activation producers, LEAN form of fused mode 1 ==============================
+    // Same protocol, same loads, same fp32 arithmetic and rounding points as the mode-1 producers below (bit-identical), but
+    // everything that depends only on the thread is computed ONCE: the pixel offset of each of its 11 halo rows relative
+    // to the tile origin, its shared-memory cell (row j + 32 keeps the swizzle phase: + 4096 B per item) and bit masks of
+    // the rows that sit on the halo border.  Per tile only the `live` mask (border rows outside the image keep the conv's
+    // zero padding) and one base pointer remain; per vector: one 64-bit multiply-add, the load, the math, the store.
+    // The mode-1 loop spends ~125 SASS instructions per 8-channel vector, ~36 of them arithmetic (ncu: 216 M warp
+    // instructions per launch of the dominant shape against 82 M for the TMA-fed kernel).
+    const int pt = tid - 192;                      // 0..255
+    const int cv = pt & 7, r0 = pt >> 3;
+    const int Ct = P.C0 + P.C1;
+    const int nfused = P.seg_chunks[0];
+    int other_stages = 0;
+    for (int s = 1; s < P.nseg; ++s) other_stages += P.seg_chunks[s];
+    const int yy0 = r0 / HALO_W, xx0 = r0 - yy0 * HALO_W;   // halo row r0 + 32 j = (yy0 + 3 j + wraps, (xx0 + 2 j) mod 10)
+    uint32_t m_rows = 0, m_left = 0, m_right = 0, m_top = 0, m_bot = 0;
+#pragma unroll
+    for (int j = 0; j < PROD_ITEMS; ++j) {
+      const int row = r0 + 32 * j;
+      const int yy = row / HALO_W, xx = row - yy * HALO_W;
+      if (row < HALO_ROWS) {
+        m_rows |= 1u << j;
+        if (xx == 0) m_left |= 1u << j;
+        if (xx == HALO_W - 1) m_right |= 1u << j;
+        if (yy == 0) m_top |= 1u << j;
+        if (yy == HALO_H - 1) m_bot |= 1u << j;
+      }
+    }
+    const uint32_t cell0 = (uint32_t)(r0 * 128 + ((cv ^ (r0 & 7)) << 4));
+    int sa = 0; uint32_t pa = 0;
+    uint4 v[PROD_ITEMS];
+    uint32_t live_cur = 0, live_nxt = 0;
+    // tile decomposition (three integer divisions) once per tile, not once per chunk: (n, pixel index of the tile origin, live)
+    int t_n = 0, t_pix = 0; uint32_t t_live = 0;
+    auto decompose = [&](int tile) {
+      const int m_tile = tile / P.n_cblk;
+      const int n = m_tile / tiles_per_utt, rem = m_tile - n * tiles_per_utt;
+      const int ty = rem / P.tiles_w, tx = rem - ty * P.tiles_w;
+      const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+      t_n = n; t_pix = y0 * P.W + x0;
+      t_live = m_rows & ~((x0 == 0 ? m_left : 0u) | (x0 + TILE_W == P.W ? m_right : 0u) |
+                          (y0 == 0 ? m_top : 0u) | (y0 + TILE_H == P.H ? m_bot : 0u));
+    };
+    auto issue_loads = [&](int ch) {                 // chunk `ch` of the tile last passed to decompose()
+      live_nxt = t_live;
+      const int cg = ch * 64 + cv * 8;             // channel of the concatenated input
+      const __half* src; int Cs, cs;
+      if (cg < P.C0) { src = P.src0; Cs = P.C0; cs = cg; } else { src = P.src1; Cs = P.C1; cs = cg - P.C0; }
+      src += ((size_t)t_n * P.H * P.W + (size_t)t_pix) * Cs + cs;
+#pragma unroll
+      for (int j = 0; j < PROD_ITEMS; ++j) {
+        v[j] = make_uint4(0u, 0u, 0u, 0u);
+        const int tx = xx0 + 2 * j, wr = (tx >= HALO_W) + (tx >= 2 * HALO_W);        // 32 = 3 * 10 + 2
+        const int pix = (yy0 + 3 * j + wr - 1) * P.W + (tx - HALO_W * wr - 1);   // (yy - 1) * W + (xx - 1)
+        if ((live_nxt >> j) & 1u) v[j] = __ldg(reinterpret_cast<const uint4*>(src + (long long)pix * Cs));
+      }
+    };
+    float4 abn[4];
+    auto load_ab = [&](int ch) {                     // (a, b) of chunk `ch` of the tile last passed to decompose()
+      const float4* q = reinterpret_cast<const float4*>(P.ab + (size_t)t_n * Ct + ch * 64 + cv * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) abn[k] = __ldg(q + k);
+    };
+    if ((int)blockIdx.x < P.num_tiles) { decompose(blockIdx.x); load_ab(0); issue_loads(0); }
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      for (int ch = 0; ch < nfused; ++ch) {
+        float a[8], b[8];                          // (a, b)/2: the half argument of the tanh form of silu
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a[2 * k] = 0.5f * abn[k].x; b[2 * k] = 0.5f * abn[k].y; a[2 * k + 1] = 0.5f * abn[k].z; b[2 * k + 1] = 0.5f * abn[k].w;
+        }
+        // the last chunk of a tile prefetches for the CTA's NEXT tile: switch the decomposition there (the loads of this
+        // chunk are already in registers, its live mask in live_nxt)
+        const bool more = tile + (int)gridDim.x < P.num_tiles;
+        if (ch + 1 == nfused && more) decompose(tile + gridDim.x);
+        if (ch + 1 < nfused) load_ab(ch + 1); else if (more) load_ab(0);
+        live_cur = live_nxt;
+        mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 600 + sa);
+        const uint32_t cell = smem_u32(smem + sa * A_STRIDE) + cell0;
+#pragma unroll
+        for (int j = 0; j < PROD_ITEMS; ++j) {
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);    // out-of-image pixels: the conv's zero padding
+          if ((live_cur >> j) & 1u) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[j]);
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(h[k]);
+              ow[k] = silu_half_pair(fmaf(a[2 * k], f.x, b[2 * k]), fmaf(a[2 * k + 1], f.y, b[2 * k + 1]));
+            }
+          }
+          if ((m_rows >> j) & 1u) sts128(cell + 4096 * j, o);
+        }
+        fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
+        named_bar_sync(2, NUM_PROD_THREADS);
+        if (pt == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+        if (ch + 1 < nfused) issue_loads(ch + 1); else if (more) issue_loads(0);
+      }
+      for (int i = 0; i < other_stages; ++i) {     // stages of the TMA-fed segments: bystander arrival (see the header)
+        mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 610 + sa);
+        named_bar_sync(3, NUM_PROD_THREADS);
+        if (pt == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+      }
+    }
   } else if (P.fused) {
     // =========================== activation producers (warps 6..13): raw x -> silu(a*x+b) -> halo tile ======
     // 256 threads share one stage (11 x 128-bit vectors each, all loads in flight at once).  The loads of the NEXT
@@ -775,7 +883,7 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   out.slots = P.tiles_w * P.tiles_h;
   P.stats = out.stats; P.slots = out.slots;
   P.desc_mode = 0;
-  P.mma_style = g_tc6_mma_style; P.tma_poll = g_tc6_tma_poll; P.role_map = g_tc6_roles;
+  P.mma_style = g_tc6_mma_style; P.tma_poll = g_tc6_tma_poll; P.role_map = g_tc6_roles; P.lean = g_tc6_lean;
   P.dbg = dbg;
 #ifdef SGMSE_B200_PDL
   P.ablate = g_tc6_ablate;
@@ -809,6 +917,7 @@ thread_local int g_tc6_rings = 0;   // 0: 2 activation + 6 weight stages; 1: 3 +
 thread_local int g_tc6_mma_style = 0;
 thread_local int g_tc6_tma_poll = 0;
 thread_local int g_tc6_roles = 0;    // Tc6Params::role_map
+thread_local int g_tc6_lean = 0;     // Tc6Params::lean
 
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   if (a.gn_ab) {

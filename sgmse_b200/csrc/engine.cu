@@ -1513,7 +1513,7 @@ void enhance_ode(Engine& e, const float* wav, int B, int L, const sgmse_b200_ode
 static void activate(const sgmse_b200_engine& e) {
   const auto& o = e.opts;
   sgmse::g_tc_variant = o.tc_variant; sgmse::g_tc1_narrow = o.tc1_narrow; sgmse::g_tc6_rings = o.tc6_rings;
-  sgmse::g_tc6_mma_style = o.tc6_mma; sgmse::g_tc6_tma_poll = o.tc6_tma_poll; sgmse::g_tc6_roles = o.tc6_roles;
+  sgmse::g_tc6_mma_style = o.tc6_mma; sgmse::g_tc6_tma_poll = o.tc6_tma_poll; sgmse::g_tc6_roles = o.tc6_roles; sgmse::g_tc6_lean = o.tc6_lean;
   sgmse::g_tc6_ablate = o.tc6_ablate; sgmse::g_attn_variant = o.attn_variant; sgmse::g_fir_variant = o.fir_variant;
   sgmse::g_inconv_variant = o.inconv_variant; sgmse::g_outconv_variant = o.outconv_variant;
   sgmse::g_combine_variant = o.combine_variant; sgmse::g_gn_self = o.gn_self; sgmse::g_gnfin_variant = o.gnfin_variant;
@@ -1846,6 +1846,7 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "tc6_mma") { e->opts.tc6_mma = (int)value; clear_graphs(*e); }
   else if (k == "tc6_tma_poll") { e->opts.tc6_tma_poll = (int)value; clear_graphs(*e); }
   else if (k == "tc6_roles") { e->opts.tc6_roles = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_lean") { e->opts.tc6_lean = (int)value; clear_graphs(*e); }
   else if (k == "fir_variant") { e->opts.fir_variant = (int)value; clear_graphs(*e); }
   else if (k == "inconv_variant") { e->opts.inconv_variant = (int)value; clear_graphs(*e); }
   else if (k == "combine_variant") { e->opts.combine_variant = (int)value; clear_graphs(*e); }

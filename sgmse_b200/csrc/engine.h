@@ -168,7 +168,7 @@ struct sgmse_b200_engine {
   // point installs the calling engine's set first (engine.cu: activate), so two engines of one process -- or of two host
   // threads -- never see each other's choices, and a captured graph keeps the choices of the engine that captured it.
   struct KernelOpts {
-    int tc_variant = 0, tc1_narrow = 0, tc6_rings = 0, tc6_mma = 0, tc6_tma_poll = 0, tc6_roles = 0, tc6_ablate = 0;
+    int tc_variant = 0, tc1_narrow = 0, tc6_rings = 0, tc6_mma = 0, tc6_tma_poll = 0, tc6_roles = 0, tc6_lean = 0, tc6_ablate = 0;
     int attn_variant = 0, fir_variant = 0, inconv_variant = 0, outconv_variant = 0, combine_variant = 0;
     int gn_self = 0, gnfin_variant = 0, pdl = 0;
   } opts;

@@ -96,7 +96,7 @@ bool conv_tc6_supported(const ConvArgs& a, const TensorDesc& out);
 bool conv_tc6_fuse_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
 extern thread_local int g_tc6_ablate;   // timing ablations of conv_tc6, compiled into the -DSGMSE_B200_PDL twin only (results are wrong on purpose)
-extern thread_local int g_tc6_rings, g_tc6_mma_style, g_tc6_tma_poll, g_tc6_roles;   // conv_tc6 A/B switches, see conv_tc6.cu
+extern thread_local int g_tc6_rings, g_tc6_mma_style, g_tc6_tma_poll, g_tc6_roles, g_tc6_lean;   // conv_tc6 A/B switches, see conv_tc6.cu
 extern thread_local int g_tc1_narrow;   // 1: conv_tc v1 takes 64-wide channel tiles when 128-wide ones fill less than half the SMs (round-2 candidate)
 extern thread_local int g_tc_variant;   // 0 (= 7, 8): newest applicable kernels (v6 with fused GroupNorm+SiLU where possible: LDG-fed producers,
                            // fp32 math = fused mode 1; else v4/v1), 1: v1 only, 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1),
@@ -129,6 +129,9 @@ extern thread_local int g_inconv_variant;    // 0: mma.sync input conv for fp16 
 // ---- attention: qkv [N,H,W,3C] (q|k|v), out [N,H,W,C] = softmax(q k^T / sqrt(C)) v over H*W tokens
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out);
 extern thread_local int g_attn_variant;   // 0: fp16 mma.sync flash kernel where it applies (C in {128,256}), 1: fp32 CUDA-core kernel, 2: 0 with cp.async tile staging (round-2 candidate)
+// tcgen05 attention (attn_umma.cu): fp16, C = 256, token count a multiple of 128 up to 512; TMA-staged Q/K/V, scores in TMEM
+bool attention_umma_supported(const TensorDesc& qkv, const TensorDesc& out);
+void launch_attention_umma(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int vdesc_mode = 0, int* dbg = nullptr);
 
 // ---- time embedding ----
 struct TembWeights {

@@ -1,11 +1,14 @@
 """GPU parity tests: the CUDA engine (through the C-ABI) against the CPU oracle and the committed
 reference golden fixtures.  Run on the B200 box: ``pytest -m gpu``.
 
-Tolerances (stated, per north_star):
-  * mode fp32 (CUDA-core validation path): rel-L2 <= 2e-4 per forward vs the fp32 CPU oracle,
-    <= 1e-3 after an N=3 sampler run;
-  * mode fp16_tc (product path: fp16 activations, tcgen05 MMA with fp32 accumulation -- the same 10-bit
-    mantissa as the TF32 cuDNN path the reference itself takes on a GPU): rel-L2 <= 2e-2 per forward.
+Tolerances: every bound below is <= 2x the error MEASURED on a B200 (profiles/r02_parity.txt holds the measured values):
+  * mode fp32 (CUDA-core validation path): rel-L2 of a few 1e-6 per forward, per sampler run and per waveform vs the
+    fp32 CPU oracle / the reference fixtures;
+  * mode fp16_tc (product path: fp16 activation storage, tcgen05 MMA with fp32 accumulation -- the same 10-bit mantissa as
+    the TF32 cuDNN path the reference itself takes on a GPU): 2.1e-3 .. 2.7e-3 per forward, 1.1e-3 .. 1.7e-3 after 3 .. 12
+    sampler steps on the mid-size network, 2.0e-2 (34 dB SI-SDR) after the full N = 30 run of the full-size network
+    (tests/test_gpu_zz_next_rows.py; storage rounding random-walks through 60 evaluations: fp16_direct, which shares
+    nothing with fp16_tc but the storage format, lands at 34.3 dB, profiles/r02_parity.txt).
 """
 import math
 import os
@@ -54,8 +57,9 @@ def test_golden_forward_and_score(golden_dir, name, mode, tol):
     eng.load_state_dict(sd)
     x, y, t = (torch.from_numpy(z[k]).cuda() for k in ("x", "y", "t"))
     out = eng.dnn_forward(torch.cat([x, y], 1), t)
-    assert rel_l2(out, z["dnn_out"]) < tol
-    assert rel_l2(eng.score(x, y, t), z["score"]) < tol
+    e1, e2 = rel_l2(out, z["dnn_out"]), rel_l2(eng.score(x, y, t), z["score"])
+    print(f"golden {name} {mode}: dnn rel-L2 {e1:.3e}, score rel-L2 {e2:.3e}")
+    assert e1 < tol and e2 < tol
     eng.close()
 
 
@@ -72,7 +76,9 @@ def test_golden_pc_sampler(golden_dir, name, pred, corr):
     noise = torch.stack(draws).cuda()
     smp, nfe = eng.pc_sample(y, noise=noise, N=N, predictor=pred, corrector=corr, corrector_steps=1, snr=0.5)
     assert nfe == int(z[f"nfe_{pred}_{corr}"])
-    assert rel_l2(smp, z[f"pc_{pred}_{corr}"]) < 1e-3
+    e = rel_l2(smp, z[f"pc_{pred}_{corr}"])
+    print(f"golden {name} pc {pred}+{corr}: rel-L2 {e:.3e}")
+    assert e < 2e-5
     eng.close()
 
 
@@ -85,9 +91,11 @@ def test_golden_enhance_chain(golden_dir, name):
     B, N = wav.shape[0], 3
     draws = o_sde.make_noise((B, 1, 64, 64), o_sde.n_noise_draws(N, "reverse_diffusion", "ald", 1), seed=11)
     Y, norm = eng.analysis(wav.cuda())
-    assert rel_l2(Y, z["Y"]) < 1e-4
+    e_y = rel_l2(Y, z["Y"])
     xh = eng.enhance(wav.cuda(), noise=torch.stack(draws).cuda(), N=N)
-    assert rel_l2(xh, z["enh"]) < 2e-3
+    e_w = rel_l2(xh, z["enh"])
+    print(f"golden {name} chain: spectrogram rel-L2 {e_y:.3e}, waveform rel-L2 {e_w:.3e}")
+    assert e_y < 2e-5 and e_w < 2e-5
     # host-buffer entry point (H2D/D2H inside the call) gives the same result
     xh2 = eng.enhance(wav.pin_memory(), noise=torch.stack(draws).cuda(), N=N)
     assert torch.equal(xh.cpu(), xh2)
@@ -225,8 +233,10 @@ def test_per_module_taps_mid(mode, tol):
         got = eng.tap(name)
         worst.append((rel_l2(got, v), name))
     worst.sort(reverse=True)
+    e_out = rel_l2(out, ref)
+    print(f"per-module taps {mode}: worst {worst[0][1]} rel-L2 {worst[0][0]:.3e}, output rel-L2 {e_out:.3e}")
     assert worst[0][0] < tol, worst[:5]
-    assert rel_l2(out, ref) < tol
+    assert e_out < tol
     eng.close()
 
 
@@ -238,7 +248,8 @@ def full_sd():
     return o_w.make_state_dict(NetConfig.ncsnpp(), seed=0)
 
 
-@pytest.mark.parametrize("mode,tol,T", [("fp32", 2e-4, 128), ("fp16_tc", 2e-2, 128), ("fp16_tc", 2e-2, 512)])
+# measured: 4.02e-6, 2.57e-3, 2.15e-3
+@pytest.mark.parametrize("mode,tol,T", [("fp32", 8e-6, 128), ("fp16_tc", 5.2e-3, 128), ("fp16_tc", 4.3e-3, 512)])
 def test_full_size_forward(full_sd, mode, tol, T):
     """T=128 (1-s clip): the coarsest levels hold < 32 pixels and take the CUDA-core path even in fp16_tc mode;
     T=512 (the 4-s benchmark shape): every convolution must run on tcgen05."""
@@ -279,7 +290,7 @@ def test_full_size_48k_forward():
     out = eng.dnn_forward(x.cuda(), t.cuda())
     err = rel_l2(out, ref)
     print(f"full-size 48k forward fp16_tc: rel-L2 {err:.3e}")
-    assert err < 2e-2 and eng.counter("tc_convs_last_forward") > 0
+    assert err < 4.8e-3 and eng.counter("tc_convs_last_forward") > 0          # measured 2.41e-3
     eng.close()
 
 
@@ -298,7 +309,7 @@ def test_end_to_end_si_sdr(full_sd):
     got = eng.enhance(wav.cuda(), noise=torch.stack(draws).cuda(), N=N)[0].cpu().numpy()
     sdr = o_pipe.si_sdr(ref, got)
     print(f"end-to-end SI-SDR(oracle, engine) = {sdr:.1f} dB")
-    assert sdr > 35.0
+    assert sdr > 48.7                              # measured 54.7 dB; twice the error = -6 dB
     eng.close()
 
 
@@ -404,7 +415,8 @@ def test_full_size_sampler_properties(full_sd):
 MID_PAIRS = [("reverse_diffusion", "ald", 3), ("reverse_diffusion", "langevin", 3), ("none", "ald", 3),
              ("reverse_diffusion", "none", 3), ("reverse_diffusion", "ald", 12)]
 # measured on a B200 (profiles/r02_parity.txt), bounds <= 2x the measured error of the worst pair
-MID_TOL = {"fp32": dict(score=2e-4, pc=1e-3, enh=2e-3), "fp16_tc": dict(score=2e-2, pc=2e-2, enh=2e-2)}
+# measured: fp32 score 3.2e-6, pc <= 2.2e-6, chain 2.0e-6; fp16_tc score 2.48e-3, pc <= 1.67e-3, chain 1.66e-3 (SI-SDR 54.9 dB)
+MID_TOL = {"fp32": dict(score=6.4e-6, pc=4.4e-6, enh=4.1e-6), "fp16_tc": dict(score=5e-3, pc=3.4e-3, enh=3.4e-3)}
 
 
 @pytest.mark.parametrize("mode", ["fp32", "fp16_tc"])
@@ -467,7 +479,7 @@ def test_fp16_activation_range_is_kept_or_reported():
     out = eng.dnn_forward(x.cuda(), t.cuda())
     err = rel_l2(out, ref)
     print(f"fp16 range stress: block outputs up to {peak:.3g}, rel-L2 {err:.3e}, range events {eng.counter('fp16_range_events')}")
-    assert torch.isfinite(torch.view_as_real(out)).all() and eng.counter("fp16_range_events") == 0 and err < 2e-2
+    assert torch.isfinite(torch.view_as_real(out)).all() and eng.counter("fp16_range_events") == 0 and err < 4.1e-3   # measured 2.05e-3
     # (2) 8x more: block outputs ~1.6e5 > 65504 -> inf in storage; the statistics pass counts it, the host-buffer call refuses
     sd8 = _scale_resblock_convs(base, 8 * 4660.0)
     eng.load_state_dict(sd8)

@@ -161,12 +161,14 @@ def test_full_size_prior_draw_statistics(full_sd):
     eng.close()
 
 
-# Bounds of the N = 30 run.  Emulating the product mode's storage precision on the CPU oracle (conv operands and results
-# rounded to fp16, fp32 accumulation; 0.5-s clip, same 60 evaluations) moves the enhanced waveform by rel-L2 8.9e-3 =
-# 41 dB SI-SDR against the fp32 run: the sampler amplifies a per-evaluation error of a few 1e-3 about threefold.  The
-# product-mode bound leaves room for what the emulation lacks (tanh.approx SiLU, fp16 FIR arithmetic).
-FULL_N30_FP32_SDR, FULL_N30_FP32_REL = 45.0, 6e-3
-FULL_N30_TC_SDR, FULL_N30_TC_REL = 25.0, 6e-2
+# Bounds of the N = 30 run = twice the error measured on a B200 (profiles/r02_parity.txt): fp32 mode 91.6 dB / 2.66e-5;
+# product mode 34.2 dB / 1.97e-2.  The product-mode figure is the random walk of fp16 STORAGE rounding through 60 network
+# evaluations, not an arithmetic defect: mode fp16_direct (CUDA-core convolutions, exact expf SiLU, fp32 FIR -- nothing in
+# common with fp16_tc but the storage format) lands at 34.3 dB, the two fp16 pipelines are 48.8 dB from each other, and
+# single-approximation toggles move the figure by -3 .. +3 dB in either direction (tools/parity_decompose.py).  A CPU
+# emulation of fp16 storage on a 0.5-s clip had predicted 41 dB.
+FULL_N30_FP32_SDR, FULL_N30_FP32_REL = 85.6, 5.4e-5
+FULL_N30_TC_SDR, FULL_N30_TC_REL = 28.2, 4e-2
 
 
 def test_full_size_n30_against_the_reference_run(golden_dir):
@@ -213,7 +215,7 @@ def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
     got, n = eng.sb_sample(y.cuda(), sampler_type="ode", N=2)
     err = rel_l2(got, ref)
     print(f"full-size v2 SB-ODE (fp16_tc, edm preconditioning): rel-L2 {err:.3e}")
-    assert n == 50 and eng.counter("tc_convs_last_forward") > 0 and err < 3e-2
+    assert n == 50 and eng.counter("tc_convs_last_forward") > 0 and err < 4.4e-3           # measured 2.19e-3
     eng.close()
 
 
@@ -233,7 +235,7 @@ def test_full_size_ode_on_the_product_path(full_sd):
                                   return_stats=True)
     err = rel_l2(got, ref)
     print(f"full-size ODE (fp16_tc): nfe {nfe} (oracle {nfe_ref}), {st}, rel-L2 {err:.3e}")
-    assert st["status"] == 0 and abs(nfe - nfe_ref) <= 12 and err < 3e-2
+    assert st["status"] == 0 and abs(nfe - nfe_ref) <= 12 and err < 2.3e-3                  # measured 1.10e-3, nfe 32 = 32
     assert eng.counter("tc_convs_last_forward") > 0
     eng.close()
 
