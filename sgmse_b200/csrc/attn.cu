@@ -297,22 +297,19 @@ void run_tc(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int S) {
 }
 }  // namespace
 
-thread_local int g_attn_variant = 0;   // 0: tensor-core kernel where it applies, 1: always the fp32 CUDA-core kernel, 2: 0 with cp.async tile staging
+thread_local int g_attn_variant = 0;   // see kernels.h
 
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out) {
   const int C = out.C, S = qkv.H * qkv.W;
   SG_CHECK(qkv.C == 3 * C && C % 8 == 0, "attention: qkv must have 3C channels");
-  // 5: tcgen05 kernel (attn_umma.cu) where it applies (fp16, C = 256, 128 | tokens <= 512); 6: the same with the other reading
-  // of the MN-major descriptor strides (bring-up switch)
-  if ((g_attn_variant == 5 || g_attn_variant == 6) && attention_umma_supported(qkv, out)) {
-    launch_attention_umma(st, qkv, out, g_attn_variant == 6 ? 1 : 0, nullptr);
-    return;
-  }
+  // default: the tcgen05 kernel (attn_umma.cu) where it applies (fp16, C = 256, 128 | tokens <= 512: the three 512-token
+  // blocks of the 16 kHz network at T = 512); the mma.sync kernel below serves the 32-token bottleneck and C = 128
+  if (g_attn_variant == 0 && attention_umma_supported(qkv, out)) { launch_attention_umma(st, qkv, out, nullptr); return; }
   if (qkv.dt == DT_F16 && g_attn_variant == 2) {
     if (C == 256) { run_tc<256, true>(st, qkv, out, S); return; }
     if (C == 128) { run_tc<128, true>(st, qkv, out, S); return; }
   }
-  if (qkv.dt == DT_F16 && (g_attn_variant == 0 || g_attn_variant == 2 || g_attn_variant >= 5)) {
+  if (qkv.dt == DT_F16 && (g_attn_variant == 0 || g_attn_variant == 2 || g_attn_variant == 3)) {
     if (C == 256) { run_tc<256>(st, qkv, out, S); return; }
     if (C == 128) { run_tc<128>(st, qkv, out, S); return; }
   }

@@ -69,7 +69,7 @@ constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(C >> 3) << 17)
 
 __global__ void __launch_bounds__(128, 1)
 attention_umma_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v,
-                      int S, float scale_log2e, __half* __restrict__ out, int vdesc_mode, int* dbg) {
+                      int S, float scale_log2e, __half* __restrict__ out, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
@@ -185,7 +185,9 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
   // ---------------- phase 3: O = P V ----------------
   if (tid == 0) {
     const uint32_t pa = smem_u32(smem + OFF_P);
-    const uint32_t lbo = vdesc_mode == 1 ? 1024u : (uint32_t)V_CHUNK, sbo = vdesc_mode == 1 ? (uint32_t)V_CHUNK : 1024u;
+    // MN-major strides (verified on a B200, tools/check_attention.py: the opposite assignment gives rel-L2 0.7): leading byte
+    // offset = next 64 channels (the next TMA box), stride byte offset = next 8 keys
+    const uint32_t lbo = (uint32_t)V_CHUNK, sbo = 1024u;
     for (int vb = 0; vb < nvb; ++vb) {
       const int st = vb % V_STAGES;
       mbar_wait(&v_full[st], (vb / V_STAGES) & 1, dbg, 906 + st);
@@ -245,7 +247,7 @@ bool attention_umma_supported(const TensorDesc& qkv, const TensorDesc& out) {
   return qkv.dt == DT_F16 && out.dt == DT_F16 && out.C == C && qkv.C == 3 * C && S % QB == 0 && S >= QB && S <= MAX_S;
 }
 
-void launch_attention_umma(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int vdesc_mode, int* dbg) {
+void launch_attention_umma(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int* dbg) {
   SG_CHECK(attention_umma_supported(qkv, out), "attention_umma: needs fp16, C = 256 and a token count in {128, 256, 384, 512}");
   const int S = qkv.H * qkv.W;
   const CUtensorMap mqk = make_w_map(qkv.p, qkv.N * S, 3 * C, QB);
@@ -254,7 +256,7 @@ void launch_attention_umma(cudaStream_t st, const TensorDesc& qkv, TensorDesc& o
   if (first_use_on_device(attr_devs))
     CUDA_OK(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
   launch_k(attention_umma_kernel, dim3(S / QB, qkv.N), dim3(128), (size_t)DYN_BYTES, st, mqk, mv, S,
-           1.4426950408889634f / sqrtf((float)C), (__half*)out.p, vdesc_mode, dbg);
+           1.4426950408889634f / sqrtf((float)C), (__half*)out.p, dbg);
   CUDA_OK(cudaGetLastError());
 }
 

@@ -625,6 +625,130 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       }
     };
     if (P.fused == 3) produce(std::true_type{}); else produce(std::false_type{});
+  } else if (P.fused && P.lean >= 2) {
+    // =========================== activation producers, STRIP form of fused mode 1 =============================
+    // Same protocol, loads, fp32 arithmetic and rounding points as mode 1 (bit-identical).  A thread owns one 8-channel
+    // vector column cv of one halo COLUMN xx and every third halo row: (cv, xx, ph) with rows yy = ph + 3 i, i = 0..11
+    // (8 x 10 x 3 = 240 of the 256 producer threads; row 33 only exists for ph = 0).  Then
+    //   * global addresses advance by a constant 3 W Cs elements from item to item,
+    //   * the shared-memory row is p + 30 i with p = 10 ph + xx: the swizzle phase (p + 6 i) & 7 has period 4 in i, so four
+    //     per-thread cell registers + compile-time immediates address all twelve stores,
+    //   * a left / right image border kills ALL items of the threads of column 0 / 9 (a per-tile, per-thread flag), the top /
+    //     bottom border only item 0 / 11 of the ph = 0 threads: items 1..10 carry no predicate at all.
+    // ncu on the dominant shape: mode 1 217 M warp instructions / 890-920 k cycles, the first lean form 187 M / 790 k, the
+    // TMA-fed kernel without producers 82 M / 606 k -- the producers' instruction stream is what the MMA warp waits for.
+    // lean 3: the same with the half2 GroupNorm + SiLU arithmetic of fused mode 3 (split-mean table ab16, 7 instead of 9
+    // instructions per channel pair; NOT bit-identical to the fp32 form, same error level: tc_variant 10 in the tests).
+    constexpr int STRIP_ITEMS = 12;
+    auto strip = [&](auto h2tag) {
+    constexpr bool H2 = decltype(h2tag)::value;
+    const int pt = tid - 192;                      // 0..255
+    const int cv = pt & 7, p = pt >> 3;            // p = 10 ph + xx
+    const bool active = p < 30;
+    const int ph = p / HALO_W, xx = p - ph * HALO_W;
+    const bool has11 = active && ph == 0;          // halo row 33 = item 11 of the ph = 0 threads
+    const int Ct = P.C0 + P.C1;
+    const int nfused = P.seg_chunks[0];
+    int other_stages = 0;
+    for (int s = 1; s < P.nseg; ++s) other_stages += P.seg_chunks[s];
+    uint32_t sw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sw[k] = (uint32_t)(p * 128 + ((cv ^ ((p + 6 * k) & 7)) << 4));
+    int sa = 0; uint32_t pa = 0;
+    uint4 v[STRIP_ITEMS];
+    // per tile: bit 0 = all items outside the image (or idle thread), bit 1 = item 0 outside, bit 2 = item 11 outside
+    uint32_t fl_cur = 0, fl_nxt = 0, t_fl = 0;
+    int t_n = 0; long long t_pix = 0;
+    auto decompose = [&](int tile) {
+      const int m_tile = tile / P.n_cblk;
+      const int n = m_tile / tiles_per_utt, rem = m_tile - n * tiles_per_utt;
+      const int ty = rem / P.tiles_w, tx = rem - ty * P.tiles_w;
+      const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+      t_n = n;
+      t_pix = (long long)(y0 - 1 + ph) * P.W + (x0 - 1 + xx);       // pixel of item 0 (never loaded when it lies outside the image)
+      const bool dead = !active || (xx == 0 && x0 == 0) || (xx == HALO_W - 1 && x0 + TILE_W == P.W);
+      t_fl = (dead ? 1u : 0u) | ((ph == 0 && y0 == 0) ? 2u : 0u) | ((ph == 0 && y0 + TILE_H == P.H) ? 4u : 0u);
+    };
+    auto issue_loads = [&](int ch) {                 // chunk `ch` of the tile last passed to decompose()
+      fl_nxt = t_fl;
+      if (t_fl & 1u) return;
+      const int cg = ch * 64 + cv * 8;             // channel of the concatenated input
+      const __half* src; int Cs, cs;
+      if (cg < P.C0) { src = P.src0; Cs = P.C0; cs = cg; } else { src = P.src1; Cs = P.C1; cs = cg - P.C0; }
+      src += ((long long)t_n * P.H * P.W + t_pix) * Cs + cs;
+      const long long stride = (long long)3 * P.W * Cs;             // three image rows down
+      if (!(t_fl & 2u)) v[0] = __ldg(reinterpret_cast<const uint4*>(src));
+#pragma unroll
+      for (int i = 1; i < STRIP_ITEMS - 1; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(src + i * stride));
+      if (has11 && !(t_fl & 4u)) v[11] = __ldg(reinterpret_cast<const uint4*>(src + 11 * stride));
+    };
+    float4 abn[4];
+    auto load_ab = [&](int ch) {                     // (a, b) of chunk `ch` of the tile last passed to decompose()
+      const float4* q = H2 ? reinterpret_cast<const float4*>(P.ab16 + (((size_t)t_n * Ct + ch * 64 + cv * 8) >> 1))
+                           : reinterpret_cast<const float4*>(P.ab + (size_t)t_n * Ct + ch * 64 + cv * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) abn[k] = __ldg(q + k);
+    };
+    if ((int)blockIdx.x < P.num_tiles) { decompose(blockIdx.x); load_ab(0); issue_loads(0); }
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      for (int ch = 0; ch < nfused; ++ch) {
+        float4 c4[4];                              // fp32: (a, b)/2 of two channels, the half argument of the tanh form of silu;
+#pragma unroll                                     // half2: {m_hi, m_lo, a/2, beta/2} of a channel pair
+        for (int k = 0; k < 4; ++k) {
+          c4[k] = abn[k];
+          if (!H2) { c4[k].x *= 0.5f; c4[k].y *= 0.5f; c4[k].z *= 0.5f; c4[k].w *= 0.5f; }
+        }
+        const bool more = tile + (int)gridDim.x < P.num_tiles;
+        if (ch + 1 == nfused && more) decompose(tile + gridDim.x);
+        if (ch + 1 < nfused) load_ab(ch + 1); else if (more) load_ab(0);
+        fl_cur = fl_nxt;
+        mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 600 + sa);
+        const uint32_t stage = smem_u32(smem + sa * A_STRIDE);
+        const uint32_t cellk[4] = {stage + sw[0], stage + sw[1], stage + sw[2], stage + sw[3]};
+        auto act = [&](const uint4& x) {
+          uint4 o;
+          const uint32_t* xw = reinterpret_cast<const uint32_t*>(&x);
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (H2) {
+              const uint4 q = *reinterpret_cast<const uint4*>(&c4[k]);
+              ow[k] = gn_silu_h2(xw[k], q.x, q.y, q.z, q.w);
+            } else {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xw[k]));
+              ow[k] = silu_half_pair(fmaf(c4[k].x, f.x, c4[k].y), fmaf(c4[k].z, f.y, c4[k].w));
+            }
+          }
+          return o;
+        };
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);             // out-of-image pixels: the conv's zero padding
+        if (active) {
+          if (fl_cur & 1u) {
+#pragma unroll
+            for (int i = 0; i < STRIP_ITEMS - 1; ++i) sts128(cellk[i & 3] + (uint32_t)(30 * 128 * i), zero);
+            if (has11) sts128(cellk[3] + (uint32_t)(30 * 128 * 11), zero);
+          } else {
+            sts128(cellk[0], (fl_cur & 2u) ? zero : act(v[0]));
+#pragma unroll
+            for (int i = 1; i < STRIP_ITEMS - 1; ++i) sts128(cellk[i & 3] + (uint32_t)(30 * 128 * i), act(v[i]));    // halo row p + 30 i
+            if (has11) sts128(cellk[3] + (uint32_t)(30 * 128 * 11), (fl_cur & 4u) ? zero : act(v[11]));
+          }
+        }
+        fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
+        named_bar_sync(2, NUM_PROD_THREADS);
+        if (pt == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+        if (ch + 1 < nfused) issue_loads(ch + 1); else if (more) issue_loads(0);
+      }
+      for (int i = 0; i < other_stages; ++i) {     // stages of the TMA-fed segments: bystander arrival (see the header)
+        mbar_wait(&a_empty[sa], pa ^ 1, P.dbg, 610 + sa);
+        named_bar_sync(3, NUM_PROD_THREADS);
+        if (pt == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+      }
+    }
+    };
+    if (P.lean == 3 && P.ab16) strip(std::true_type{}); else strip(std::false_type{});
   } else if (P.fused && P.lean) {
     // =========================== activation producers, LEAN form of fused mode 1 ==============================
     // Same protocol, same loads, same fp32 arithmetic and rounding points as the mode-1 producers below (bit-identical), but

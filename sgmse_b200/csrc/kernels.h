@@ -128,10 +128,10 @@ extern thread_local int g_inconv_variant;    // 0: mma.sync input conv for fp16 
 
 // ---- attention: qkv [N,H,W,3C] (q|k|v), out [N,H,W,C] = softmax(q k^T / sqrt(C)) v over H*W tokens
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out);
-extern thread_local int g_attn_variant;   // 0: fp16 mma.sync flash kernel where it applies (C in {128,256}), 1: fp32 CUDA-core kernel, 2: 0 with cp.async tile staging (round-2 candidate)
+extern thread_local int g_attn_variant;   // 0: tcgen05 kernel (attn_umma.cu) where it applies, else the fp16 mma.sync flash kernel (C in {128,256}); 1: fp32 CUDA-core kernel; 2: mma.sync with cp.async tile staging; 3: mma.sync (the round-1 default)
 // tcgen05 attention (attn_umma.cu): fp16, C = 256, token count a multiple of 128 up to 512; TMA-staged Q/K/V, scores in TMEM
 bool attention_umma_supported(const TensorDesc& qkv, const TensorDesc& out);
-void launch_attention_umma(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int vdesc_mode = 0, int* dbg = nullptr);
+void launch_attention_umma(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out, int* dbg = nullptr);
 
 // ---- time embedding ----
 struct TembWeights {

@@ -71,7 +71,11 @@ class BatchedEnhancer:
         self.device = device
 
     def __call__(self, waves: Sequence[torch.Tensor], seed: int = 0, sr: Optional[int] = None,
-                 resample: Optional[Callable[[torch.Tensor, int, int], torch.Tensor]] = None, **sampler_kw):
+                 resample: Optional[Callable[[torch.Tensor, int, int], torch.Tensor]] = None, utt_base: int = 0,
+                 noise_for: Optional[Callable[[int, int], torch.Tensor]] = None, **sampler_kw):
+        """``utt_base``: first noise id of this call (a pipeline that feeds several calls keeps the ids of a run distinct).
+        ``noise_for(clip_index, padded_frames)`` -> c64 [draws, 1, 1, F, Tpad]: injected noise per clip instead of the
+        in-kernel Philox generator (parity tests against the reference's file loop)."""
         eng = self.engine
         target_sr = int(eng.cfg.sr)
         clips = []
@@ -93,7 +97,10 @@ class BatchedEnhancer:
                 assert Y.shape[-1] == tp
                 specs.append(Y)
                 norms.append(norm)
-            X, _ = eng.pc_sample(torch.cat(specs, dim=0), seed=seed, utt_offset=plan.utt_id[idx[0]], **sampler_kw)
+            kw = dict(sampler_kw)
+            if noise_for is not None:
+                kw["noise"] = torch.cat([torch.as_tensor(noise_for(i, tp)).to(self.device) for i in idx], dim=1)
+            X, _ = eng.pc_sample(torch.cat(specs, dim=0), seed=seed, utt_offset=utt_base + plan.utt_id[idx[0]], **kw)
             for j, i in enumerate(idx):                     # per-clip back end (enhancement.py:95-98)
                 outs[i] = eng.synthesis(X[j:j + 1], norms[j], int(clips[i].numel()))[0]
-        return outs, plan.utt_id
+        return outs, [utt_base + i for i in plan.utt_id]

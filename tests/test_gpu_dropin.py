@@ -183,3 +183,27 @@ def test_in_training_evaluation_follows_the_ema_swap():
     finally:
         sgmse_b200.uninstall(model)
         eng.close()
+
+
+def test_batched_file_service_against_the_reference_file_loop():
+    """SURVEY.md §8f-2 against the REFERENCE (not against the engine itself): clips of three different lengths -- two padded
+    frame counts, so two buckets -- through the unmodified reference's per-file loop (enhancement.py:58-99 on the CPU, injected
+    noise) and through BatchedEnhancer with the same per-clip noise; every clip individually, in both engine modes."""
+    import sgmse_b200
+    from sgmse_b200 import BatchedEnhancer, engine_from_score_model
+    model = make_model(seed=7)
+    g = torch.Generator().manual_seed(8)
+    lengths = [4000, 1900, 3100, 2000]                      # 126, 60, 97, 63 frames -> padded to 128, 64, 128, 64
+    clips = [0.1 * torch.randn(n, generator=g) * (1.0 + 0.5 * i) for i, n in enumerate(lengths)]
+    nd = o_sde.n_noise_draws(N, "reverse_diffusion", "ald", 1)
+    draws = {i: o_sde.make_noise((1, 1, 64, 128 if lengths[i] > 2048 else 64), nd, seed=40 + i) for i in range(len(clips))}
+    refs = [reference_run(model, c[None], draws[i])[2] for i, c in enumerate(clips)]
+    for mode, tol in (("fp32", 1e-5), ("fp16_tc", 2.2e-3)):
+        eng = engine_from_score_model(model, mode=mode, max_batch=2)
+        outs, ids = BatchedEnhancer(eng)(clips, seed=0, N=N, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.5,
+                                         noise_for=lambda i, tp: torch.stack(draws[i]))
+        errs = [rel_l2(o, r) for o, r in zip(outs, refs)]
+        print(f"batched file service vs the reference file loop, {mode}: per-clip waveform rel-L2 " + ", ".join(f"{e:.2e}" for e in errs))
+        assert all(o.shape[0] == n for o, n in zip(outs, lengths)) and sorted(ids) == [0, 1, 2, 3]
+        assert max(errs) < tol
+        eng.close()

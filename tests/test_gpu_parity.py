@@ -342,10 +342,24 @@ def test_tc_kernel_variants_agree(full_sd):
     # the two fp32-math producers evaluate the same expression on the same values: bit-identical
     assert torch.equal(outs[0], outs[9])
     # A/B switches of conv_tc6: ring depths, UMMA issue style, TMA issue loop -- all bit-identical to the default
-    for key, val in (("tc6_rings", 1), ("tc6_mma", 1), ("tc6_tma_poll", 1), ("tc6_roles", 1)):
+    for key, val in (("tc6_rings", 1), ("tc6_mma", 1), ("tc6_tma_poll", 1), ("tc6_roles", 1), ("tc6_lean", 1), ("tc6_lean", 2)):
         eng.set_option(key, val)
         assert torch.equal(eng.dnn_forward(x, t), outs[0]), key
         eng.set_option(key, 0)
+    # the half2 form of the strip producers: same error level as the other fused forms
+    eng.set_option("tc6_lean", 3)
+    e3 = rel_l2(eng.dnn_forward(x, t), outs[1])
+    eng.set_option("tc6_lean", 0)
+    print(f"tc6_lean=3 (half2 strip producers) vs v1: rel-L2 {e3:.3e}")
+    assert e3 < 5e-3
+    # attention: tcgen05 kernel (default) vs mma.sync (3) vs fp32 CUDA-core (1)
+    eng.set_option("attn_variant", 3)
+    o3 = eng.dnn_forward(x, t)
+    eng.set_option("attn_variant", 1)
+    o1 = eng.dnn_forward(x, t)
+    eng.set_option("attn_variant", 0)
+    print(f"attention kernels, network output: tcgen05 vs fp32 CUDA-core rel-L2 {rel_l2(outs[0], o1):.3e}, mma.sync vs fp32 {rel_l2(o3, o1):.3e}")
+    assert rel_l2(outs[0], o1) < 3e-3 and rel_l2(o3, o1) < 3e-3
     eng.set_option("tc_variant", 0)
     eng.close()
 

@@ -376,7 +376,7 @@ def test_plain_c_client_on_the_product_path(tmp_path):
 
 
 # ---- opt-in kernel candidates staged for round 2 (DESIGN.md §3 worklist / §9b): not part of the default suite -------------
-CANDIDATES = [("outconv_variant", 3, 0.0), ("inconv_variant", 2, 0.0), ("attn_variant", 2, 0.0), ("combine_variant", 1, 0.0),
+CANDIDATES = [("outconv_variant", 3, 0.0), ("inconv_variant", 2, 0.0), ("attn_variant", 2, 1e-3), ("combine_variant", 1, 0.0),
               ("tc1_narrow", 1, 0.0), ("gn_self", 1, 0.0), ("gnfin_variant", 1, 0.0), ("fir_variant", 2, 2e-3)]
 
 

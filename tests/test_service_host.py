@@ -1,5 +1,6 @@
 """Host logic of the batched file service (sgmse_b200/service.py) with a stand-in engine: bucketing by
 padded frame count, batch cutting, noise-id assignment, per-clip front/back end, resampling hook.  No GPU."""
+import os
 import types
 
 import pytest
@@ -91,3 +92,37 @@ def test_langevin_corrector_is_sampled_clip_by_clip():
     eng.calls.clear()
     BatchedEnhancer(eng, device="cpu")(waves, seed=1, corrector="ald")
     assert [c[1][0] for c in eng.calls if c[0] == "pc_sample"] == [3]
+
+
+def test_directory_enhancer_mirrors_the_enhancement_py_file_loop(tmp_path):
+    """sgmse_b200/files.py: glob order and relative output paths of enhancement.py:38-60,100-103, resampling to the model's rate
+    (:65-66), reader / GPU / writer windows, noise ids continuing across windows; WAV I/O through scipy (no soundfile here)."""
+    import numpy as np
+    from scipy.io import wavfile
+    from sgmse_b200.files import DirectoryEnhancer, list_audio_files, read_audio
+    src, dst = tmp_path / "noisy", tmp_path / "enhanced"
+    (src / "spk1").mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    specs = {"b.wav": (16000, 8000, np.float32), "a.wav": (16000, 8100, np.int16), os.path.join("spk1", "c.wav"): (8000, 4000, np.float32)}
+    for name, (sr, n, dt) in specs.items():
+        x = 0.1 * rng.standard_normal(n)
+        wavfile.write(str(src / name), sr, (x * 32767).astype(np.int16) if dt == np.int16 else x.astype(np.float32))
+    files = list_audio_files(str(src))
+    assert [os.path.relpath(f, str(src)) for f in files] == ["a.wav", "b.wav", os.path.join("spk1", "c.wav")]
+    y, sr = read_audio(files[0])
+    assert y.shape == (1, 8100) and sr == 16000 and y.dtype == torch.float32 and y.abs().max() < 1.0
+    eng = FakeEngine(max_batch=2)
+    outs, ids = DirectoryEnhancer(eng, window=2, io_workers=2, device="cpu")(str(src), str(dst), seed=5, N=30)
+    assert [os.path.relpath(o, str(dst)) for o in outs] == ["a.wav", "b.wav", os.path.join("spk1", "c.wav")]
+    assert sorted(ids) == [0, 1, 2] and ids[2] == 2                     # window 1 = {a, b}, window 2 = {c}: ids continue
+    lens = []
+    for o in outs:
+        sr_o, x = wavfile.read(o)
+        assert sr_o == 16000 and x.dtype == np.float32
+        lens.append(len(x))
+    assert lens == [8100, 8000, 8000]                                   # c.wav: 4000 samples at 8 kHz -> 8000 at the model's 16 kHz
+    assert [c[1] for c in eng.calls if c[0] == "analysis"] == [(1, 8100), (1, 8000), (1, 8000)] or \
+           sorted(c[1] for c in eng.calls if c[0] == "analysis") == [(1, 8000), (1, 8000), (1, 8100)]
+    with pytest.raises(ValueError, match="mono"):
+        wavfile.write(str(src / "st.wav"), 16000, np.zeros((100, 2), np.float32))
+        DirectoryEnhancer(eng, device="cpu")(str(src), str(dst))

@@ -1,5 +1,5 @@
-"""Bring-up gate of the tcgen05 attention kernel (csrc/attn_umma.cu): the full-size network at the benchmark shape with
-attn_variant 5 / 6 (the two readings of the MN-major descriptor strides) against the mma.sync kernel (attn_variant 0) --
+"""Gate of the tcgen05 attention kernel (csrc/attn_umma.cu, attn_variant 0 = default): the full-size network at the benchmark
+shape against the mma.sync kernel (attn_variant 3, the round-1 default) and the fp32 CUDA-core kernel (attn_variant 1) --
 outputs of the three 512-token attention blocks (oracle tap names m21, m23, m50) and of the whole network.
 
     python tools/check_attention.py [--batch 2]
@@ -37,15 +37,15 @@ def rel(p, q):
     return (torch.linalg.vector_norm((p - q).float()) / torch.linalg.vector_norm(q.float())).item()
 
 
-ref_out, ref_taps = run(0)
+ref_out, ref_taps = run(3)
 ok = False
-for v in (5, 6):
+for v in (0, 1):
     try:
         out, taps = run(v)
         errs = {k: rel(taps[k], ref_taps[k]) for k in taps}
         e = rel(out, ref_out)
         good = all(torch.isfinite(taps[k]).all().item() for k in taps) and max(errs.values()) < 5e-3 and e < 5e-3
-        ok = ok or good
+        ok = ok or (good and v == 0)
         print(f"attn_variant={v}: " + ", ".join(f"{k} rel-L2 {errs[k]:.3e}" for k in errs) + f"; network output rel-L2 {e:.3e} -> {'OK' if good else 'MISMATCH'}", flush=True)
     except RuntimeError as ex:
         print(f"attn_variant={v}: FAILED {ex}", flush=True)

@@ -18,7 +18,7 @@ import torch
 from sgmse_b200 import Engine, EngineConfig
 from sgmse_b200.synth import synthetic_blob
 
-CANDIDATES = [("outconv_variant", 3, 0.0), ("inconv_variant", 2, 0.0), ("attn_variant", 2, 0.0), ("combine_variant", 1, 0.0),
+CANDIDATES = [("outconv_variant", 3, 0.0), ("inconv_variant", 2, 0.0), ("attn_variant", 2, 1e-3), ("combine_variant", 1, 0.0),
               ("tc1_narrow", 1, 0.0), ("gn_self", 1, 0.0), ("gnfin_variant", 1, 0.0), ("fir_variant", 2, 2e-3)]
 SMALL = dict(nf=32, ch_mult=(1, 2, 2), image_size=64, num_res_blocks=1, attn_resolutions=(16,), n_fft=126, hop_length=32)
 CASES = [("small nf=32 [2,64,64]", EngineConfig(mode="fp16_tc", max_batch=2, use_graphs=False, **SMALL), (2, 2, 64, 64)),
