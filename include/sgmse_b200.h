@@ -224,7 +224,11 @@ int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, 
  * "fir_variant", "inconv_variant", "outconv_variant", "combine_variant", "tc1_narrow", "gn_self", "gnfin_variant", "tc6_*") are
  * state of THIS engine: every entry point installs the calling engine's selection before it launches anything, so another
  * engine of the same process (another device, another host thread) never sees them, and a captured sampler graph keeps
- * the selection it was captured with; 0 is always the verified default.  No environment variable changes kernel
+ * the selection it was captured with.  Value 0 always selects the current default kernel; since round 2 these are
+ * the gated round-2 kernels (strip-mapped conv_tc6 producers, cp.async / prefetched small-end kernels, half2 FIR-up, folded
+ * gn_finalize, tcgen05 attention), and the round-1 kernels keep a number of their own: tc6_lean 4, fir_variant 3,
+ * outconv_variant 4, inconv_variant 3, combine_variant 2, tc1_narrow / gn_self / gnfin_variant 2, attn_variant 3
+ * (tests/test_gpu_zz_next_rows.py::test_round1_kernels_agree_with_the_defaults).  No environment variable changes kernel
  * selection.  "tc_variant" 2 / 3 / 5 (superseded convolution generations), "tc6_ablate" and "pdl" (0/1: programmatic
  * dependent launch between the kernels of the launch sequence) exist only in the lab twin built with -DSGMSE_B200_PDL
  * (libsgmse_b200_pdl.so, counter "pdl_compiled" = 1); the product library refuses them. */

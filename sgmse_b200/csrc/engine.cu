@@ -1510,13 +1510,29 @@ void enhance_ode(Engine& e, const float* wav, int B, int L, const sgmse_b200_ode
 // C-ABI
 // ================================================================================================
 // Install the calling engine's kernel selection into the thread-local switches the launch helpers read.
+// Option value 0 always means "the current default kernel".  Round 2 made the gated round-2 candidates the defaults (bit-identical
+// to the round-1 kernels except fir_variant: half2 FIR-up, rel-L2 8e-4 per forward); the round-1 kernels stay selectable under a
+// new number.  The launch helpers keep their internal numbering, the translation lives here:
+//   tc6_lean        0 = strip-mapped producers (internal 2) | 1 = first lean form | 3 = strip + half2 math | 4 = round-1 mode-1 producers
+//   fir_variant     0 = all loads in flight + half2 FIR-up (internal 2) | 1 = expf silu, fp32 FIR | 3 = round-1 kernel
+//   outconv_variant 0 = cp.async staging (internal 3) | 1 = CUDA-core | 2 = fused GroupNorm | 4 = round-1 kernel
+//   inconv_variant  0 = prefetched A fragments (internal 2) | 1 = CUDA-core | 3 = round-1 kernel
+//   combine_variant 0 = thread per 8-channel vector (internal 1) | 2 = round-1 kernel
+//   tc1_narrow / gn_self / gnfin_variant   0 = on (internal 1) | 2 = off (round 1)
+static int xl(int v, int new_default, int old_number) { return v == 0 ? new_default : (v == old_number ? 0 : v); }
 static void activate(const sgmse_b200_engine& e) {
   const auto& o = e.opts;
-  sgmse::g_tc_variant = o.tc_variant; sgmse::g_tc1_narrow = o.tc1_narrow; sgmse::g_tc6_rings = o.tc6_rings;
-  sgmse::g_tc6_mma_style = o.tc6_mma; sgmse::g_tc6_tma_poll = o.tc6_tma_poll; sgmse::g_tc6_roles = o.tc6_roles; sgmse::g_tc6_lean = o.tc6_lean;
-  sgmse::g_tc6_ablate = o.tc6_ablate; sgmse::g_attn_variant = o.attn_variant; sgmse::g_fir_variant = o.fir_variant;
-  sgmse::g_inconv_variant = o.inconv_variant; sgmse::g_outconv_variant = o.outconv_variant;
-  sgmse::g_combine_variant = o.combine_variant; sgmse::g_gn_self = o.gn_self; sgmse::g_gnfin_variant = o.gnfin_variant;
+  sgmse::g_tc_variant = o.tc_variant; sgmse::g_tc6_rings = o.tc6_rings;
+  sgmse::g_tc6_mma_style = o.tc6_mma; sgmse::g_tc6_tma_poll = o.tc6_tma_poll; sgmse::g_tc6_roles = o.tc6_roles;
+  sgmse::g_tc6_ablate = o.tc6_ablate; sgmse::g_attn_variant = o.attn_variant;
+  sgmse::g_tc6_lean = xl(o.tc6_lean, 2, 4);
+  sgmse::g_fir_variant = xl(o.fir_variant, 2, 3);
+  sgmse::g_outconv_variant = xl(o.outconv_variant, 3, 4);
+  sgmse::g_inconv_variant = xl(o.inconv_variant, 2, 3);
+  sgmse::g_combine_variant = xl(o.combine_variant, 1, 2);
+  sgmse::g_tc1_narrow = xl(o.tc1_narrow, 1, 2);
+  sgmse::g_gn_self = xl(o.gn_self, 1, 2);
+  sgmse::g_gnfin_variant = xl(o.gnfin_variant, 1, 2);
   sgmse::g_pdl = o.pdl;
 }
 
@@ -1801,6 +1817,7 @@ long long sgmse_b200_workspace_bytes(sgmse_b200_engine* e, int B, int F, int T) 
   // host-only dry run of the launch sequence (no CUDA call): exercises the whole layer walk
   try {
     SG_CHECK(e && B > 0, "bad argument");
+    activate(*e);
     Arena saved = e->arena;
     e->arena = Arena{};
     e->arena.dry = true;

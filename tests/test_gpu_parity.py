@@ -342,7 +342,7 @@ def test_tc_kernel_variants_agree(full_sd):
     # the two fp32-math producers evaluate the same expression on the same values: bit-identical
     assert torch.equal(outs[0], outs[9])
     # A/B switches of conv_tc6: ring depths, UMMA issue style, TMA issue loop -- all bit-identical to the default
-    for key, val in (("tc6_rings", 1), ("tc6_mma", 1), ("tc6_tma_poll", 1), ("tc6_roles", 1), ("tc6_lean", 1), ("tc6_lean", 2)):
+    for key, val in (("tc6_rings", 1), ("tc6_mma", 1), ("tc6_tma_poll", 1), ("tc6_roles", 1), ("tc6_lean", 1), ("tc6_lean", 4)):
         eng.set_option(key, val)
         assert torch.equal(eng.dnn_forward(x, t), outs[0]), key
         eng.set_option(key, 0)
