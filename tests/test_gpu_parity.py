@@ -50,7 +50,8 @@ def small_engine(kind, mode, **kw):
 # supports 16/32-channel layers
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["ncsnpp_small", "ncsnpp48k_small"])
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("fp16_direct", 2e-2)])
+# measured: fp32 1.8e-6 / 9.1e-7, fp16_direct 2.4e-3 / 1.1e-3 (ncsnpp_small / ncsnpp48k_small)
+@pytest.mark.parametrize("mode,tol", [("fp32", 3.7e-6), ("fp16_direct", 4.9e-3)])
 def test_golden_forward_and_score(golden_dir, name, mode, tol):
     z, sd = load_golden(golden_dir, name)
     eng = small_engine(name, mode)
@@ -78,7 +79,7 @@ def test_golden_pc_sampler(golden_dir, name, pred, corr):
     assert nfe == int(z[f"nfe_{pred}_{corr}"])
     e = rel_l2(smp, z[f"pc_{pred}_{corr}"])
     print(f"golden {name} pc {pred}+{corr}: rel-L2 {e:.3e}")
-    assert e < 2e-5
+    assert e < 1.9e-6                              # measured <= 9.4e-7 over the eight cases
     eng.close()
 
 
@@ -95,7 +96,7 @@ def test_golden_enhance_chain(golden_dir, name):
     xh = eng.enhance(wav.cuda(), noise=torch.stack(draws).cuda(), N=N)
     e_w = rel_l2(xh, z["enh"])
     print(f"golden {name} chain: spectrogram rel-L2 {e_y:.3e}, waveform rel-L2 {e_w:.3e}")
-    assert e_y < 2e-5 and e_w < 2e-5
+    assert e_y < 4.3e-7 and e_w < 1.3e-6            # measured 2.1e-7 / 6.3e-7
     # host-buffer entry point (H2D/D2H inside the call) gives the same result
     xh2 = eng.enhance(wav.pin_memory(), noise=torch.stack(draws).cuda(), N=N)
     assert torch.equal(xh.cpu(), xh2)
@@ -211,7 +212,8 @@ MID_N = NetConfig.ncsnpp(nf=64, ch_mult=(1, 2, 2), image_size=64, attn_resolutio
 MID_E = dict(nf=64, ch_mult=(1, 2, 2), image_size=64, attn_resolutions=(16,), num_res_blocks=1, n_fft=126, hop_length=32)
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("fp16_direct", 2e-2), ("fp16_tc", 2e-2)])
+# measured (worst module, pyr2): 3.6e-6, 2.53e-3, 2.53e-3
+@pytest.mark.parametrize("mode,tol", [("fp32", 7.2e-6), ("fp16_direct", 5.1e-3), ("fp16_tc", 5.1e-3)])
 def test_per_module_taps_mid(mode, tol):
     sd = o_w.make_state_dict(MID_N, seed=5)
     eng = Engine(EngineConfig(mode=mode, **MID_E))

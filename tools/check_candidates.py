@@ -19,7 +19,7 @@ from sgmse_b200 import Engine, EngineConfig
 from sgmse_b200.synth import synthetic_blob
 
 # (option, number of the ROUND-1 kernel, tolerance against the current default = 0)
-CANDIDATES = [("outconv_variant", 4, 0.0), ("inconv_variant", 3, 0.0), ("attn_variant", 3, 1e-3), ("combine_variant", 2, 0.0),
+CANDIDATES = [("outconv_variant", 4, 0.0), ("inconv_variant", 3, 0.0), ("attn_variant", 3, 2e-3), ("combine_variant", 2, 0.0),
               ("tc1_narrow", 2, 0.0), ("gn_self", 2, 0.0), ("gnfin_variant", 2, 0.0), ("fir_variant", 3, 2e-3), ("tc6_lean", 4, 0.0),
               ("tc6_lean", 1, 0.0)]
 SMALL = dict(nf=32, ch_mult=(1, 2, 2), image_size=64, num_res_blocks=1, attn_resolutions=(16,), n_fft=126, hop_length=32)
