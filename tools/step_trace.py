@@ -20,10 +20,13 @@ from sgmse_b200.synth import synthetic_blob, synthetic_speech
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--lanes", type=int, default=0, help="0 = engine default (2)")
 ap.add_argument("--opt", action="append", default=[])
 a = ap.parse_args()
 eng = Engine(EngineConfig(mode="fp16_tc", max_batch=16, use_graphs=True))
 eng.load_blob(synthetic_blob(eng, 0))
+if a.lanes:
+    eng.set_option("lanes", a.lanes)
 for kv in a.opt:
     k, v = kv.split("=")
     eng.set_option(k, int(v))
@@ -52,7 +55,7 @@ for i in range(a.steps):
 torch.cuda.synchronize()
 proc.terminate()
 ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(a.steps)]
-print("options", a.opt)
+print("options", a.opt, "lanes", a.lanes or "default")
 print("ms per step:", " ".join(f"{m:.1f}" for m in ms))
 cum = 0.0
 for i, m in enumerate(ms):
