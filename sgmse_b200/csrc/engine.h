@@ -156,7 +156,7 @@ struct sgmse_b200_engine {
   // launch sequences on forked streams, so that the HBM-bound kernels of one lane (GroupNorm apply, FIR, PC
   // update) overlap the tensor-bound convolutions of the other.  A lane is a shadow engine: it shares the
   // packed weights (owns_weights == false) and owns its workspace, state and staging buffers.
-  int num_lanes = 2;
+  int num_lanes = 1;                          // round 2: one lane is faster under the power cap (profiles/r02_step_trace.txt: 1 158 vs 1 189 ms per step)
   bool owns_weights = true;
   std::vector<sgmse_b200_engine*> lanes;      // lanes[0] == this
   std::vector<cudaStream_t> lane_streams;     // lane_streams[0] unused (lane 0 runs on the caller's stream)
