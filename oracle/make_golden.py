@@ -270,6 +270,12 @@ def golden_mid_tc(name="ncsnpp_mid"):
             smp, nfe = model.get_pc_sampler(pred, corr, y, N=N, corrector_steps=1, snr=0.5)()
         out[f"pc_{pred}_{corr}_N{N}"] = _np(smp)
         out[f"nfe_{pred}_{corr}_N{N}"] = np.int64(nfe)
+    # BASELINE config 4 sampler settings (README.md:43: dereverberation checkpoint, --N 50 --snr 0.33): 100 evaluations
+    draws = sde_mod.make_noise((B, 1, F, T), sde_mod.n_noise_draws(50, "reverse_diffusion", "ald", 1), seed=9)
+    with refshim.injected_noise(draws):
+        smp, nfe = model.get_pc_sampler("reverse_diffusion", "ald", y, N=50, corrector_steps=1, snr=0.33)()
+    out["pc_dereverb_N50_snr033"] = _np(smp)
+    out["nfe_dereverb_N50_snr033"] = np.int64(nfe)
     L, N = 4000, 6
     wav = 0.1 * torch.randn(B, L, generator=g)
     enh = []

@@ -432,7 +432,7 @@ MID_PAIRS = [("reverse_diffusion", "ald", 3), ("reverse_diffusion", "langevin", 
              ("reverse_diffusion", "none", 3), ("reverse_diffusion", "ald", 12)]
 # measured on a B200 (profiles/r02_parity.txt), bounds <= 2x the measured error of the worst pair
 # measured: fp32 score 3.2e-6, pc <= 2.2e-6, chain 2.0e-6; fp16_tc score 2.48e-3, pc <= 1.67e-3, chain 1.66e-3 (SI-SDR 54.9 dB)
-MID_TOL = {"fp32": dict(score=6.4e-6, pc=4.4e-6, enh=4.1e-6), "fp16_tc": dict(score=5e-3, pc=3.4e-3, enh=3.4e-3)}
+MID_TOL = {"fp32": dict(score=6.4e-6, pc=4.4e-6, enh=4.1e-6, n50=1e-5), "fp16_tc": dict(score=5e-3, pc=3.4e-3, enh=3.6e-3, n50=6e-3)}
 
 
 @pytest.mark.parametrize("mode", ["fp32", "fp16_tc"])
@@ -455,6 +455,12 @@ def test_golden_mid_sampler_and_chain(golden_dir, mode):
         e = rel_l2(smp, z[f"pc_{pred}_{corr}_N{N}"])
         report.append(f"{pred}+{corr} N={N} {e:.3e}")
         assert e < tol["pc"], report
+    # BASELINE config 4 sampler settings (README.md:43: N = 50, snr 0.33 -> 100 evaluations)
+    draws = o_sde.make_noise(tuple(y.shape), o_sde.n_noise_draws(50, "reverse_diffusion", "ald", 1), seed=9)
+    smp, nfe = eng.pc_sample(y, noise=torch.stack(draws).cuda(), N=50, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.33)
+    e50 = rel_l2(smp, z["pc_dereverb_N50_snr033"])
+    report.append(f"dereverb settings N=50 snr 0.33 {e50:.3e}")
+    assert nfe == int(z["nfe_dereverb_N50_snr033"]) == 100 and e50 < tol["n50"], report
     wav = torch.from_numpy(z["wav"])
     draws = o_sde.make_noise((2, 1, 64, 128), o_sde.n_noise_draws(6, "reverse_diffusion", "ald", 1), seed=11)
     xh = eng.enhance(wav.cuda(), noise=torch.stack(draws).cuda(), N=6).cpu()

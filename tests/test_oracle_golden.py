@@ -251,6 +251,12 @@ def test_mid_size_fixture_is_reproduced_by_the_oracle(golden_dir):
                                          predictor=pred, corrector=corr, corrector_steps=1, snr=0.5, noise=draws)
             assert nfe == int(z[f"nfe_{pred}_{corr}_N{N}"])
             assert _rel(smp, z[f"pc_{pred}_{corr}_N{N}"]) < 5e-4, (pred, corr, N)
+        # BASELINE config 4 sampler settings (N = 50, snr 0.33)
+        draws = sde_mod.make_noise(tuple(y.shape), sde_mod.n_noise_draws(50, "reverse_diffusion", "ald", 1), seed=9)
+        smp, nfe = sde_mod.pc_sample(lambda a, b, c: ncsnpp.score(sd, cfg, a, b, c), y, sde_mod.OUVE(), N=50,
+                                     predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.33, noise=draws)
+        assert nfe == int(z["nfe_dereverb_N50_snr033"]) == 100
+        assert _rel(smp, z["pc_dereverb_N50_snr033"]) < 5e-4
     wav = torch.from_numpy(z["wav"])
     draws = sde_mod.make_noise((2, 1, 64, 128), sde_mod.n_noise_draws(6, "reverse_diffusion", "ald", 1), seed=11)
     xh = pipeline.enhance(sd, cfg, spec_mod.SpecConfig(n_fft=126, hop_length=32), sde_mod.OUVE(), wav, draws, N=6)
