@@ -122,12 +122,12 @@ def pick_cpu_threads(forward):
     """Thread sweep on the FULL shape of the workload: one warm + one timed score-network evaluation on a
     [1, 2, 256, 512] input per candidate count, ascending; the fastest wins.  More threads are NOT faster for this
     batch-1 network (MKL-DNN convolutions: 16 threads 3.75 s, 64 threads 5.3 s, 128 threads 73 s per evaluation on the
-    128-CPU host of the B200 box, profiles/r02_bench_reference_arm.json), so the sweep stops once a candidate is more than
-    twice as slow as the best so far.  The table goes into the JSON line (`cpu_baseline.thread_sweep_s_per_forward`)."""
+    128-CPU host of the B200 box, profiles/r02_bench_reference_arm.json), so the sweep stops once two candidates in a row are
+    slower than the best so far (or one is more than twice as slow): the 128-thread point alone would cost 2.5 minutes.  The table goes into the JSON line (`cpu_baseline.thread_sweep_s_per_forward`)."""
     if _CPU["threads"] is not None:
         return _CPU["threads"]
     import torch
-    sweep, best = {}, (float("inf"), 1)
+    sweep, best, worse = {}, (float("inf"), 1), 0
     for c in _thread_candidates():
         torch.set_num_threads(c)
         forward()
@@ -136,10 +136,12 @@ def pick_cpu_threads(forward):
         dt = time.perf_counter() - t0
         sweep[str(c)] = round(dt, 3)
         if dt < best[0]:
-            best = (dt, c)
-        elif dt > 2.0 * best[0]:
-            sweep["stopped_after"] = c
-            break
+            best, worse = (dt, c), 0
+        else:
+            worse += 1
+            if worse >= 2 or dt > 2.0 * best[0]:       # two counts in a row slower than the best: the curve has turned
+                sweep["stopped_after"] = c
+                break
     _CPU.update(threads=best[1], sweep=sweep, forward_s=best[0])
     torch.set_num_threads(best[1])
     return best[1]

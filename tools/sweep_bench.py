@@ -33,6 +33,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--micro-batch", type=int, default=16)
 ap.add_argument("--N", type=int, default=30)
+ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="Engine.set_option (e.g. pdl=1 with SGMSE_B200_PDL=1)")
 a = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -42,6 +43,9 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 eng = Engine(EngineConfig(mode="fp16_tc", max_batch=a.micro_batch, use_graphs=True), device=dev)
 eng.load_blob(broadcast_weights(synthetic_blob(eng, 0) if rank == 0 else None, eng.weights_numel(), dev))
+for kv in a.opt:
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 L = 64000
 kw = dict(N=a.N, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.5)
 
@@ -84,7 +88,7 @@ for B in [int(b) for b in a.batches.split(",")]:
             "higher_is_better": True, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
             "config": {"workload": "SGMSE+ NCSN++ (VoiceBank-DEMAND config), 16 kHz, 4-s clips, PC reverse_diffusion+ald N=%d snr 0.5" % a.N,
                        "global_batch": B, "per_rank_batch": [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)],
-                       "micro_batch": a.micro_batch, "parallelism": f"dp{world} (fixed global batch sharded, no data-path collective)",
+                       "micro_batch": a.micro_batch, **({"options": list(a.opt)} if a.opt else {}), "parallelism": f"dp{world} (fixed global batch sharded, no data-path collective)",
                        "timed": "host-buffer entry point (pinned wav in / out), CUDA events, max over ranks"},
             "latency_ms": round(ms_step, 3), "rtf": round(ms_step * 1e-3 / (B * 4.0), 6), "clocks": clk}
     if B == 1 and rank == 0:
