@@ -33,6 +33,7 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 # the LAB twin: the product sources + LAB_SOURCES with -DSGMSE_B200_PDL (programmatic dependent launch, timing ablations of
 # conv_tc6, the superseded convolution generations); never loaded unless SGMSE_B200_PDL=1
 PDL_LIBNAME = "libsgmse_b200_pdl.so"
+PRODUCT_DEFS: list = []                # see DESIGN.md section 3 (programmatic dependent launch)
 
 
 def lib_path(pdl: bool = False) -> str:
@@ -45,7 +46,7 @@ def _digest(extra: str = "") -> str:
     for f in SOURCES + LAB_SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(ARCH + CFLAGS).encode())
+    h.update(" ".join(ARCH + CFLAGS + PRODUCT_DEFS).encode())
     return h.hexdigest()
 
 
@@ -56,7 +57,7 @@ def build(force: bool = False, verbose: bool = False, pdl: bool = False) -> str:
     stamp = os.path.join(LIBDIR, "build_pdl.stamp" if pdl else "build.stamp")
     dig = _digest("pdl" if pdl else "")
     out = lib_path(pdl)
-    defs = ["-DSGMSE_B200_PDL"] if pdl else []
+    defs = ["-DSGMSE_B200_PDL", "-DSGMSE_B200_LAB"] if pdl else PRODUCT_DEFS
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dig:
         return out
     objdir = os.path.join(LIBDIR, "obj_pdl" if pdl else "obj")

@@ -78,6 +78,7 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 extern thread_local int g_pdl;              // runtime switch (option "pdl"); refused unless the library was built with SGMSE_B200_PDL
 bool pdl_compiled();
+bool lab_compiled();
 
 #ifdef __CUDACC__
 // Launch of a PDL-aware kernel: plain <<<>>> unless g_pdl, else cudaLaunchKernelEx with the programmatic stream

@@ -460,7 +460,7 @@ void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* db
   }
   if (a.residual) SG_CHECK(a.residual->C == out.C && a.residual->dt == DT_F16, "conv_tc: residual mismatch");
   if (a.gn_ab) {                                                      // the engine only asks for fusion when it applies
-#ifdef SGMSE_B200_PDL        // the superseded generations (conv_tc2/3/5) live in the lab twin only (build.py)
+#ifdef SGMSE_B200_LAB        // the superseded generations (conv_tc2/3/5) live in the lab twin only (build.py)
     if (g_tc_variant == 5) { launch_conv_tc5(st, a, out, dbg); return; }
 #endif
     launch_conv_tc6(st, a, out, dbg);
@@ -468,7 +468,7 @@ void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* db
   }
   if ((g_tc_variant == 0 || g_tc_variant >= 6) && conv_tc6_supported(a, out)) { launch_conv_tc6(st, a, out, dbg); return; }
   if ((g_tc_variant == 0 || g_tc_variant >= 4) && conv_tc4_supported(a, out)) { launch_conv_tc4(st, a, out, dbg); return; }
-#ifdef SGMSE_B200_PDL
+#ifdef SGMSE_B200_LAB
   if (g_tc_variant == 3 && conv_tc3_supported(a, out)) { launch_conv_tc3(st, a, out, dbg); return; }
   if (g_tc_variant != 1 && conv_tc2_supported(a, out)) { launch_conv_tc2(st, a, out, dbg); return; }
 #endif

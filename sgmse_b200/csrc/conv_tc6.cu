@@ -83,7 +83,7 @@ struct Tc6Params {
   int lean;                      // fused mode 1 only: 1 = producers with per-thread precomputed offsets / edge masks (same arithmetic)
   int role_map;                  // 0: warp 0 TMA, 1 MMA, 2-5 epilogue, 6-13 producers; 1: producers 0-7, epilogue 8-11, TMA 12, MMA 13
   int* dbg;
-#ifdef SGMSE_B200_PDL
+#ifdef SGMSE_B200_LAB
   // ABLATIONS (twin library only, option "tc6_ablate"; results are WRONG on purpose, only the time is of interest):
   //   bit 0: weight tiles are loaded for a CTA's first tile only, later tiles reuse whatever the ring holds -> what the
   //          288 KB of weight tiles per 256-pixel tile cost (the L2 -> SM hypothesis of DESIGN.md §3)
@@ -223,7 +223,7 @@ __device__ __forceinline__ uint32_t silu_half_pair(float hz0, float hz1) {
   return yu;
 }
 
-#ifdef SGMSE_B200_PDL
+#ifdef SGMSE_B200_LAB
 #define TC6_ABLATE_RAW_COPY (P.ablate & 2)
 #else
 #define TC6_ABLATE_RAW_COPY false
@@ -402,7 +402,7 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             for (int tap = 0; tap < ntap; ++tap) {
               const int kb = P.seg_kb0[s] + tap * chunks + ch;
               mbar_wait(&w_empty[sb], pb ^ 1, P.dbg, 150 + sb);
-#ifdef SGMSE_B200_PDL
+#ifdef SGMSE_B200_LAB
               if ((P.ablate & 1) && tile != (int)blockIdx.x) {
                 mbar_arrive(&w_full[sb]);            // ablation: no load, the stage keeps its previous bytes
               } else
@@ -1009,7 +1009,7 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   P.desc_mode = 0;
   P.mma_style = g_tc6_mma_style; P.tma_poll = g_tc6_tma_poll; P.role_map = g_tc6_roles; P.lean = g_tc6_lean;
   P.dbg = dbg;
-#ifdef SGMSE_B200_PDL
+#ifdef SGMSE_B200_LAB
   P.ablate = g_tc6_ablate;
 #endif
   auto kern = conv_tc6_kernel<A_STAGES, B_STAGES>;

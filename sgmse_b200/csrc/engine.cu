@@ -437,7 +437,7 @@ struct Fwd {
     // Fused path (conv_tc5): the 3x3 convs read the RAW tensor and apply GroupNorm+SiLU on the way into shared
     // memory, so the gn_apply pass (one read + one write of the tensor) and its buffer disappear.
     const bool fuse_ok = e.cfg.mode == SGMSE_B200_MODE_FP16_TC && (g_tc_variant == 0 || g_tc_variant == 5 || g_tc_variant >= 7);
-#ifdef SGMSE_B200_PDL
+#ifdef SGMSE_B200_LAB
     auto shape_ok = g_tc_variant == 5 ? conv_tc5_shape_ok : conv_tc6_fuse_shape_ok;
 #else
     auto shape_ok = conv_tc6_fuse_shape_ok;
@@ -1850,7 +1850,7 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "tc_variant") {
     // changes which intermediate buffers a forward needs: drop cached workspace sizes, graphs and shadow lanes
     // 2, 3, 5 = the superseded kernel generations conv_tc2 / conv_tc3 / conv_tc5: compiled into the lab twin only
-    SG_CHECK((value != 2 && value != 3 && value != 5) || sgmse::pdl_compiled(),
+    SG_CHECK((value != 2 && value != 3 && value != 5) || sgmse::lab_compiled(),
              "tc_variant %lld selects a superseded kernel generation that exists in the lab twin library only "
              "(python -m sgmse_b200.build --pdl, SGMSE_B200_PDL=1)", value);
     e->opts.tc_variant = (int)value;
@@ -1871,7 +1871,7 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "gn_self") { e->opts.gn_self = (int)value; clear_graphs(*e); }
   else if (k == "gnfin_variant") { e->opts.gnfin_variant = (int)value; clear_graphs(*e); }
   else if (k == "tc6_ablate") {
-    SG_CHECK(value == 0 || sgmse::pdl_compiled(), "option 'tc6_ablate' exists in the -DSGMSE_B200_PDL twin library only");
+    SG_CHECK(value == 0 || sgmse::lab_compiled(), "option 'tc6_ablate' exists in the lab twin library only");
     e->opts.tc6_ablate = (int)value;
     clear_graphs(*e);
   }
@@ -1914,6 +1914,7 @@ long long sgmse_b200_get_counter(const sgmse_b200_engine* e, const char* key) {
   if (k == "graph_launches") return e->graph_launches;
   if (k == "cached_graphs") return (long long)e->graphs.size();
   if (k == "pdl_compiled") return sgmse::pdl_compiled() ? 1 : 0;
+  if (k == "lab_compiled") return sgmse::lab_compiled() ? 1 : 0;
   if (k == "pdl") return e->opts.pdl;
   if (k == "workspace_bytes") return (long long)e->arena.cap;
   if (k == "weights_bytes") return (long long)e->weights_bytes;

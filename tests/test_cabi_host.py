@@ -256,10 +256,13 @@ def test_kernel_selection_is_per_engine_and_the_product_library_has_no_lab_kerne
     launch are refused by the product library, a selection made on one engine is invisible to another."""
     from sgmse_b200 import Engine, EngineConfig
     a, b = Engine(EngineConfig(max_batch=1)), Engine(EngineConfig(max_batch=1))
-    if a.counter("pdl_compiled") == 0:
+    if a.counter("lab_compiled") == 0:
         for v in (2, 3, 5):
             with pytest.raises(RuntimeError, match="lab twin"):
                 a.set_option("tc_variant", v)
+        with pytest.raises(RuntimeError, match="lab twin"):
+            a.set_option("tc6_ablate", 1)
+    if a.counter("pdl_compiled") == 0:
         with pytest.raises(RuntimeError, match="SGMSE_B200_PDL"):
             a.set_option("pdl", 1)
     a.set_option("tc_variant", 6)

@@ -328,7 +328,7 @@ def test_tc_kernel_variants_agree(full_sd):
     # 6: halo-tile kernel (conv_tc6) without fusion
     # 9: conv_tc6 fused with the TMA-fed raw tile transformed in place (fp32 math); 10: the same with half2 math on the
     # split-mean coefficient table; 0 = default = conv_tc6 fused with LDG-fed producers (fp32 math)
-    lab = eng.counter("pdl_compiled") == 1           # the superseded generations 2 / 3 / 5 exist in the lab twin only
+    lab = eng.counter("lab_compiled") == 1           # the superseded generations 2 / 3 / 5 exist in the lab twin only
     variants = (1, 2, 3, 4, 5, 6, 9, 10, 0) if lab else (1, 4, 6, 9, 10, 0)
     if not lab:
         with pytest.raises(RuntimeError, match="lab twin"):
