@@ -123,7 +123,7 @@ def pick_cpu_threads(forward):
     [1, 2, 256, 512] input per candidate count, ascending; the fastest wins.  More threads are NOT faster for this
     batch-1 network (MKL-DNN convolutions: 16 threads 3.75 s, 64 threads 5.3 s, 128 threads 73 s per evaluation on the
     128-CPU host of the B200 box, profiles/r02_bench_reference_arm.json), so the sweep stops once two candidates in a row are
-    slower than the best so far (or one is more than twice as slow): the 128-thread point alone would cost 2.5 minutes.  The table goes into the JSON line (`cpu_baseline.thread_sweep_s_per_forward`)."""
+    slower than the best so far or one is more than 1.25x slower: the 128-thread point alone would cost 2.5 minutes.  The table goes into the JSON line (`cpu_baseline.thread_sweep_s_per_forward`)."""
     if _CPU["threads"] is not None:
         return _CPU["threads"]
     import torch
@@ -139,7 +139,7 @@ def pick_cpu_threads(forward):
             best, worse = (dt, c), 0
         else:
             worse += 1
-            if worse >= 2 or dt > 2.0 * best[0]:       # two counts in a row slower than the best: the curve has turned
+            if worse >= 2 or dt > 1.25 * best[0]:      # the curve has turned (3.7 s at 48 threads, 5.1 s at 64, 69 s at 128)
                 sweep["stopped_after"] = c
                 break
     _CPU.update(threads=best[1], sweep=sweep, forward_s=best[0])
