@@ -229,7 +229,7 @@ int sgmse_b200_get_tap(sgmse_b200_engine* e, const char* name, float* out_host, 
  * gn_finalize, tcgen05 attention), and the round-1 kernels keep a number of their own: tc6_lean 4, fir_variant 3,
  * outconv_variant 4, inconv_variant 3, combine_variant 2, tc1_narrow / gn_self / gnfin_variant 2, attn_variant 3
  * (tests/test_gpu_zz_next_rows.py::test_round1_kernels_agree_with_the_defaults).  No environment variable changes kernel
- * selection.  "tc_variant" 2 / 3 / 5 (superseded convolution generations), "tc6_ablate" and "pdl" (0/1: programmatic
+ * selection.  "tc_variant" 2 / 3 / 5 / 9 / 10 and "tc6_lean" 1 / 4 (superseded convolution generations and producer forms), "tc6_ablate" and "pdl" (0/1: programmatic
  * dependent launch between the kernels of the launch sequence) exist only in the lab twin built with -DSGMSE_B200_PDL
  * (libsgmse_b200_pdl.so, counter "pdl_compiled" = 1); the product library refuses them. */
 int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value);

@@ -536,6 +536,7 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       if (++as == 2) { as = 0; as_phase ^= 1; }
     }
     if (e == 0) tma_store_wait_all0();
+#ifdef SGMSE_B200_LAB   // superseded producer forms (A/B record): TMA-fed in-place producers (fused modes 2 / 3)
   } else if (P.fused >= 2) {
     // =========================== activation producers (warps 6..13), in place: TMA-landed raw tile -> silu(a*x+b) ===
     // thread = (8-channel vector cv, rows (pt >> 3) + 32 j): its (a, b) live in registers, prefetched one chunk ahead
@@ -625,6 +626,9 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       }
     };
     if (P.fused == 3) produce(std::true_type{}); else produce(std::false_type{});
+#else
+  } else if (false) {
+#endif
   } else if (P.fused && P.lean >= 2) {
     // =========================== activation producers, STRIP form of fused mode 1 =============================
     // Same protocol, loads, fp32 arithmetic and rounding points as mode 1 (bit-identical).  A thread owns one 8-channel
@@ -749,6 +753,7 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     }
     };
     if (P.lean == 3 && P.ab16) strip(std::true_type{}); else strip(std::false_type{});
+#ifdef SGMSE_B200_LAB   // first lean form and the round-1 mode-1 producers (bit-identical to the strip form above)
   } else if (P.fused && P.lean) {
     // =========================== activation producers, LEAN form of fused mode 1 ==============================
     // Same protocol, same loads, same fp32 arithmetic and rounding points as the mode-1 producers below (bit-identical), but
@@ -949,6 +954,7 @@ conv_tc6_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
       }
     }
+#endif
   }
 
   __syncwarp();
@@ -978,7 +984,11 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   // fused producers: 1 = LDG-fed, fp32 math (default: fastest in the interleaved A/B of round 1, profiles/r01_ab_forward.txt);
   // 2 = TMA-fed raw tile transformed in place, fp32 math (variant 9); 3 = in place, half2 math on the split-mean table
   // (variant 10)
+#ifdef SGMSE_B200_LAB
   P.fused = a.gn_ab ? ((g_tc_variant == 10 && a.gn_ab16) ? 3 : (g_tc_variant == 9 || g_tc_variant == 10) ? 2 : 1) : 0;
+#else
+  P.fused = a.gn_ab ? 1 : 0;                   // product library: LDG-fed strip producers only
+#endif
   const TensorDesc* cat = (a.gn_ab && a.gn_has_cat) ? &a.gn_cat : nullptr;
   CUtensorMap ma[MAX_SEG];
   int kb = 0;
@@ -1008,6 +1018,9 @@ void launch6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg) {
   P.stats = out.stats; P.slots = out.slots;
   P.desc_mode = 0;
   P.mma_style = g_tc6_mma_style; P.tma_poll = g_tc6_tma_poll; P.role_map = g_tc6_roles; P.lean = g_tc6_lean;
+#ifndef SGMSE_B200_LAB
+  if (P.lean != 3) P.lean = 2;                 // 2 = strip producers (fp32 math), 3 = the same with half2 math; the rest lives in the lab twin
+#endif
   P.dbg = dbg;
 #ifdef SGMSE_B200_LAB
   P.ablate = g_tc6_ablate;

@@ -1850,7 +1850,8 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "tc_variant") {
     // changes which intermediate buffers a forward needs: drop cached workspace sizes, graphs and shadow lanes
     // 2, 3, 5 = the superseded kernel generations conv_tc2 / conv_tc3 / conv_tc5: compiled into the lab twin only
-    SG_CHECK((value != 2 && value != 3 && value != 5) || sgmse::lab_compiled(),
+    // 9, 10 = the TMA-fed in-place producer forms of conv_tc6 (fused modes 2 / 3): lab twin only as well
+    SG_CHECK((value != 2 && value != 3 && value != 5 && value != 9 && value != 10) || sgmse::lab_compiled(),
              "tc_variant %lld selects a superseded kernel generation that exists in the lab twin library only "
              "(python -m sgmse_b200.build --pdl, SGMSE_B200_PDL=1)", value);
     e->opts.tc_variant = (int)value;
@@ -1863,7 +1864,12 @@ int sgmse_b200_set_option(sgmse_b200_engine* e, const char* key, long long value
   else if (k == "tc6_mma") { e->opts.tc6_mma = (int)value; clear_graphs(*e); }
   else if (k == "tc6_tma_poll") { e->opts.tc6_tma_poll = (int)value; clear_graphs(*e); }
   else if (k == "tc6_roles") { e->opts.tc6_roles = (int)value; clear_graphs(*e); }
-  else if (k == "tc6_lean") { e->opts.tc6_lean = (int)value; clear_graphs(*e); }
+  else if (k == "tc6_lean") {
+    SG_CHECK((value != 1 && value != 4) || sgmse::lab_compiled(),
+             "tc6_lean %lld selects a superseded producer form that exists in the lab twin library only", value);
+    e->opts.tc6_lean = (int)value;
+    clear_graphs(*e);
+  }
   else if (k == "fir_variant") { e->opts.fir_variant = (int)value; clear_graphs(*e); }
   else if (k == "inconv_variant") { e->opts.inconv_variant = (int)value; clear_graphs(*e); }
   else if (k == "combine_variant") { e->opts.combine_variant = (int)value; clear_graphs(*e); }

@@ -257,11 +257,14 @@ def test_kernel_selection_is_per_engine_and_the_product_library_has_no_lab_kerne
     from sgmse_b200 import Engine, EngineConfig
     a, b = Engine(EngineConfig(max_batch=1)), Engine(EngineConfig(max_batch=1))
     if a.counter("lab_compiled") == 0:
-        for v in (2, 3, 5):
+        for v in (2, 3, 5, 9, 10):
             with pytest.raises(RuntimeError, match="lab twin"):
                 a.set_option("tc_variant", v)
-        with pytest.raises(RuntimeError, match="lab twin"):
-            a.set_option("tc6_ablate", 1)
+        for key, v in (("tc6_ablate", 1), ("tc6_lean", 1), ("tc6_lean", 4)):
+            with pytest.raises(RuntimeError, match="lab twin"):
+                a.set_option(key, v)
+        a.set_option("tc6_lean", 3)            # the half2 form of the strip producers is product code
+        a.set_option("tc6_lean", 0)
     if a.counter("pdl_compiled") == 0:
         with pytest.raises(RuntimeError, match="SGMSE_B200_PDL"):
             a.set_option("pdl", 1)

@@ -329,7 +329,7 @@ def test_tc_kernel_variants_agree(full_sd):
     # 9: conv_tc6 fused with the TMA-fed raw tile transformed in place (fp32 math); 10: the same with half2 math on the
     # split-mean coefficient table; 0 = default = conv_tc6 fused with LDG-fed producers (fp32 math)
     lab = eng.counter("lab_compiled") == 1           # the superseded generations 2 / 3 / 5 exist in the lab twin only
-    variants = (1, 2, 3, 4, 5, 6, 9, 10, 0) if lab else (1, 4, 6, 9, 10, 0)
+    variants = (1, 2, 3, 4, 5, 6, 9, 10, 0) if lab else (1, 4, 6, 0)
     if not lab:
         with pytest.raises(RuntimeError, match="lab twin"):
             eng.set_option("tc_variant", 2)
@@ -341,10 +341,12 @@ def test_tc_kernel_variants_agree(full_sd):
     errs = {v: rel_l2(outs[v], outs[1]) for v in variants if v != 1}
     print("tc variants vs v1: " + ", ".join(f"v{v if v else '6-fused'} rel-L2 {e:.3e}" for v, e in errs.items()))
     assert all(e < 5e-3 for e in errs.values())
-    # the two fp32-math producers evaluate the same expression on the same values: bit-identical
-    assert torch.equal(outs[0], outs[9])
+    # the fp32-math producer forms evaluate the same expression on the same values: bit-identical
+    if lab:
+        assert torch.equal(outs[0], outs[9])
     # A/B switches of conv_tc6: ring depths, UMMA issue style, TMA issue loop -- all bit-identical to the default
-    for key, val in (("tc6_rings", 1), ("tc6_mma", 1), ("tc6_tma_poll", 1), ("tc6_roles", 1), ("tc6_lean", 1), ("tc6_lean", 4)):
+    switches = [("tc6_rings", 1), ("tc6_mma", 1), ("tc6_tma_poll", 1), ("tc6_roles", 1)] + ([("tc6_lean", 1), ("tc6_lean", 4)] if lab else [])
+    for key, val in switches:
         eng.set_option(key, val)
         assert torch.equal(eng.dnn_forward(x, t), outs[0]), key
         eng.set_option(key, 0)

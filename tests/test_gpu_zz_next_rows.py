@@ -192,7 +192,12 @@ def test_full_size_n30_against_the_reference_run(golden_dir):
         got = eng.enhance(wav.cuda(), noise=noise, N=N, predictor="reverse_diffusion", corrector="ald", corrector_steps=1,
                           snr=float(z["snr"]))[0].cpu().numpy()
         sdr, rel = o_pipe.si_sdr(ref, got), float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
-        print(f"full-size N=30 vs the reference's CPU run ({float(z['cpu_seconds']):.0f} s there): {mode} SI-SDR {sdr:.1f} dB, rel-L2 {rel:.2e}")
+        # the metric north_star names, in its own terms: SI-SDR of both outputs against a common third signal (the noisy input;
+        # there is no clean target for random-init weights) -- what a +-0.01 dB statement about enhancement quality is made of
+        tgt = wav[0].numpy()
+        d_metric = abs(o_pipe.si_sdr(tgt, got) - o_pipe.si_sdr(tgt, ref))
+        print(f"full-size N=30 vs the reference's CPU run ({float(z['cpu_seconds']):.0f} s there): {mode} SI-SDR {sdr:.1f} dB, rel-L2 {rel:.2e}; "
+              f"|SI-SDR(input, engine) - SI-SDR(input, reference)| = {d_metric:.4f} dB")
         assert np.isfinite(got).all() and sdr > min_sdr and rel < max_rel
         eng.close()
 
@@ -391,6 +396,10 @@ def test_round1_kernels_agree_with_the_defaults(full_sd, key, val, tol):
     half2 FIR-up of the default FIR kernel -> rel-L2 <= 2e-3 against the round-1 fp32 form (measured 8.3e-4); the tcgen05
     attention kernel against the mma.sync one <= 1e-3."""
     eng = Engine(EngineConfig(mode="fp16_tc", max_batch=2, use_graphs=False))
+    if key == "tc6_lean" and eng.counter("lab_compiled") == 0:
+        eng.close()
+        pytest.skip("the superseded conv_tc6 producer forms are compiled into the lab twin only (SGMSE_B200_PDL=1); "
+                    "verified bit-identical on a B200 in round 2 (profiles/r02_parity.txt)")
     eng.load_state_dict(full_sd)
     g = torch.Generator().manual_seed(3)
     x = (torch.complex(torch.randn(2, 2, 256, 128, generator=g), torch.randn(2, 2, 256, 128, generator=g)) * 0.3).cuda()
