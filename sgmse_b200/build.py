@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libsgmse_b200.so"
-SOURCES = ["gn.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc4.cu", "conv_tc6.cu", "small.cu", "attn.cu", "attn_umma.cu", "misc.cu", "ode.cu", "engine.cu"]
+SOURCES = ["gn.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc4.cu", "conv_tc6.cu", "small.cu", "attn.cu", "attn_umma.cu", "misc.cu", "pack.cu", "ode.cu", "engine.cu"]
 # superseded tcgen05 convolution generations (tc_variant 2 / 3 / 5): kept for the A/B record, compiled into the lab twin only
 LAB_SOURCES = ["conv_tc2.cu", "conv_tc3.cu", "conv_tc5.cu"]
 HEADERS = ["common.cuh", "kernels.h", "engine.h", "rk45.h", os.path.join("..", "..", "include", "sgmse_b200.h")]

@@ -348,6 +348,111 @@ void load_weights(Engine& e, const float* blob) {
   e.loaded = true;
 }
 
+// The same packed state as load_weights(), produced on the device from a blob that already lives there (pack.cu): no 262 MB
+// device -> host copy, no host loops, no re-upload.  Used by sgmse_b200_load_weights_device, i.e. by every refresh() of an
+// installed model (EMA swap at the start of a validation epoch).  Mirrors load_weights() statement by statement.
+void* dev_alloc(Engine& e, size_t bytes) {
+  void* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, bytes));
+  e.dev_allocs.push_back(d);
+  e.weights_bytes += bytes;
+  return d;
+}
+void pack_conv_dev(Engine& e, cudaStream_t st, const PackJob& job_in, ConvW& cw) {
+  PackJob j = job_in;
+  const bool f16 = e.cfg.mode != SGMSE_B200_MODE_FP32;
+  cw.ktot = j.ktot; cw.cout = j.cout;
+  const size_t n = (size_t)j.ktot * j.cout;
+  cw.w_direct = dev_alloc(e, n * (f16 ? 2 : 4));
+  __half* ht = nullptr;
+  j.ld = j.ktot;
+  if (e.cfg.mode == SGMSE_B200_MODE_FP16_TC && j.cout % 64 == 0 && j.ktot % 64 == 0) {
+    j.ld = j.ktot + (j.identity_tail ? j.cout : 0);
+    ht = (__half*)dev_alloc(e, (size_t)j.cout * j.ld * 2);
+    cw.w_tc = ht; cw.w_tc_ld = j.ld; cw.identity_tail = j.identity_tail != 0;
+  }
+  launch_pack_conv(st, e.blob_dev, j, cw.w_direct, f16, ht);
+}
+PackJob conv_job(std::initializer_list<PackSeg> segs, int cout, int mode, bool identity_tail) {
+  PackJob j{};
+  int kb = 0;
+  for (const PackSeg& sg : segs) {
+    j.seg[j.nseg] = sg;
+    j.seg[j.nseg].kbase = kb;
+    kb += sg.taps * sg.cin;
+    ++j.nseg;
+  }
+  j.cout = cout; j.ktot = kb; j.mode = mode; j.identity_tail = identity_tail ? 1 : 0;
+  return j;
+}
+
+void load_weights_device(Engine& e, const float* blob_src, cudaStream_t st) {
+  free_weights(e);
+  if (!e.range_flag) {
+    CUDA_OK(cudaMalloc((void**)&e.range_flag, sizeof(unsigned int)));
+    CUDA_OK(cudaMemset(e.range_flag, 0, sizeof(unsigned int)));
+  }
+  const sgmse_b200_config& c = e.cfg;
+  CUDA_OK(cudaMalloc(&e.blob_dev, (size_t)e.weights_numel * 4));
+  CUDA_OK(cudaMemcpyAsync(e.blob_dev, blob_src, (size_t)e.weights_numel * 4, cudaMemcpyDeviceToDevice, st));
+  e.weights_bytes += (size_t)e.weights_numel * 4;
+  const float* blob = e.blob_dev;
+  const int nf = c.nf, D = 4 * nf;
+  e.inconv_w_packed = (float*)dev_alloc(e, (size_t)36 * nf * 4);
+  launch_pack_inconv(st, blob + e.inconv_w, nf, e.inconv_w_packed);
+  e.dense_w_stacked = (float*)dev_alloc(e, (size_t)e.total_temb_c * D * 4);
+  e.dense_b_stacked = (float*)dev_alloc(e, (size_t)e.total_temb_c * 4);
+  std::vector<std::pair<Layer*, long long>> out_bias;          // host copies of the 4-channel output biases (kernel arguments)
+  for (Layer& l : e.layers) {
+    if (l.kind == LK_RES) {
+      pack_conv_dev(e, st, conv_job({{l.conv0_w, l.cin, 9, 0}}, l.cout, 0, false), l.c0);
+      if (l.shortcut) pack_conv_dev(e, st, conv_job({{l.conv1_w, l.cout, 9, 0}, {l.conv2_w, l.cin, 1, 0}}, l.cout, 0, false), l.c1);
+      else pack_conv_dev(e, st, conv_job({{l.conv1_w, l.cout, 9, 0}}, l.cout, 0, /*identity_tail=*/true), l.c1);
+      l.c1.bias = (float*)dev_alloc(e, (size_t)l.cout * 4);
+      launch_add_vec(st, blob + l.conv1_b, l.shortcut ? blob + l.conv2_b : nullptr, l.c1.bias, l.cout);
+      CUDA_OK(cudaMemcpyAsync(e.dense_w_stacked + (size_t)l.temb_off * D, blob + l.dense_w, (size_t)l.cout * D * 4, cudaMemcpyDeviceToDevice, st));
+      launch_add_vec(st, blob + l.dense_b, blob + l.conv0_b, e.dense_b_stacked + l.temb_off, l.cout);
+    } else if (l.kind == LK_ATTN) {
+      const int C = l.cin;
+      PackJob q{};
+      q.nseg = 3; q.cout = 3 * C; q.ktot = C; q.mode = 2; q.identity_tail = 0;
+      for (int jx = 0; jx < 3; ++jx) q.seg[jx] = PackSeg{l.nin_w[jx], C, 1, 0};
+      pack_conv_dev(e, st, q, l.c0);
+      l.c0.bias = (float*)dev_alloc(e, (size_t)3 * C * 4);
+      for (int jx = 0; jx < 3; ++jx)
+        CUDA_OK(cudaMemcpyAsync(l.c0.bias + jx * C, blob + l.nin_b[jx], (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+      pack_conv_dev(e, st, conv_job({{l.nin_w[3], C, 1, 0}}, C, 1, /*identity_tail=*/true), l.c1);
+      l.c1.bias = e.blob_dev + l.nin_b[3];
+    } else if (l.kind == LK_COMBINE) {
+      const int C = l.cout;
+      l.small_w = (float*)dev_alloc(e, (size_t)4 * C * 4);
+      launch_pack_combine(st, blob + l.conv0_w, C, l.small_w);
+      l.small_b = e.blob_dev + l.conv0_b;
+    } else {  // LK_OUTCONV
+      const int C = l.cin;
+      l.small_w = (float*)dev_alloc(e, (size_t)9 * C * 4 * 4);
+      l.small_wfrag = C % 16 == 0 ? (uint2*)dev_alloc(e, (size_t)9 * (C / 16) * 32 * sizeof(uint2)) : nullptr;
+      launch_pack_outconv(st, blob + l.conv0_w, C, l.small_w, l.small_wfrag);
+      out_bias.push_back({&l, l.conv0_b});
+    }
+  }
+  // the few scalars the launch sequence passes by value
+  for (auto& ob : out_bias) CUDA_OK(cudaMemcpyAsync(ob.first->out_bias_host, blob + ob.second, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  float ol[10];
+  CUDA_OK(cudaMemcpyAsync(ol, blob + e.outl_w, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(ol + 8, blob + e.outl_b, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  for (int o = 0; o < 2; ++o) {
+    for (int i = 0; i < 4; ++i) e.out_layer.w[o][i] = ol[o * 4 + i];
+    e.out_layer.b[o] = ol[8 + o];
+  }
+  e.out_layer.scale_after = c.backbone == SGMSE_B200_BACKBONE_NCSNPP_48K ? 1 : 0;
+  e.out_layer.scale_by_sigma = c.scale_by_sigma;
+  for (auto& g : e.graphs) cudaGraphExecDestroy(g.second.exec);
+  e.graphs.clear();
+  e.loaded = true;
+}
+
 TembWeights temb_weights(const Engine& e) {
   TembWeights w{};
   w.gfp_w = e.blob_dev + e.gfp_w;
@@ -1595,10 +1700,7 @@ int sgmse_b200_load_weights_device(sgmse_b200_engine* e, const float* blob_dev, 
   SG_CHECK(e && blob_dev, "null argument");
   activate(*e);
   SG_CHECK(numel == e->weights_numel, "weight blob has %lld floats, the network needs %lld", numel, e->weights_numel);
-  std::vector<float> host((size_t)numel);
-  CUDA_OK(cudaMemcpyAsync(host.data(), blob_dev, (size_t)numel * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-  load_weights(*e, host.data());
+  load_weights_device(*e, blob_dev, (cudaStream_t)stream);      // packed on the device (pack.cu): no host round trip
   API_END
 }
 

@@ -225,4 +225,13 @@ void launch_spec_back(cudaStream_t st, const float2* X /*[B][F][Tpad]*/, int B, 
 void launch_overlap_add(cudaStream_t st, const float* frames, const float* norm, int B, int Tpad, int n_fft, int hop,
                         int sqrt_window, int L, float* wav);
 
+// ---- device-side weight packing (pack.cu; engine.cu: load_weights_device) ----
+struct PackSeg { long long w; int cin, taps, kbase; };
+struct PackJob { PackSeg seg[4]; int nseg, cout, ktot, ld, mode, identity_tail; };
+void launch_pack_conv(cudaStream_t st, const float* blob, const PackJob& j, void* kd, bool kd_half, __half* ht);
+void launch_pack_inconv(cudaStream_t st, const float* w, int nf, float* out);
+void launch_pack_combine(cudaStream_t st, const float* w, int C, float* out);
+void launch_pack_outconv(cudaStream_t st, const float* w, int C, float* out, uint2* frag);
+void launch_add_vec(cudaStream_t st, const float* a, const float* b, float* out, int n);
+
 }  // namespace sgmse

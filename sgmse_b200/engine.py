@@ -232,9 +232,9 @@ class Engine:
             _lib.check(self.lib.sgmse_b200_load_weights(self._h, blob.data_ptr(), blob.numel()))
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], on_device: bool = False):
-        """``on_device``: flatten where the parameters live (one D2H copy of the flat blob instead of one per tensor; the
-        packing itself runs on the host -- sgmse_b200_load_weights_device; used when weights are refreshed between
-        training epochs)."""
+        """``on_device``: flatten where the parameters live; a CUDA blob is packed on the device
+        (sgmse_b200_load_weights_device, csrc/pack.cu: no host round trip -- the path of every ``refresh()`` between
+        training epochs), a host blob on the host (sgmse_b200_load_weights); both give bit-identical packed weights."""
         dev = next(iter(sd.values())).device if on_device else "cpu"
         self.load_blob(self.flatten_state_dict(sd, device=dev))
 

@@ -552,3 +552,37 @@ def test_kernel_options_are_per_engine(full_sd):
     assert torch.equal(sb, sb2) and not torch.equal(sa, sb)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("kind,mode", [("ncsnpp", "fp16_tc"), ("ncsnpp", "fp32"), ("ncsnpp_small", "fp16_direct"), ("v2", "fp16_tc")])
+def test_device_side_weight_packing_equals_the_host_path(full_sd, kind, mode):
+    """sgmse_b200_load_weights_device packs the state_dict blob where it lives (csrc/pack.cu) -- the path of refresh() after an
+    EMA swap and of every CUDA blob (bench.py) -- instead of copying 262 MB to the host and back: the packed weights, hence the
+    network outputs, must be bit-identical to the host packer's, for the tcgen05 layouts (K-major + identity tail, q|k|v
+    concatenation, mma.sync fragments of the 4-channel ends) as well as the CUDA-core ones."""
+    if kind == "ncsnpp":
+        cfg, sd, shape = EngineConfig(mode=mode, max_batch=1), full_sd, (1, 2, 256, 128)
+    elif kind == "v2":
+        pre = dict(loss_type="data_prediction", network_scaling="1/sigma", c_in="edm", c_out="edm", c_skip="edm", sigma_data=0.1)
+        cfg, sd, shape = EngineConfig.ncsnpp_v2(mode=mode, max_batch=1, sde="sbve", sb_k=2.6, sb_c=0.4, **pre), full_sd, (1, 2, 256, 128)
+    else:
+        ncfg = NetConfig.ncsnpp(attn_resolutions=(16,), **SMALL_N)
+        cfg, sd, shape = EngineConfig(attn_resolutions=(16,), mode=mode, **SMALL_E), o_w.make_state_dict(ncfg, seed=2), (2, 2, 64, 64)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.complex(torch.randn(*shape, generator=g), torch.randn(*shape, generator=g)) * 0.3).cuda()
+    t = torch.full((shape[0],), 0.37).cuda()
+    host, dev = Engine(cfg), Engine(cfg)
+    host.load_state_dict(sd)                                   # CPU tensors -> host packer
+    dev.load_state_dict({k: v.cuda() for k, v in sd.items()}, on_device=True)   # CUDA blob -> device packer
+    fwd = (lambda e: e.model_forward(x[:, :1], x[:, 1:], t)) if kind == "v2" else (lambda e: e.dnn_forward(x, t))
+    a, b = fwd(host), fwd(dev)
+    assert torch.isfinite(torch.view_as_real(a)).all() and torch.equal(a, b)
+    y = x[:, 1:2].contiguous()
+    if kind != "v2":
+        sa, _ = host.pc_sample(y, N=2, seed=11)
+        sb, _ = dev.pc_sample(y, N=2, seed=11)
+        assert torch.equal(sa, sb)
+        dev.load_state_dict({k: (v * 1.01).cuda() for k, v in sd.items()}, on_device=True)      # a refresh: new weights, new result
+        assert not torch.equal(fwd(dev), a)
+    host.close()
+    dev.close()
