@@ -168,7 +168,7 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 
 namespace {
-// ASYNC (attn_variant 2, round-2 candidate, not yet run on a GPU): Q/K/V tiles are staged with cp.async (zero-fill past the
+// ASYNC (attn_variant 2; gated on a B200 in round 2, bit-identical to the plain staging): Q/K/V tiles are staged with cp.async (zero-fill past the
 // last token).  The SASS of the plain load_tile loop is LDG.128 -> STS.128 -> branch, 16 (C = 128) / 32 (C = 256) serialized
 // round trips per tile and two tiles per key block: ~50 us of a 53 us launch whose 4.3 GFLOP need < 10.  Same bytes in
 // shared memory, same arithmetic: bit-identical.

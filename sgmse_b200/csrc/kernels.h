@@ -35,14 +35,14 @@ enum Resample { RS_NONE = 0, RS_DOWN = 1, RS_UP = 2 };
 void launch_gn_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float2* ab, bool silu,
                      Resample rs, TensorDesc& out0, TensorDesc* out1);
 
-// gn_self (round-2 candidate): GroupNorm finalize folded into the plain apply for tensors with H*W <= 512 (see gn.cu)
-extern thread_local int g_gnfin_variant;   // 1: gn_finalize with its partial loads batched eight at a time (round-2 candidate, bit-identical)
+// gn_self (round 2, on by default since): GroupNorm finalize folded into the plain apply for tensors with H*W <= 512 (see gn.cu)
+extern thread_local int g_gnfin_variant;   // 1: gn_finalize with its partial loads batched eight at a time (round 2, the default since; bit-identical)
 extern thread_local int g_gn_self;
 bool gn_self_applies(const TensorDesc& x0, const TensorDesc* x1);
 void launch_gn_norm_apply(cudaStream_t st, const TensorDesc& x0, const TensorDesc* x1, const float* gamma, const float* beta,
                           int groups, bool silu, TensorDesc& out, unsigned int* range_flag = nullptr);
 extern thread_local int g_fir_variant;   // 0: one-MUFU (tanh-form) silu + half2 FIR-down arithmetic in the tiled fp16 kernels; 1: expf silu, fp32 FIR
-                            // 2: 0 + phase-1 loads in flight at once + half2 quad FIR-up (round-2 candidate, see gn.cu)
+                            // 2: 0 + phase-1 loads in flight at once + half2 quad FIR-up (round 2, the default since; see gn.cu)
 
 // ---- convolutions ----
 struct ConvSeg {
@@ -97,7 +97,7 @@ bool conv_tc6_fuse_shape_ok(int H, int W, int c0, int c1, int cout, int nraw);
 void launch_conv_tc6(cudaStream_t st, const ConvArgs& a, TensorDesc& out, int* dbg_flag);
 extern thread_local int g_tc6_ablate;   // timing ablations of conv_tc6, compiled into the -DSGMSE_B200_PDL twin only (results are wrong on purpose)
 extern thread_local int g_tc6_rings, g_tc6_mma_style, g_tc6_tma_poll, g_tc6_roles, g_tc6_lean;   // conv_tc6 A/B switches, see conv_tc6.cu
-extern thread_local int g_tc1_narrow;   // 1: conv_tc v1 takes 64-wide channel tiles when 128-wide ones fill less than half the SMs (round-2 candidate)
+extern thread_local int g_tc1_narrow;   // 1: conv_tc v1 takes 64-wide channel tiles when 128-wide ones fill less than half the SMs (round 2, the default since)
 extern thread_local int g_tc_variant;   // 0 (= 7, 8): newest applicable kernels (v6 with fused GroupNorm+SiLU where possible: LDG-fed producers,
                            // fp32 math = fused mode 1; else v4/v1), 1: v1 only, 2: v2 (+v1), 3: v3 CTA pairs (+v2, v1),
                            // 4: v4 (+v1) without GroupNorm fusion, 5: v5 fused GN (+v4), 6: v6 without fusion (+v4),
@@ -122,9 +122,9 @@ void launch_out_conv(cudaStream_t st, const TensorDesc& act, const float* w, con
                      const float4* addend, float4* out, const float2* gn_ab = nullptr, const uint2* wfrag = nullptr);
 extern thread_local int g_outconv_variant;   // 0: mma.sync kernel for fp16 C in {128, 256}; 1: CUDA-core kernels; 2: mma.sync kernel with
                                 // GroupNorm+SiLU fused into its staging (measured slower than gn_apply + conv: profiles/)
-                                // 3: the mma.sync kernel with its tile staged by cp.async (round-2 candidate, see small.cu)
-extern thread_local int g_combine_variant;   // 0: thread per channel (2-byte accesses); 1: thread per 8-channel vector (round-2 candidate, bit-identical)
-extern thread_local int g_inconv_variant;    // 0: mma.sync input conv for fp16 C in {32, 64, 128}; 1: CUDA-core kernel; 2: 0 with prefetched A fragments (round-2 candidate)
+                                // 3: the mma.sync kernel with its tile staged by cp.async (round 2, the default since; see small.cu)
+extern thread_local int g_combine_variant;   // 0: thread per channel (2-byte accesses); 1: thread per 8-channel vector (round 2, the default since; bit-identical)
+extern thread_local int g_inconv_variant;    // 0: mma.sync input conv for fp16 C in {32, 64, 128}; 1: CUDA-core kernel; 2: 0 with prefetched A fragments (round 2, the default since)
 
 // ---- attention: qkv [N,H,W,3C] (q|k|v), out [N,H,W,C] = softmax(q k^T / sqrt(C)) v over H*W tokens
 void launch_attention(cudaStream_t st, const TensorDesc& qkv, TensorDesc& out);

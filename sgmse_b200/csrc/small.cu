@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) input_conv_kernel(const float4* __restric
 //   B fragments (k x channels) are built once per block in shared memory; the block then walks tiles of 128 pixels.
 //   Output goes through a per-warp padded smem tile so that global stores are 128-bit and row-contiguous.
 thread_local int g_inconv_variant = 0;   // 0: tensor-core kernel for fp16 output where it applies, 1: CUDA-core kernel,
-                            // 2 (round-2 candidate, not yet run on a GPU): 0 with the A fragments of the NEXT 16-pixel m-tile
+                            // 2 (round 2, the default since -- gated on a B200, bit-identical): 0 with the A fragments of the NEXT 16-pixel m-tile
                             //   loaded before the 48 MMAs of the current one (today every m-tile starts with an exposed
                             //   L1/L2 round trip at 16 warps per SM); same arithmetic, bit-identical
 
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(128) combine_kernel(const float4* __restrict__
   }
 }
 
-// combine_variant 1 (round-2 candidate, not yet run on a GPU): a thread owns 8 channels (one 128-bit vector) of one
+// combine_variant 1 (round 2, the default since -- gated on a B200, bit-identical): a thread owns 8 channels (one 128-bit vector) of one
 // 32-pixel tile and walks the tile's pixels in order -- the same per-channel expression and the same summation order as
 // the kernel above, so results and statistics are bit-identical -- with 8 vector loads in flight per thread instead of
 // four 2-byte ones (the scalar kernel keeps ~16 KB in flight per SM: 2.4 TB/s on the 268 MB of the top level).
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(256) out_conv_coop_kernel(const T* __restrict_
 // fp16 tensor-core variant (mma.sync m16n8k16, N = 8 with the 4 real outputs in columns 0..3): a block stages a
 // 16x16 pixel tile (+1 halo) of the activation in shared memory once, every warp computes two 16-pixel rows with
 // 9 taps x C/16 MMAs each.  ~15x fewer instructions than the CUDA-core kernels above; HBM/L2-bound.
-// ASYNC (outconv_variant 3, round-2 candidate, not yet run on a GPU): the 18x18-pixel tile is staged with cp.async
+// ASYNC (outconv_variant 3; round 2, the default since -- gated on a B200, bit-identical): the 18x18-pixel tile is staged with cp.async
 // (16 B each, zero-filled outside the image), i.e. all ~20 (C = 128) / ~40 (C = 256) loads of a thread are in flight at
 // once.  The SASS of the plain staging loop is LDG.128 -> STS.128 -> branch: one memory round trip per loop trip, which
 // is why the kernel sits at 2.1 TB/s (260 us for 545 MB).  Same bytes in shared memory, same arithmetic: bit-identical.

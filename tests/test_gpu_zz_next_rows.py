@@ -202,7 +202,7 @@ def test_full_size_n30_against_the_reference_run(golden_dir):
         eng.close()
 
 
-# ---- full size, product mode (not yet run on a GPU) ----
+# ---- full size, product mode ----
 def test_full_size_v2_sb_ode_on_the_product_path(full_sd):
     """SURVEY.md §8f-1 at full size in the product mode: 'ncsnpp_v2' (same 65.6 M-parameter layout) with EDM
     preconditioning -- c_in goes through the mma.sync input conv and the input pyramid, c_skip / c_out / 1/sigma through

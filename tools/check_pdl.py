@@ -1,4 +1,4 @@
-"""Round-2 A/B of programmatic dependent launch (PDL) -- written at the end of round 1, NOT yet run on a GPU.
+"""Round-2 A/B of programmatic dependent launch (PDL) -- written at the end of round 1; run in round 2: bit-identical, slower (profiles/r02_pdl_check.txt).
 
     python -m sgmse_b200.build --pdl                 # here (cross-compiles): sgmse_b200/lib/libsgmse_b200_pdl.so
     SGMSE_B200_PDL=1 python tools/check_pdl.py       # on the B200 box: correctness first, then timing

@@ -14,7 +14,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNEL_SOURCES = ["sgmse_b200/csrc/conv_tc6.cu", "sgmse_b200/csrc/common.cuh", "sgmse_b200/csrc/kernels.h"]
+KERNEL_SOURCES = ["sgmse_b200/csrc/conv_tc6.cu", "sgmse_b200/csrc/common.cuh"]    # the kernel and its device helpers (kernels.h holds declarations only)
 
 
 def source_digest():

@@ -1,4 +1,4 @@
-// Micro-benchmark of the XU (MUFU) pipe on B200 -- written at the end of round 1, NOT yet run.
+// Micro-benchmark of the XU (MUFU) pipe on B200 -- written at the end of round 1; run in round 2 (profiles/r02_mufu_bench.txt): 16 elements / clk / SM for every MUFU form.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/mufu_bench tools/mufu_bench.cu && /tmp/mufu_bench
 //
