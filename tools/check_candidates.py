@@ -1,13 +1,13 @@
-"""Round-2 gate for the kernel candidates written at the end of round 1 without GPU minutes (DESIGN.md §3 worklist, §9b).
+"""Gate between the round-2 default kernels (option value 0) and the round-1 kernels they replaced (which keep a number of their own).
 
     python tools/check_candidates.py            # on the B200 box
 
-For each option it evaluates the score network with the option off and on -- the reduced config of the golden fixtures
-and the full-size network at [2, 256, 128] and [2, 256, 512] -- and checks what the candidate promises:
-bit-identical output for `outconv_variant 3`, `inconv_variant 2`, `attn_variant 2`, `combine_variant 1`, `tc1_narrow 1`, `gn_self 1`
-(same arithmetic, different memory pipelining / tiling); rel-L2 <= 2e-3 for `fir_variant 2` (half2 FIR-up arithmetic).
-A candidate that passes goes into `tools/ab_forward.py` for timing and, if it pays, becomes the default together with a
-GPU test in tests/test_gpu_parity.py::test_small_end_kernel_variants_agree.
+For each option it evaluates the score network with the default and with the round-1 kernel -- the reduced config of the golden
+fixtures and the full-size network at [2, 256, 128] and [2, 256, 512] -- and checks the promise: bit-identical output for
+`outconv_variant`, `inconv_variant`, `combine_variant`, `tc1_narrow`, `gn_self`, `gnfin_variant`, `tc6_lean` (same arithmetic, different
+memory pipelining / tiling / thread mapping); rel-L2 <= 2e-3 for `fir_variant` (half2 FIR-up arithmetic) and for `attn_variant`
+(tcgen05 vs mma.sync).  First run in round 2 with the old numbering (profiles/r02_candidates_gate.txt); the same gate is
+tests/test_gpu_zz_next_rows.py::test_round1_kernels_agree_with_the_defaults.
 """
 import os
 import sys
