@@ -429,3 +429,39 @@ def test_two_rank_nccl_shard_invariance():
     print(r.stdout[-400:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "sharded == single-process on every rank: True" in r.stdout and "langevin refused when sharded: True" in r.stdout
+
+
+def test_directory_enhancer_on_the_gpu(tmp_path):
+    """sgmse_b200/files.py end to end on the device: WAV files of three lengths (one at another sampling rate) through reader threads ->
+    batched engine -> writer threads; every written file equals BatchedEnhancer's result for the same clips and noise ids, bit for bit
+    (float32 WAV), and the pipeline windows do not change a result."""
+    import numpy as np
+    from scipy.io import wavfile
+    from sgmse_b200 import BatchedEnhancer, DirectoryEnhancer
+    from sgmse_b200.files import default_resample, list_audio_files, read_audio
+    src, dst = tmp_path / "noisy", tmp_path / "out"
+    (src / "sub").mkdir(parents=True)
+    rng = np.random.default_rng(3)
+    for name, sr, n in (("a.wav", 16000, 4000), ("b.wav", 16000, 2000), (os.path.join("sub", "c.wav"), 8000, 1500), ("d.wav", 16000, 3900)):
+        wavfile.write(str(src / name), sr, (0.1 * rng.standard_normal(n)).astype(np.float32))
+    eng = Engine(EngineConfig(attn_resolutions=(16,), mode="fp16_tc", max_batch=2, nf=64, ch_mult=(1, 2, 2), image_size=64, num_res_blocks=1,
+                              n_fft=126, hop_length=32))
+    eng.load_state_dict(o_w.make_state_dict(NetConfig.ncsnpp(nf=64, ch_mult=(1, 2, 2), image_size=64, attn_resolutions=(16,), num_res_blocks=1), seed=5))
+    kw = dict(N=2, predictor="reverse_diffusion", corrector="ald", corrector_steps=1, snr=0.5)
+    outs, ids = DirectoryEnhancer(eng, window=2, io_workers=2)(str(src), str(dst), seed=7, **kw)
+    files = list_audio_files(str(src))
+    assert [os.path.relpath(o, str(dst)) for o in outs] == [os.path.relpath(f, str(src)) for f in files] and sorted(ids) == [0, 1, 2, 3]
+    # the same clips, window by window, through the batched service directly
+    clips = []
+    for f in files:
+        y, sr = read_audio(f)
+        clips.append((default_resample(y, sr, 16000) if sr != 16000 else y)[0])
+    want = []
+    for w0 in range(0, 4, 2):
+        o, _ = BatchedEnhancer(eng)(clips[w0:w0 + 2], seed=7, utt_base=w0, **kw)
+        want += o
+    for path, w, c in zip(outs, want, clips):
+        sr, x = wavfile.read(path)
+        assert sr == 16000 and x.dtype == np.float32 and x.shape[0] == c.numel() and np.isfinite(x).all()
+        assert np.array_equal(x, w.cpu().numpy())
+    eng.close()
